@@ -1,0 +1,120 @@
+/*
+ * rabi_b200 -- C ABI of the B200-native (sm_100a) backend for RABI's MAF hot path.
+ *
+ * The reference (mackelab/RABI, /root/reference) is pure Python and has NO FFI of its own: its seam is the
+ * hydra "module_path + class_name" plugin boundary (src/rbibm/rbibm/scripts/rbibm_script.py:597-636,753-764).
+ * This header is therefore the boundary a maintainer binds with ctypes; every entry point
+ * names the reference code whose arithmetic it replaces.  Paths below are relative to /root/reference/src.
+ *
+ * Conventions
+ *  - all tensors are fp32, row-major, contiguous; "_dev" pointers are device pointers owned by the caller
+ *    (normally torch allocations), "_host" pointers are host memory;
+ *  - the library owns only the packed weight image and a scratch workspace (grown on demand);
+ *  - every compute call takes the CUDA stream to launch on (cudaStream_t passed as void*; 0 = default stream);
+ *  - return value: 0 = ok, non-zero = error; rabi_last_error() gives the message.  No exceptions cross the ABI;
+ *  - a handle belongs to one device and is not thread-safe;
+ *  - sample-major layout: theta / z are [S, B, D] (sample, observation row, dimension); per-row results are [B];
+ *    "A" is the layer-0 context projection of all K transforms, [K, H0, B] (row index fastest).
+ */
+#ifndef RABI_B200_H
+#define RABI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rabi_maf rabi_maf_t;
+typedef void* rabi_stream_t; /* cudaStream_t */
+
+#define RABI_MAX_HIDDEN_LAYERS 4
+#define RABI_MAX_TRANSFORMS 8
+
+/* Library / build information ("sm_100a", version).  Never NULL. */
+const char* rabi_build_info(void);
+
+/* Message of the last failed call on this handle (h may be NULL: last create failure). */
+const char* rabi_last_error(const rabi_maf_t* h);
+
+/* ---- construction: replaces InverseAffineAutoregressiveModel.__init__ -> PyroFlowModel.__init__ building K
+ * ConditionalAutoRegressiveNN(D, C, hidden) (rbi/rbi/models/flows.py:72-113, models/base.py:277-343,
+ * models/transforms.py:92-98).  log_scale_{min,max}: AffineAutoregressive clamp (config/model/maf_pyro.yaml:6-7). */
+int rabi_maf_create(rabi_maf_t** out, int device, int K, int D, int C, int n_hidden, const int* hidden,
+                    float log_scale_min, float log_scale_max);
+int rabi_maf_destroy(rabi_maf_t* h);
+
+/* MADE structure of transform k: the `permutation` buffer (int64[D]) and the `mask` buffer of MaskedLinear
+ * layer `layer` (0..n_hidden; fp32 [out, in], in = C + D for layer 0, out = 2*D for the last layer), exactly as
+ * they sit in the reference state_dict (t{k}.nn.permutation, t{k}.nn.layers.{layer}.mask).  Host pointers. */
+int rabi_maf_set_permutation(rabi_maf_t* h, int k, const int64_t* perm_host);
+int rabi_maf_set_mask(rabi_maf_t* h, int k, int layer, const float* mask_host, int out_features, int in_features);
+/* Optional Permute layer applied after transform k (shuffle=True: buffers permute{k}, models/base.py:326-333;
+ * pyro Permute: y[i] = x[perm[i]]).  NULL removes it.  Folded into the kernels' gather/scatter indices. */
+int rabi_maf_set_post_permutation(rabi_maf_t* h, int k, const int64_t* perm_host);
+/* Validates that every mask is the MADE prefix structure Pyro's create_mask produces, builds the packed image
+ * layout and uploads the index tables.  Must be called once after all permutations/masks are set. */
+int rabi_maf_finalize_structure(rabi_maf_t* h);
+
+/* Parameters of MaskedLinear layer `layer` of transform k (t{k}.nn.layers.{layer}.{weight,bias}): RAW (unmasked)
+ * weights [out, in] and bias [out] as DEVICE pointers; the mask multiply of MaskedLinear.forward
+ * (F.linear(x, W*mask, b)) and the re-layout are done once here instead of on every call. */
+int rabi_maf_set_weights(rabi_maf_t* h, int k, int layer, const float* W_dev, const float* b_dev, rabi_stream_t s);
+
+/* Layer-0 context projection for all K transforms: A[k, u, b] = b0_k[u] + sum_c W0_k[u, c] * ctx[b, c], with
+ * ctx = (x - zs_mean) / zs_std when zs_* are non-NULL (ZScoreLayer, rbi/rbi/models/module.py:109-122), else ctx = x.
+ * This is the part of ConditionalAutoRegressiveNN.forward that depends only on the observation row. */
+int rabi_maf_ctx_project(rabi_maf_t* h, const float* x_dev, const float* zs_mean_dev, const float* zs_std_dev,
+                         int B, float* A_dev, rabi_stream_t s);
+/* Transposed projection (input gradient): g_x[b, c] (+)= (1/zs_std[c]) * sum_{k,u} W0_k[u, c] * gA[k, u, b]. */
+int rabi_maf_ctx_project_bwd(rabi_maf_t* h, const float* gA_dev, const float* zs_std_dev, int B, float* gx_dev,
+                             rabi_stream_t s);
+
+/* q.log_prob(theta): K MADE passes (TransformedDistribution.log_prob over AffineAutoregressive._call,
+ * models/base.py:417-446 + pyro AffineAutoregressive).  theta [S,B,D] -> logp [S,B]. */
+int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const float* theta_dev, int S, int B, float* logp_dev,
+                          rabi_stream_t s);
+/* q.rsample from given base noise z [S,B,D] (AffineAutoregressive._inverse, one pass-equivalent instead of D
+ * passes); logq_dev (optional) receives log q(theta) of the drawn samples (the "free" cache-hit log_prob, Q9). */
+int rabi_maf_rsample_fwd(rabi_maf_t* h, const float* A_dev, const float* z_dev, int S, int B, float* theta_dev,
+                         float* logq_dev, rabi_stream_t s);
+
+/* MC reverse KL per row, no gradient: kl[b] = mean_s[log p(th_s) - log q(th_s)], th_s ~ p via z
+ * (general_kl_divergence, rbi/rbi/loss/kl_div.py:38-56; ReverseKLLoss, loss/eval_loss.py:129-150).
+ * A_p: projection of the distribution sampled from (first KL argument), A_q: of the second. */
+int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_q_dev, const float* z_dev, int S, int B,
+                 float* kl_dev, rabi_stream_t s);
+
+/* One L2-PGD iteration on the reverse-KL attack loss, identity(+z-score) embedding (dx == C):
+ *   loss = inv_B * sum_b KL(q(.|x+delta) || q(.|x));  g = d loss / d delta;
+ *   g /= max(||g||_2, norm_floor);  delta += eps_iter*g;  delta = clamp(x+delta, clip_min, clip_max) - x;
+ *   delta *= min(1, eps/||delta||_2)
+ * (advertorch perturb_iterative ord=2 as driven by rbi/rbi/attacks/advertorch_attack.py:100-114 with
+ * loss_fn = ReverseKLLoss(reduction="mean")).  A_q = rabi_maf_ctx_project of the clean x (iteration invariant).
+ * kl_dev (optional, [B]) receives the per-row KL estimate of this iteration. */
+int rabi_rkl_pgd_step(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* zs_mean_dev,
+                      const float* zs_std_dev, const float* A_q_dev, const float* z_dev, int S, int B, float eps,
+                      float eps_iter, float clip_min, float clip_max, float inv_B, float norm_floor, float* kl_dev,
+                      rabi_stream_t s);
+/* Gradient only: gx[b, :] = d/dx~ [ inv_B * KL(q(.|x~_b) || q_target_b) ] for x~ = x_dev (what ``loss.backward()`` leaves
+ * in ``delta.grad`` inside perturb_iterative); kl_dev (optional) the per-row KL. */
+int rabi_rkl_input_grad(rabi_maf_t* h, const float* x_dev, const float* zs_mean_dev, const float* zs_std_dev,
+                        const float* A_q_dev, const float* z_dev, int S, int B, float inv_B, float* gx_dev,
+                        float* kl_dev, rabi_stream_t s);
+
+/* nb_iter PGD iterations (z_all_dev: [nb_iter, S, B, D]) followed by x_adv = clamp(x + delta, clip_min, clip_max).
+ * A_q_dev: projection of the attack target; NULL = untargeted, i.e. the projection of the clean x (computed here).
+ * A negative inv_B descends on the loss (targeted attack, perturb_iterative(minimize=True)). */
+int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* zs_mean_dev,
+                     const float* zs_std_dev, const float* A_q_dev, const float* z_all_dev, int nb_iter, int S, int B, float eps,
+                     float eps_iter, float clip_min, float clip_max, float inv_B, float norm_floor,
+                     float* x_adv_dev, rabi_stream_t s);
+
+/* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
+unsigned long long rabi_launch_count(const rabi_maf_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RABI_B200_H */

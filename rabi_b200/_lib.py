@@ -1,0 +1,109 @@
+"""ctypes binding of ``librabi_b200.so`` (C ABI declared in include/rabi_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, an exception is raised.
+``build()`` compiles the library in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "librabi_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+SOURCES = ["rabi_maf.cu"]
+
+EXPORTS = [
+    "rabi_build_info", "rabi_last_error", "rabi_maf_create", "rabi_maf_destroy", "rabi_maf_set_permutation",
+    "rabi_maf_set_mask", "rabi_maf_set_post_permutation", "rabi_maf_finalize_structure", "rabi_maf_set_weights", "rabi_maf_ctx_project",
+    "rabi_maf_ctx_project_bwd", "rabi_maf_log_prob_fwd", "rabi_maf_rsample_fwd", "rabi_rkl_fwd",
+    "rabi_rkl_input_grad", "rabi_rkl_pgd_step", "rabi_rkl_pgd_run", "rabi_launch_count",
+]
+
+
+class RabiError(RuntimeError):
+    pass
+
+
+def _sources():
+    out = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "rabi_b200.h")]
+    return out, deps
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu -> _lib/librabi_b200.so (sm_100a).  Rebuilds when a source is newer than the .so."""
+    srcs, deps = _sources()
+    if not force and os.path.exists(LIB_PATH):
+        so_m = os.path.getmtime(LIB_PATH)
+        if all(os.path.getmtime(d) <= so_m for d in deps):
+            return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, *srcs]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RabiError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RabiError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(rabi_b200 has no CPU / PyTorch fallback)."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    fp = POINTER(c_float)
+    vp = c_void_p
+    L.rabi_build_info.restype = c_char_p
+    L.rabi_build_info.argtypes = []
+    L.rabi_last_error.restype = c_char_p
+    L.rabi_last_error.argtypes = [vp]
+    L.rabi_launch_count.restype = c_ulonglong
+    L.rabi_launch_count.argtypes = [vp]
+    L.rabi_maf_create.argtypes = [POINTER(vp), c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_float, c_float]
+    L.rabi_maf_destroy.argtypes = [vp]
+    L.rabi_maf_set_permutation.argtypes = [vp, c_int, POINTER(c_int64)]
+    L.rabi_maf_set_post_permutation.argtypes = [vp, c_int, POINTER(c_int64)]
+    L.rabi_maf_set_mask.argtypes = [vp, c_int, c_int, fp, c_int, c_int]
+    L.rabi_maf_finalize_structure.argtypes = [vp]
+    L.rabi_maf_set_weights.argtypes = [vp, c_int, c_int, vp, vp, vp]
+    L.rabi_maf_ctx_project.argtypes = [vp, vp, vp, vp, c_int, vp, vp]
+    L.rabi_maf_ctx_project_bwd.argtypes = [vp, vp, vp, c_int, vp, vp]
+    L.rabi_maf_log_prob_fwd.argtypes = [vp, vp, vp, c_int, c_int, vp, vp]
+    L.rabi_maf_rsample_fwd.argtypes = [vp, vp, vp, c_int, c_int, vp, vp, vp]
+    L.rabi_rkl_fwd.argtypes = [vp, vp, vp, vp, c_int, c_int, vp, vp]
+    L.rabi_rkl_input_grad.argtypes = [vp, vp, vp, vp, vp, vp, c_int, c_int, c_float, vp, vp, vp]
+    L.rabi_rkl_pgd_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_float, c_float, c_float, c_float,
+                                    c_float, c_float, vp, vp]
+    L.rabi_rkl_pgd_run.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
+                                   c_float, c_float, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if fn.restype is c_int or name.startswith(("rabi_maf_", "rabi_rkl_")):
+            fn.restype = c_int
+    _lib = L
+    return L

@@ -1,0 +1,756 @@
+// rabi_b200: C-ABI library (include/rabi_b200.h) -- host side + launchers.  sm_100a only.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/rabi_b200.h"
+#include "maf_image.h"
+#include "maf_pairs.cuh"
+
+using namespace rabi;
+
+static std::string g_create_error;
+
+struct rabi_maf {
+    int device = 0;
+    int K = 0, D = 0, C = 0, L = 0;
+    int H[RABI_MAXL] = {0, 0, 0, 0};
+    float lo = -5.f, hi = 3.f;
+    bool finalized = false;
+    std::vector<std::vector<int64_t>> perm;               // [K][D]
+    std::vector<std::vector<int64_t>> post;               // [K][D] optional Permute layer after transform k
+    std::vector<std::vector<std::vector<float>>> masks;   // [K][L+1][out*in]
+    MafImg img;                                           // device pointers inside
+    std::vector<int> meta_host;
+    float* f_dev = nullptr;
+    int* m_dev = nullptr;
+    size_t n_float = 0, n_int = 0;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    unsigned long long launches = 0;
+    std::string err;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+};
+
+static int fail(rabi_maf* h, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h)
+        h->err = buf;
+    else
+        g_create_error = buf;
+    return 1;
+}
+
+#define CU_OK(h, expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) return fail(h, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" const char* rabi_build_info(void) { return "rabi_b200 0.1 (sm_100a, CUDA " __DATE__ ")"; }
+extern "C" const char* rabi_last_error(const rabi_maf_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" unsigned long long rabi_launch_count(const rabi_maf_t* h) { return h ? h->launches : 0ull; }
+
+extern "C" int rabi_maf_create(rabi_maf_t** out, int device, int K, int D, int C, int n_hidden, const int* hidden,
+                               float log_scale_min, float log_scale_max) {
+    if (!out) return fail(nullptr, "out is NULL");
+    *out = nullptr;
+    if (K < 1 || K > RABI_MAXK) return fail(nullptr, "num_transforms must be in [1,%d], got %d", RABI_MAXK, K);
+    if (n_hidden < 1 || n_hidden > RABI_MAXL)
+        return fail(nullptr, "number of hidden layers must be in [1,%d], got %d", RABI_MAXL, n_hidden);
+    if (D < 1 || C < 1) return fail(nullptr, "D and C must be positive (C == 0: unconditional MADE is not on the path)");
+    for (int l = 0; l < n_hidden; ++l)
+        if (hidden[l] < D)  // pyro/nn/auto_reg_nn.py: "Hidden dimension must not be less than input dimension."
+            return fail(nullptr, "Hidden dimension must not be less than input dimension.");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, "no CUDA device available (rabi_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, "invalid device %d", device);
+    rabi_maf* h = new rabi_maf();
+    h->device = device;
+    h->K = K;
+    h->D = D;
+    h->C = C;
+    h->L = n_hidden;
+    for (int l = 0; l < n_hidden; ++l) h->H[l] = hidden[l];
+    h->lo = log_scale_min;
+    h->hi = log_scale_max;
+    h->perm.assign(K, std::vector<int64_t>());
+    h->post.assign(K, std::vector<int64_t>());
+    h->masks.assign(K, std::vector<std::vector<float>>(n_hidden + 1));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, "cudaGetDeviceProperties failed");
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = h;
+    return 0;
+}
+
+extern "C" int rabi_maf_destroy(rabi_maf_t* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->f_dev) cudaFree(h->f_dev);
+    if (h->m_dev) cudaFree(h->m_dev);
+    if (h->ws) cudaFree(h->ws);
+    delete h;
+    return 0;
+}
+
+static int layer_out(const rabi_maf* h, int layer) { return layer < h->L ? h->H[layer] : 2 * h->D; }
+static int layer_in(const rabi_maf* h, int layer) { return layer == 0 ? h->C + h->D : h->H[layer - 1]; }
+
+extern "C" int rabi_maf_set_permutation(rabi_maf_t* h, int k, const int64_t* perm_host) {
+    if (!h) return 1;
+    if (k < 0 || k >= h->K) return fail(h, "transform index %d out of range", k);
+    std::vector<char> seen(h->D, 0);
+    for (int j = 0; j < h->D; ++j) {
+        int64_t v = perm_host[j];
+        if (v < 0 || v >= h->D || seen[v]) return fail(h, "permutation of transform %d is not a permutation of 0..D-1", k);
+        seen[v] = 1;
+    }
+    h->perm[k].assign(perm_host, perm_host + h->D);
+    h->finalized = false;
+    return 0;
+}
+
+extern "C" int rabi_maf_set_post_permutation(rabi_maf_t* h, int k, const int64_t* perm_host) {
+    if (!h) return 1;
+    if (k < 0 || k >= h->K) return fail(h, "transform index %d out of range", k);
+    if (!perm_host) {
+        h->post[k].clear();
+        h->finalized = false;
+        return 0;
+    }
+    std::vector<char> seen(h->D, 0);
+    for (int j = 0; j < h->D; ++j) {
+        int64_t v = perm_host[j];
+        if (v < 0 || v >= h->D || seen[v]) return fail(h, "permute%d is not a permutation of 0..D-1", k);
+        seen[v] = 1;
+    }
+    h->post[k].assign(perm_host, perm_host + h->D);
+    h->finalized = false;
+    return 0;
+}
+
+extern "C" int rabi_maf_set_mask(rabi_maf_t* h, int k, int layer, const float* mask_host, int out_features,
+                                 int in_features) {
+    if (!h) return 1;
+    if (k < 0 || k >= h->K) return fail(h, "transform index %d out of range", k);
+    if (layer < 0 || layer > h->L) return fail(h, "layer index %d out of range", layer);
+    if (out_features != layer_out(h, layer) || in_features != layer_in(h, layer))
+        return fail(h, "mask of t%d.layers.%d has shape [%d,%d], expected [%d,%d]", k, layer, out_features, in_features,
+                    layer_out(h, layer), layer_in(h, layer));
+    h->masks[k][layer].assign(mask_host, mask_host + (size_t)out_features * in_features);
+    h->finalized = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int rabi_maf_finalize_structure(rabi_maf_t* h) {
+    if (!h) return 1;
+    const int K = h->K, D = h->D, C = h->C, L = h->L;
+    CU_OK(h, cudaSetDevice(h->device));
+    MafImg& g = h->img;
+    memset(&g, 0, sizeof(g));
+    g.K = K;
+    g.D = D;
+    g.C = C;
+    g.L = L;
+    g.lo = h->lo;
+    g.hi = h->hi;
+    g.Hmax = 0;
+    for (int l = 0; l < L; ++l) {
+        g.H[l] = h->H[l];
+        g.Hmax = std::max(g.Hmax, h->H[l]);
+    }
+    size_t nf = 0;
+    std::vector<int>& meta = h->meta_host;
+    meta.clear();
+    auto falloc = [&](size_t n) {
+        size_t o = nf;
+        nf += (n + 3) & ~(size_t)3;
+        return (int)o;
+    };
+    auto ialloc = [&](size_t n) {
+        size_t o = meta.size();
+        meta.resize(o + n, 0);
+        return (int)o;
+    };
+    const int H0 = h->H[0], H0p = round4(H0);
+    g.H0p = H0p;
+    g.ldKH = K * H0p;
+    g.W0cT = falloc((size_t)C * g.ldKH);
+    for (int k = 0; k < K; ++k) {
+        if ((int)h->perm[k].size() != D) return fail(h, "permutation of transform %d was not set", k);
+        for (int l = 0; l <= L; ++l)
+            if (h->masks[k][l].empty()) return fail(h, "mask of t%d.layers.%d was not set", k, l);
+        TImg& t = g.t[k];
+        const std::vector<int64_t>& perm = h->perm[k];
+        t.ldc = round4(C);
+        t.W0c = falloc((size_t)(H0p + 4) * t.ldc);
+        t.ldt = round4(D);
+        t.W0t = falloc((size_t)(H0p + 4) * t.ldt);
+        t.b0 = falloc(H0p + 4);
+        for (int l = 1; l < L; ++l) {
+            t.ld[l] = round4(h->H[l - 1]);
+            t.W[l] = falloc((size_t)(round4(h->H[l]) + 4) * t.ld[l]);
+            t.b[l] = falloc(round4(h->H[l]) + 4);
+        }
+        t.ldo = round4(h->H[L - 1]);
+        t.Wo = falloc((size_t)(round4(2 * D) + 4) * t.ldo);
+        t.bo = falloc(round4(2 * D) + 4);
+
+        t.perm = ialloc(D);
+        for (int j = 0; j < D; ++j) meta[t.perm + j] = (int)perm[j];
+        t.permy = ialloc(D);
+        if (h->post[k].empty()) {
+            for (int j = 0; j < D; ++j) meta[t.permy + j] = (int)perm[j];
+        } else {  // Permute: y[i] = x[post[i]]  ->  variable perm[j] lands at i with post[i] == perm[j]
+            std::vector<int> inv(D);
+            for (int i = 0; i < D; ++i) inv[h->post[k][i]] = i;
+            for (int j = 0; j < D; ++j) meta[t.permy + j] = inv[perm[j]];
+        }
+        // ---- layer 0: context columns must be fully connected; theta columns a prefix in order space
+        t.deg0 = ialloc(H0);
+        {
+            const std::vector<float>& m = h->masks[k][0];
+            const int in = C + D;
+            for (int u = 0; u < H0; ++u) {
+                for (int c = 0; c < C; ++c)
+                    if (m[(size_t)u * in + c] != 1.f)
+                        return fail(h, "t%d.layers.0.mask: context column %d of unit %d is masked; not a Pyro MADE mask", k, c, u);
+                int dg = 0;
+                for (int j = 0; j < D; ++j) dg += m[(size_t)u * in + C + perm[j]] != 0.f;
+                for (int j = 0; j < D; ++j)
+                    if ((m[(size_t)u * in + C + perm[j]] != 0.f) != (j < dg))
+                        return fail(h, "t%d.layers.0.mask: row %d is not a prefix in permutation order", k, u);
+                meta[t.deg0 + u] = dg;
+                if (u > 0 && dg < meta[t.deg0 + u - 1])
+                    return fail(h, "t%d.layers.0.mask: unit degrees are not non-decreasing", k);
+            }
+        }
+        // groups of layer 0
+        std::vector<std::vector<int>> deg(L);
+        deg[0].assign(meta.begin() + t.deg0, meta.begin() + t.deg0 + H0);
+        auto build_groups = [&](int l) -> int {
+            int off = ialloc(D + 1);
+            const std::vector<int>& d = deg[l];
+            int n = (int)d.size();
+            int u = 0;
+            for (int j = 0; j <= D; ++j) {
+                while (u < n && d[u] < j) ++u;
+                meta[off + j] = u;
+            }
+            meta[off + D] = n;
+            return off;
+        };
+        for (int u = 0; u < H0; ++u)
+            if (deg[0][u] < 0 || deg[0][u] > D - 1)
+                return fail(h, "t%d.layers.0.mask: unit %d sees all %d variables (degree out of range)", k, u, D);
+        t.grp[0] = build_groups(0);
+        // ---- hidden layers
+        for (int l = 1; l < L; ++l) {
+            const int Hl = h->H[l], Hin = h->H[l - 1];
+            const std::vector<float>& m = h->masks[k][l];
+            t.pre[l] = ialloc(Hl);
+            deg[l].assign(Hl, 0);
+            for (int v = 0; v < Hl; ++v) {
+                int e = 0;
+                for (int u = 0; u < Hin; ++u) e += m[(size_t)v * Hin + u] != 0.f;
+                for (int u = 0; u < Hin; ++u)
+                    if ((m[(size_t)v * Hin + u] != 0.f) != (u < e))
+                        return fail(h, "t%d.layers.%d.mask: row %d is not a prefix", k, l, v);
+                meta[t.pre[l] + v] = e;
+                // degree: the j with grp_{l-1}[j+1] == e
+                int dj = -1;
+                for (int j = 0; j < D; ++j)
+                    if (meta[t.grp[l - 1] + j + 1] == e) {
+                        dj = j;
+                        break;
+                    }
+                if (dj < 0) return fail(h, "t%d.layers.%d.mask: row %d does not match a MADE degree", k, l, v);
+                deg[l][v] = dj;
+                if (v > 0 && dj < deg[l][v - 1]) return fail(h, "t%d.layers.%d.mask: degrees not non-decreasing", k, l);
+            }
+            t.grp[l] = build_groups(l);
+            t.first[l] = ialloc(round4(Hin) + 4);
+            for (int u = 0; u < round4(Hin) + 4; ++u) {
+                int v = 0;
+                while (v < Hl && meta[t.pre[l] + v] <= u) ++v;
+                meta[t.first[l] + u] = v;
+            }
+        }
+        // ---- output layer (rows perm[j] and D + perm[j])
+        {
+            const int HL = h->H[L - 1];
+            const std::vector<float>& m = h->masks[k][L];
+            t.preo = ialloc(D);
+            for (int j = 0; j < D; ++j) {
+                int e = meta[t.grp[L - 1] + j + 1];
+                for (int half = 0; half < 2; ++half) {
+                    size_t row = (size_t)(half * D + perm[j]);
+                    for (int v = 0; v < HL; ++v)
+                        if ((m[row * HL + v] != 0.f) != (v < e))
+                            return fail(h, "t%d.layers.%d.mask: output row %d is not the MADE prefix", k, L, (int)row);
+                }
+                meta[t.preo + j] = e;
+            }
+            t.firsto = ialloc(round4(HL) + 4);
+            for (int v = 0; v < round4(HL) + 4; ++v) {
+                int j = 0;
+                while (j < D && meta[t.preo + j] <= v) ++j;
+                meta[t.firsto + v] = j;
+            }
+            t.first0 = ialloc(D);
+            for (int j = 0; j < D; ++j) {
+                int u = 0;
+                while (u < H0 && meta[t.deg0 + u] <= j) ++u;
+                meta[t.first0 + j] = u;
+            }
+        }
+    }
+    if (h->f_dev) cudaFree(h->f_dev);
+    if (h->m_dev) cudaFree(h->m_dev);
+    h->n_float = nf;
+    h->n_int = meta.size();
+    CU_OK(h, cudaMalloc(&h->f_dev, nf * sizeof(float)));
+    CU_OK(h, cudaMemset(h->f_dev, 0, nf * sizeof(float)));
+    CU_OK(h, cudaMalloc(&h->m_dev, meta.size() * sizeof(int)));
+    CU_OK(h, cudaMemcpy(h->m_dev, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice));
+    g.f = h->f_dev;
+    g.m = h->m_dev;
+    h->finalized = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pack kernels: raw torch parameters -> masked, order-space image
+__global__ void k_pack_layer0(MafImg g, int k, const float* __restrict__ W, const float* __restrict__ b, float* f) {
+    const TImg t = g.t[k];
+    const int H0 = g.H[0], C = g.C, D = g.D, in = C + D;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H0 * in) return;
+    int u = idx / in, c = idx % in;
+    if (c < C) {
+        float w = W[(size_t)u * in + c];
+        f[t.W0c + (size_t)u * t.ldc + c] = w;
+        f[g.W0cT + (size_t)c * g.ldKH + k * g.H0p + u] = w;
+        if (c == 0) f[t.b0 + u] = b[u];
+    } else {
+        int j = c - C;
+        int dg = g.m[t.deg0 + u];
+        f[t.W0t + (size_t)u * t.ldt + j] = (j < dg) ? W[(size_t)u * in + C + g.m[t.perm + j]] : 0.f;
+    }
+}
+__global__ void k_pack_hidden(MafImg g, int k, int l, const float* __restrict__ W, const float* __restrict__ b, float* f) {
+    const TImg t = g.t[k];
+    const int Hl = g.H[l], Hin = g.H[l - 1];
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Hl * Hin) return;
+    int v = idx / Hin, u = idx % Hin;
+    f[t.W[l] + (size_t)v * t.ld[l] + u] = (u < g.m[t.pre[l] + v]) ? W[(size_t)v * Hin + u] : 0.f;
+    if (u == 0) f[t.b[l] + v] = b[v];
+}
+__global__ void k_pack_out(MafImg g, int k, const float* __restrict__ W, const float* __restrict__ b, float* f) {
+    const TImg t = g.t[k];
+    const int D = g.D, HL = g.H[g.L - 1];
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2 * D * HL) return;
+    int r = idx / HL, v = idx % HL;
+    int half = r / D, j = r % D;
+    int src = half * D + g.m[t.perm + j];
+    f[t.Wo + (size_t)r * t.ldo + v] = (v < g.m[t.preo + j]) ? W[(size_t)src * HL + v] : 0.f;
+    if (v == 0) f[t.bo + r] = b[src];
+}
+
+#define REQUIRE_READY(h)                                                               \
+    do {                                                                               \
+        if (!(h)) return 1;                                                            \
+        if (!(h)->finalized) return fail(h, "rabi_maf_finalize_structure was not called"); \
+        CU_OK(h, cudaSetDevice((h)->device));                                          \
+    } while (0)
+
+#define LAUNCH_CHECK(h)                                                        \
+    do {                                                                       \
+        (h)->launches++;                                                       \
+        cudaError_t _e = cudaGetLastError();                                   \
+        if (_e != cudaSuccess) return fail(h, "kernel launch failed: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" int rabi_maf_set_weights(rabi_maf_t* h, int k, int layer, const float* W_dev, const float* b_dev,
+                                    rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (k < 0 || k >= h->K) return fail(h, "transform index %d out of range", k);
+    if (layer < 0 || layer > h->L) return fail(h, "layer index %d out of range", layer);
+    cudaStream_t st = (cudaStream_t)s;
+    int n = layer_out(h, layer) * layer_in(h, layer);
+    int nb = (n + 255) / 256;
+    if (layer == 0)
+        k_pack_layer0<<<nb, 256, 0, st>>>(h->img, k, W_dev, b_dev, h->f_dev);
+    else if (layer < h->L)
+        k_pack_hidden<<<nb, 256, 0, st>>>(h->img, k, layer, W_dev, b_dev, h->f_dev);
+    else
+        k_pack_out<<<nb, 256, 0, st>>>(h->img, k, W_dev, b_dev, h->f_dev);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+static int ensure_ws(rabi_maf* h, size_t bytes) {
+    if (bytes <= h->ws_bytes) return 0;
+    // grow geometrically; synchronises (rare: only when a larger batch than ever before is seen)
+    size_t nb = std::max(bytes, h->ws_bytes * 2);
+    if (h->ws) {
+        CU_OK(h, cudaDeviceSynchronize());
+        CU_OK(h, cudaFree(h->ws));
+        h->ws = nullptr;
+        h->ws_bytes = 0;
+    }
+    CU_OK(h, cudaMalloc(&h->ws, nb));
+    h->ws_bytes = nb;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// context projection:  A[k,u,b] = b0_k[u] + sum_c W0_k[u,c] * ((x[b,c] (+ delta[b,c]) - mean[c]) / std[c])
+constexpr int CP_ROWS = 8;
+__global__ void k_ctx_project(MafImg g, const float* __restrict__ x, const float* __restrict__ delta,
+                              const float* __restrict__ zmean, const float* __restrict__ zstd, int B,
+                              float* __restrict__ A) {
+    extern __shared__ float cs[];  // [C][CP_ROWS]
+    const int C = g.C, K = g.K, H0 = g.H[0];
+    const int b0 = blockIdx.x * CP_ROWS;
+    for (int i = threadIdx.x; i < C * CP_ROWS; i += blockDim.x) {
+        int r = i / C, c = i % C;
+        int b = b0 + r;
+        float v = 0.f;
+        if (b < B) {
+            v = x[(size_t)b * C + c];
+            if (delta) v += delta[(size_t)b * C + c];
+            if (zmean) v = (v - zmean[c]) / zstd[c];
+        }
+        cs[c * CP_ROWS + r] = v;
+    }
+    __syncthreads();
+    const int ncol = K * g.H0p;
+    for (int col = threadIdx.x; col < ncol; col += blockDim.x) {
+        int k = col / g.H0p, u = col % g.H0p;
+        if (u >= H0) continue;
+        float acc[CP_ROWS];
+        float bias = g.f[g.t[k].b0 + u];
+#pragma unroll
+        for (int r = 0; r < CP_ROWS; ++r) acc[r] = bias;
+        const float* w = g.f + g.W0cT + col;
+        for (int c = 0; c < C; ++c) {
+            float wv = __ldg(w + (size_t)c * g.ldKH);
+            const float4 c0 = *reinterpret_cast<const float4*>(cs + c * CP_ROWS);
+            const float4 c1 = *reinterpret_cast<const float4*>(cs + c * CP_ROWS + 4);
+            acc[0] = fmaf(wv, c0.x, acc[0]);
+            acc[1] = fmaf(wv, c0.y, acc[1]);
+            acc[2] = fmaf(wv, c0.z, acc[2]);
+            acc[3] = fmaf(wv, c0.w, acc[3]);
+            acc[4] = fmaf(wv, c1.x, acc[4]);
+            acc[5] = fmaf(wv, c1.y, acc[5]);
+            acc[6] = fmaf(wv, c1.z, acc[6]);
+            acc[7] = fmaf(wv, c1.w, acc[7]);
+        }
+        float* out = A + ((size_t)k * H0 + u) * B + b0;
+#pragma unroll
+        for (int r = 0; r < CP_ROWS; ++r)
+            if (b0 + r < B) out[r] = acc[r];
+    }
+}
+
+// transposed projection: gx[b,c] = (1/std[c]) * sum_{k,u} W0_k[u,c] * gA[k,u,b]
+__global__ void k_ctx_project_bwd(MafImg g, const float* __restrict__ gA, const float* __restrict__ zstd, int B,
+                                  float* __restrict__ gx, int accumulate) {
+    extern __shared__ float gs[];  // [K*H0][CP_ROWS]
+    const int C = g.C, K = g.K, H0 = g.H[0];
+    const int b0 = blockIdx.x * CP_ROWS;
+    const int n = K * H0;
+    for (int i = threadIdx.x; i < n * CP_ROWS; i += blockDim.x) {
+        int ku = i / CP_ROWS, r = i % CP_ROWS;
+        gs[i] = (b0 + r < B) ? gA[(size_t)ku * B + b0 + r] : 0.f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc[CP_ROWS];
+#pragma unroll
+        for (int r = 0; r < CP_ROWS; ++r) acc[r] = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float* w = g.f + g.t[k].W0c + c;
+            const int ldc = g.t[k].ldc;
+            const float* gk = gs + (size_t)k * H0 * CP_ROWS;
+            for (int u = 0; u < H0; ++u) {
+                float wv = __ldg(w + (size_t)u * ldc);
+                const float4 c0 = *reinterpret_cast<const float4*>(gk + u * CP_ROWS);
+                const float4 c1 = *reinterpret_cast<const float4*>(gk + u * CP_ROWS + 4);
+                acc[0] = fmaf(wv, c0.x, acc[0]);
+                acc[1] = fmaf(wv, c0.y, acc[1]);
+                acc[2] = fmaf(wv, c0.z, acc[2]);
+                acc[3] = fmaf(wv, c0.w, acc[3]);
+                acc[4] = fmaf(wv, c1.x, acc[4]);
+                acc[5] = fmaf(wv, c1.y, acc[5]);
+                acc[6] = fmaf(wv, c1.z, acc[6]);
+                acc[7] = fmaf(wv, c1.w, acc[7]);
+            }
+        }
+        float inv = zstd ? 1.f / zstd[c] : 1.f;
+#pragma unroll
+        for (int r = 0; r < CP_ROWS; ++r)
+            if (b0 + r < B) {
+                float v = acc[r] * inv;
+                float* o = gx + (size_t)(b0 + r) * C + c;
+                *o = accumulate ? *o + v : v;
+            }
+    }
+}
+
+// mean over the sample axis: out[b] = (1/S) sum_s in[s,b]
+__global__ void k_mean_over_s(const float* __restrict__ in, int S, int B, float* __restrict__ out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += in[(size_t)s * B + b];
+    out[b] = acc / (float)S;
+}
+
+// advertorch perturb_iterative(ord=2) update, one warp per row.
+__global__ void k_pgd_update(const float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ grad,
+                             int B, int dx, float eps, float eps_iter, float cmin, float cmax, float floor_) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const float* gr = grad + (size_t)warp * dx;
+    const float* xr = x + (size_t)warp * dx;
+    float* dr = delta + (size_t)warp * dx;
+    float n2 = 0.f;
+    for (int c = lane; c < dx; c += 32) n2 = fmaf(gr[c], gr[c], n2);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    float inv = 1.f / fmaxf(sqrtf(n2), floor_);
+    float d2 = 0.f;
+    for (int c = lane; c < dx; c += 32) {
+        float d = dr[c] + (gr[c] * inv) * eps_iter;
+        d = fminf(fmaxf(xr[c] + d, cmin), cmax) - xr[c];
+        dr[c] = d;
+        d2 = fmaf(d, d, d2);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    float factor = fminf(eps / sqrtf(d2), 1.f);
+    for (int c = lane; c < dx; c += 32) dr[c] *= factor;
+}
+
+__global__ void k_clamp_add(const float* __restrict__ x, const float* __restrict__ delta, size_t n, float cmin,
+                            float cmax, float* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fminf(fmaxf(x[i] + delta[i], cmin), cmax);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int launch_ctx_project(rabi_maf* h, const float* x, const float* delta, const float* zm, const float* zs, int B,
+                              float* A, cudaStream_t st) {
+    if ((zm == nullptr) != (zs == nullptr)) return fail(h, "zs_mean and zs_std must both be given or both be NULL");
+    size_t smem = (size_t)h->C * CP_ROWS * sizeof(float);
+    if (smem > 48 * 1024) CU_OK(h, cudaFuncSetAttribute(k_ctx_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ctx_project<<<(B + CP_ROWS - 1) / CP_ROWS, 128, smem, st>>>(h->img, x, delta, zm, zs, B, A);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" int rabi_maf_ctx_project(rabi_maf_t* h, const float* x_dev, const float* zs_mean_dev,
+                                    const float* zs_std_dev, int B, float* A_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (B <= 0) return 0;
+    return launch_ctx_project(h, x_dev, nullptr, zs_mean_dev, zs_std_dev, B, A_dev, (cudaStream_t)s);
+}
+
+static int launch_ctx_project_bwd(rabi_maf* h, const float* gA, const float* zs, int B, float* gx, int accumulate,
+                                  cudaStream_t st) {
+    size_t smem = (size_t)h->K * h->H[0] * CP_ROWS * sizeof(float);
+    if (smem > 48 * 1024)
+        CU_OK(h, cudaFuncSetAttribute(k_ctx_project_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ctx_project_bwd<<<(B + CP_ROWS - 1) / CP_ROWS, 128, smem, st>>>(h->img, gA, zs, B, gx, accumulate);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" int rabi_maf_ctx_project_bwd(rabi_maf_t* h, const float* gA_dev, const float* zs_std_dev, int B,
+                                        float* gx_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (B <= 0) return 0;
+    return launch_ctx_project_bwd(h, gA_dev, zs_std_dev, B, gx_dev, 0, (cudaStream_t)s);
+}
+
+template <int MODE>
+static int launch_pairs(rabi_maf* h, const PairArgs& a, cudaStream_t st) {
+    const long long npairs = (long long)a.S * a.B;
+    if (npairs <= 0) return 0;
+    size_t per_thread = pair_smem_floats_per_thread(h->K, h->D, h->L, h->img.Hmax) * sizeof(float);
+    int T = 256;
+    const size_t budget = std::min<size_t>((size_t)h->max_smem_optin, 200 * 1024);
+    while (T > 32 && (size_t)T * per_thread > budget) T -= 32;
+    if ((size_t)T * per_thread > (size_t)h->max_smem_optin)
+        return fail(h, "model too large for the per-pair kernel (%zu B of shared memory per pair)", per_thread);
+    size_t smem = (size_t)T * per_thread;
+    CU_OK(h, cudaFuncSetAttribute(k_pairs<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long nblk = (npairs + T - 1) / T;
+    k_pairs<MODE><<<(unsigned)nblk, T, smem, st>>>(h->img, a);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const float* theta_dev, int S, int B,
+                                     float* logp_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    PairArgs a = {};
+    a.A_p = A_dev;
+    a.in = theta_dev;
+    a.out_lp = logp_dev;
+    a.S = S;
+    a.B = B;
+    return launch_pairs<MODE_LOGPROB>(h, a, (cudaStream_t)s);
+}
+
+extern "C" int rabi_maf_rsample_fwd(rabi_maf_t* h, const float* A_dev, const float* z_dev, int S, int B,
+                                    float* theta_dev, float* logq_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    PairArgs a = {};
+    a.A_p = A_dev;
+    a.in = z_dev;
+    a.out_theta = theta_dev;
+    a.out_lp = logq_dev;
+    a.S = S;
+    a.B = B;
+    return launch_pairs<MODE_RSAMPLE>(h, a, (cudaStream_t)s);
+}
+
+extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_q_dev, const float* z_dev, int S, int B,
+                            float* kl_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (S <= 0 || B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    if (ensure_ws(h, (size_t)S * B * sizeof(float))) return 1;
+    PairArgs a = {};
+    a.A_p = A_p_dev;
+    a.A_q = A_q_dev;
+    a.in = z_dev;
+    a.out_lp = (float*)h->ws;
+    a.S = S;
+    a.B = B;
+    if (launch_pairs<MODE_RKL_FWD>(h, a, st)) return 1;
+    k_mean_over_s<<<(B + 127) / 128, 128, 0, st>>>((const float*)h->ws, S, B, kl_dev);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// workspace layout for the PGD step: [A_p: K*H0*B][gA: K*H0*B][gx: B*C][diff: S*B]
+static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float* zm, const float* zs, const float* A_q,
+                         const float* z, int S, int B, float eps, float eps_iter, float cmin, float cmax, float inv_B,
+                         float floor_, float* kl, cudaStream_t st) {
+    const size_t nA = (size_t)h->K * h->H[0] * B;
+    float* A_p = (float*)h->ws;
+    float* gA = A_p + nA;
+    float* gx = gA + nA;
+    float* diff = gx + (size_t)B * h->C;
+    if (launch_ctx_project(h, x, delta, zm, zs, B, A_p, st)) return 1;
+    CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
+    PairArgs a = {};
+    a.A_p = A_p;
+    a.A_q = A_q;
+    a.in = z;
+    a.out_lp = kl ? diff : nullptr;
+    a.gA = gA;
+    a.S = S;
+    a.B = B;
+    a.w = inv_B / (float)S;
+    if (launch_pairs<MODE_RKL_GRAD>(h, a, st)) return 1;
+    if (launch_ctx_project_bwd(h, gA, zs, B, gx, 0, st)) return 1;
+    if (!delta) {  // gradient-only mode (rabi_rkl_input_grad)
+        if (kl) {
+            k_mean_over_s<<<(B + 127) / 128, 128, 0, st>>>(diff, S, B, kl);
+            LAUNCH_CHECK(h);
+        }
+        return 0;
+    }
+    int threads = 128, rows_per_block = threads / 32;
+    k_pgd_update<<<(B + rows_per_block - 1) / rows_per_block, threads, 0, st>>>(x, delta, gx, B, h->C, eps, eps_iter,
+                                                                                   cmin, cmax, floor_);
+    LAUNCH_CHECK(h);
+    if (kl) {
+        k_mean_over_s<<<(B + 127) / 128, 128, 0, st>>>(diff, S, B, kl);
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+static size_t pgd_ws_bytes(const rabi_maf* h, int S, int B) {
+    return (2 * (size_t)h->K * h->H[0] * B + (size_t)B * h->C + (size_t)S * B) * sizeof(float);
+}
+
+extern "C" int rabi_rkl_pgd_step(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* zs_mean_dev,
+                                 const float* zs_std_dev, const float* A_q_dev, const float* z_dev, int S, int B,
+                                 float eps, float eps_iter, float clip_min, float clip_max, float inv_B,
+                                 float norm_floor, float* kl_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (S <= 0 || B <= 0) return 0;
+    if (ensure_ws(h, pgd_ws_bytes(h, S, B))) return 1;
+    return pgd_step_impl(h, x_dev, delta_dev, zs_mean_dev, zs_std_dev, A_q_dev, z_dev, S, B, eps, eps_iter, clip_min,
+                         clip_max, inv_B, norm_floor, kl_dev, (cudaStream_t)s);
+}
+
+extern "C" int rabi_rkl_input_grad(rabi_maf_t* h, const float* x_dev, const float* zs_mean_dev, const float* zs_std_dev,
+                                   const float* A_q_dev, const float* z_dev, int S, int B, float inv_B, float* gx_dev,
+                                   float* kl_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (S <= 0 || B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    if (ensure_ws(h, pgd_ws_bytes(h, S, B))) return 1;
+    if (pgd_step_impl(h, x_dev, nullptr, zs_mean_dev, zs_std_dev, A_q_dev, z_dev, S, B, -1.f, 0.f, 0.f, 0.f, inv_B, 0.f,
+                      kl_dev, st))
+        return 1;
+    const float* gx = (const float*)h->ws + 2 * (size_t)h->K * h->H[0] * B;
+    CU_OK(h, cudaMemcpyAsync(gx_dev, gx, (size_t)B * h->C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* zs_mean_dev,
+                                const float* zs_std_dev, const float* A_q_dev, const float* z_all_dev, int nb_iter, int S,
+                                int B, float eps,
+                                float eps_iter, float clip_min, float clip_max, float inv_B, float norm_floor,
+                                float* x_adv_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (S <= 0 || B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    const size_t nA = (size_t)h->K * h->H[0] * B;
+    if (ensure_ws(h, pgd_ws_bytes(h, S, B) + nA * sizeof(float))) return 1;
+    const float* A_q = A_q_dev;
+    if (!A_q) {
+        float* own = (float*)((char*)h->ws + pgd_ws_bytes(h, S, B));
+        if (launch_ctx_project(h, x_dev, nullptr, zs_mean_dev, zs_std_dev, B, own, st)) return 1;
+        A_q = own;
+    }
+    const size_t zstride = (size_t)S * B * h->D;
+    for (int it = 0; it < nb_iter; ++it)
+        if (pgd_step_impl(h, x_dev, delta_dev, zs_mean_dev, zs_std_dev, A_q, z_all_dev + (size_t)it * zstride, S, B, eps,
+                          eps_iter, clip_min, clip_max, inv_B, norm_floor, nullptr, st))
+            return 1;
+    if (x_adv_dev) {
+        size_t n = (size_t)B * h->C;
+        k_clamp_add<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_dev, delta_dev, n, clip_min, clip_max, x_adv_dev);
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}

@@ -1,0 +1,191 @@
+"""Thin Python wrapper around one ``rabi_maf_t`` handle: device buffers, streams and error handling.
+
+PyTorch is used here only for device memory and the current CUDA stream; all arithmetic happens in
+``librabi_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import RabiError
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), (t.device, t.dtype, t.is_contiguous())
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class MafEngine:
+    """Owns the packed weight image of one MAF (K masked-MADE conditioners) on one CUDA device."""
+
+    def __init__(self, K: int, D: int, C: int, hidden: Sequence[int], log_scale_min: float, log_scale_max: float,
+                 device: torch.device):
+        self.L = _lib.lib()
+        self.K, self.D, self.C, self.hidden = int(K), int(D), int(C), [int(h) for h in hidden]
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RabiError("rabi_b200 runs on CUDA devices only (no CPU fallback); move the model with .to('cuda')")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self.h = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(self.hidden))(*self.hidden)
+        rc = self.L.rabi_maf_create(ctypes.byref(self.h), idx, self.K, self.D, self.C, len(self.hidden), arr,
+                                    float(log_scale_min), float(log_scale_max))
+        if rc != 0:
+            msg = self.L.rabi_last_error(None).decode()
+            self.h = None
+            raise ValueError(msg) if "Hidden dimension" in msg else RabiError(msg)
+        self._versions = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.rabi_maf_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RabiError(self.L.rabi_last_error(self.h).decode())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.rabi_launch_count(self.h))
+
+    # ------------------------------------------------------------------ structure / weights
+    def set_structure(self, perms: List[torch.Tensor], masks: List[List[torch.Tensor]],
+                      post_perms: Optional[List[Optional[torch.Tensor]]] = None):
+        for k in range(self.K):
+            pp = None if post_perms is None else post_perms[k]
+            if pp is not None:
+                pp = pp.detach().to("cpu", torch.int64).contiguous()
+                self._check(self.L.rabi_maf_set_post_permutation(
+                    self.h, k, ctypes.cast(pp.data_ptr(), ctypes.POINTER(ctypes.c_int64))))
+            else:
+                self._check(self.L.rabi_maf_set_post_permutation(self.h, k, None))
+            p = perms[k].detach().to("cpu", torch.int64).contiguous()
+            self._check(self.L.rabi_maf_set_permutation(self.h, k, ctypes.cast(p.data_ptr(), ctypes.POINTER(ctypes.c_int64))))
+            for l, m in enumerate(masks[k]):
+                m = m.detach().to("cpu", torch.float32).contiguous()
+                self._check(self.L.rabi_maf_set_mask(self.h, k, l, ctypes.cast(m.data_ptr(), ctypes.POINTER(ctypes.c_float)),
+                                                     m.shape[0], m.shape[1]))
+        self._check(self.L.rabi_maf_finalize_structure(self.h))
+        self._versions = None
+
+    def set_weights(self, params: List[List[Tuple[torch.Tensor, torch.Tensor]]]):
+        """params[k][layer] = (weight, bias) CUDA fp32 tensors; re-packs only what changed since the last call."""
+        vers = [[(w.data_ptr(), w._version, b.data_ptr(), b._version) for (w, b) in pk] for pk in params]
+        with torch.cuda.device(self.device):
+            for k, pk in enumerate(params):
+                for l, (w, b) in enumerate(pk):
+                    if self._versions is not None and self._versions[k][l] == vers[k][l]:
+                        continue
+                    w_, b_ = _f32c(w.detach()), _f32c(b.detach())
+                    self._check(self.L.rabi_maf_set_weights(self.h, k, l, _ptr(w_), _ptr(b_), self._stream()))
+        self._versions = vers
+
+    # ------------------------------------------------------------------ kernels
+    def ctx_project(self, x: torch.Tensor, zs_mean: Optional[torch.Tensor] = None,
+                    zs_std: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [B, C] -> A [K, H0, B]."""
+        x = _f32c(x)
+        B = x.shape[0]
+        A = torch.empty((self.K, self.hidden[0], B), device=self.device, dtype=torch.float32)
+        if B:
+            with torch.cuda.device(self.device):
+                self._check(self.L.rabi_maf_ctx_project(self.h, _ptr(x), _ptr(zs_mean), _ptr(zs_std), B, _ptr(A),
+                                                        self._stream()))
+        return A
+
+    def ctx_project_bwd(self, gA: torch.Tensor, zs_std: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B = gA.shape[-1]
+        gx = torch.empty((B, self.C), device=self.device, dtype=torch.float32)
+        if B:
+            with torch.cuda.device(self.device):
+                self._check(self.L.rabi_maf_ctx_project_bwd(self.h, _ptr(_f32c(gA)), _ptr(zs_std), B, _ptr(gx),
+                                                            self._stream()))
+        return gx
+
+    def log_prob(self, A: torch.Tensor, theta: torch.Tensor) -> torch.Tensor:
+        """theta [S, B, D] -> log q [S, B]."""
+        theta = _f32c(theta)
+        S, B, _ = theta.shape
+        out = torch.empty((S, B), device=self.device, dtype=torch.float32)
+        if S * B:
+            with torch.cuda.device(self.device):
+                self._check(self.L.rabi_maf_log_prob_fwd(self.h, _ptr(A), _ptr(theta), S, B, _ptr(out), self._stream()))
+        return out
+
+    def rsample(self, A: torch.Tensor, z: torch.Tensor, want_logq: bool = True):
+        z = _f32c(z)
+        S, B, _ = z.shape
+        theta = torch.empty_like(z)
+        logq = torch.empty((S, B), device=self.device, dtype=torch.float32) if want_logq else None
+        if S * B:
+            with torch.cuda.device(self.device):
+                self._check(self.L.rabi_maf_rsample_fwd(self.h, _ptr(A), _ptr(z), S, B, _ptr(theta), _ptr(logq),
+                                                        self._stream()))
+        return theta, logq
+
+    def rkl(self, A_p: torch.Tensor, A_q: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        z = _f32c(z)
+        S, B, _ = z.shape
+        out = torch.empty((B,), device=self.device, dtype=torch.float32)
+        if S * B:
+            with torch.cuda.device(self.device):
+                self._check(self.L.rabi_rkl_fwd(self.h, _ptr(A_p), _ptr(A_q), _ptr(z), S, B, _ptr(out), self._stream()))
+        return out
+
+    def rkl_input_grad(self, x, zs_mean, zs_std, A_q, z, inv_B, want_kl=True):
+        """-> (d[inv_B * sum_b KL(q(.|x_b) || target_b)]/dx  [B, C], kl [B] | None)."""
+        z = _f32c(z)
+        S, B, _ = z.shape
+        gx = torch.empty((B, self.C), device=self.device, dtype=torch.float32)
+        kl = torch.empty((B,), device=self.device, dtype=torch.float32) if want_kl else None
+        with torch.cuda.device(self.device):
+            self._check(self.L.rabi_rkl_input_grad(self.h, _ptr(_f32c(x)), _ptr(zs_mean), _ptr(zs_std), _ptr(A_q), _ptr(z),
+                                                   S, B, float(inv_B), _ptr(gx), _ptr(kl), self._stream()))
+        return gx, kl
+
+    def pgd_step(self, x, delta, zs_mean, zs_std, A_q, z, eps, eps_iter, clip_min, clip_max, inv_B,
+                 norm_floor=1e-6, want_kl=False):
+        z = _f32c(z)
+        S, B, _ = z.shape
+        kl = torch.empty((B,), device=self.device, dtype=torch.float32) if want_kl else None
+        with torch.cuda.device(self.device):
+            self._check(self.L.rabi_rkl_pgd_step(self.h, _ptr(x), _ptr(delta), _ptr(zs_mean), _ptr(zs_std), _ptr(A_q),
+                                                 _ptr(z), S, B, float(eps), float(eps_iter), float(clip_min),
+                                                 float(clip_max), float(inv_B), float(norm_floor), _ptr(kl),
+                                                 self._stream()))
+        return kl
+
+    def pgd_run(self, x, delta, zs_mean, zs_std, A_q, z_all, eps, eps_iter, clip_min, clip_max, inv_B,
+                norm_floor=1e-6):
+        """z_all [nb_iter, S, B, D]; updates delta in place and returns x_adv = clamp(x + delta).
+        A_q None: untargeted (projection of the clean x is computed inside)."""
+        z_all = _f32c(z_all)
+        nb_iter, S, B, _ = z_all.shape
+        x_adv = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            self._check(self.L.rabi_rkl_pgd_run(self.h, _ptr(x), _ptr(delta), _ptr(zs_mean), _ptr(zs_std), _ptr(A_q),
+                                                _ptr(z_all), nb_iter, S, B, float(eps), float(eps_iter), float(clip_min),
+                                                float(clip_max), float(inv_B), float(norm_floor), _ptr(x_adv),
+                                                self._stream()))
+        return x_adv

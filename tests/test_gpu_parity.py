@@ -1,0 +1,197 @@
+"""GPU parity tests (run on the B200 with ``-m gpu``): the sm_100a kernels, driven through the C ABI, against
+(a) the committed golden fixtures -- outputs of the UNMODIFIED reference executed in the build container -- and
+(b) the live CPU oracle on fresh seeded inputs, at the reference's shapes."""
+import pytest
+import torch
+
+from tests.util import CASES, RTOL, build_oracle, build_product, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request, dev):
+    g = load_golden(request.param)
+    return request.param, g, build_product(g, dev)
+
+
+def test_log_prob_matches_reference(case, dev):
+    name, g, model = case
+    with torch.no_grad():
+        lp = model(g["x"].to(dev)).log_prob(g["theta"].to(dev))
+    assert lp.shape == g["log_prob"].shape
+    assert rel_err(lp, g["log_prob"]) < RTOL
+
+
+def test_rsample_and_own_log_prob_match_reference(case, dev):
+    from rabi_b200 import noise
+
+    name, g, model = case
+    with torch.no_grad(), noise.injected([g["z_rsample"]]):
+        q = model(g["x"].to(dev))
+        th = q.rsample((4,))
+        lp_own = q.log_prob(th)          # "free" log-prob of the samples just drawn (reference cache hit, Q9)
+        lp_again = q.log_prob(th.clone())  # recomputed through the density pass
+    assert rel_err(th, g["rsample"]) < RTOL
+    assert rel_err(lp_own, g["rsample_log_prob"]) < RTOL
+    assert rel_err(lp_again, g["rsample_log_prob"]) < RTOL
+
+
+@pytest.mark.parametrize("S", [5, 64])
+def test_reverse_kl_matches_reference(case, dev, S):
+    from rabi_b200 import noise
+    from rabi_b200.loss import ReverseKLLoss
+
+    name, g, model = case
+    with torch.no_grad(), noise.injected([g[f"z_rkl{S}"]]):
+        kl = ReverseKLLoss(mc_samples=S, reduction=None)(model(g["x_tilde"].to(dev)), model(g["x"].to(dev)))
+    ref = g[f"rkl{S}"]
+    # KL is a difference of O(10) log-densities: tolerance relative to the log-density scale
+    scale = max(float(g["rsample_log_prob"].abs().max()), float(ref.abs().max()))
+    assert float((kl.cpu() - ref).abs().max()) < RTOL * scale
+
+
+def test_forward_kl_matches_reference(case, dev):
+    from rabi_b200 import noise
+    from rabi_b200.loss import ForwardKLLoss
+
+    name, g, model = case
+    with torch.no_grad(), noise.injected([g["z_fkl5"]]):
+        kl = ForwardKLLoss(mc_samples=5, reduction=None)(model(g["x_tilde"].to(dev)), model(g["x"].to(dev)))
+    scale = max(float(g["rsample_log_prob"].abs().max()), float(g["fkl5"].abs().max()))
+    assert float((kl.cpu() - g["fkl5"]).abs().max()) < RTOL * scale
+
+
+def test_reverse_kl_input_gradient_matches_reference(case, dev):
+    """d mean_B KL(q(.|x~) || q(.|x)) / d x~ -- what perturb_iterative's loss.backward() leaves in delta.grad."""
+    name, g, model = case
+    x, xt = g["x"].to(dev), g["x_tilde"].to(dev)
+    eng = model.engine()
+    with torch.no_grad():
+        q = model(x)
+        _, zs, _ = model.condition_inputs(xt)
+        zs = zs or (None, None)
+        gx, kl = eng.rkl_input_grad(xt, zs[0], zs[1], q.A, g["z_rkl_grad"].to(dev), 1.0 / x.shape[0])
+    assert rel_err(gx, g["rkl_grad_x"]) < RTOL
+    assert abs(float(kl.mean()) - float(g["rkl_mean"])) < RTOL * float(g["rsample_log_prob"].abs().max())
+
+
+@pytest.mark.parametrize("n_it", [1, 5, 20])
+def test_l2pgd_matches_reference(case, dev, n_it):
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+
+    name, g, model = case
+    p = g["pgd"]
+    x = g["x"].to(dev)
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=p["S"]), eps=p["eps"], nb_iter=n_it,
+                      eps_iter=p["eps_iter"], clip_min=p["clip_min"], clip_max=p["clip_max"], targeted=False)
+    with noise.injected(list(p[f"z_{n_it}"])):
+        xa = atk.perturb(x, delta_init=p["delta0"].to(dev))
+    ref = p[f"x_adv_{n_it}"]
+    # compare the perturbations (x~ - x), relative to their size
+    assert rel_err(xa.cpu() - g["x"], ref - g["x"]) < (RTOL if n_it <= 5 else 5 * RTOL)
+    assert float((xa.cpu() - g["x"]).norm(dim=-1).max()) <= p["eps"] * (1 + 1e-5)
+    assert float(xa.min()) >= p["clip_min"] - 1e-6 and float(xa.max()) <= p["clip_max"] + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------
+# live oracle at the reference's full shapes (fresh seeded inputs; sizes the oracle finishes in seconds)
+SHAPES = {
+    "gaussian_linear": dict(dx=10, D=10, hidden=[100, 100], B=64),
+    "lotka_volterra": dict(dx=100, D=4, hidden=[100, 100], B=96),
+    "pyloric": dict(dx=100, D=31, hidden=[200, 200, 200], B=24),
+}
+
+
+def _fresh(shape, dev, seed=0):
+    from oracle import rbi_oracle as O
+    from rabi_b200.models import InverseAffineAutoregressiveModel, ZScoreLayer
+
+    torch.manual_seed(seed)
+    kw = dict(log_scale_min_clip=-7, log_scale_max_clip=5, stable=False)
+    dx, D, hidden, B = shape["dx"], shape["D"], shape["hidden"], shape["B"]
+    mean, std = 0.3 * torch.randn(dx), 0.05 + 1.95 * torch.rand(dx)
+    ref = O.OracleMAF(dx, D, hidden_dims=hidden, num_transforms=3, shuffle=False,
+                      embedding_net=torch.nn.Sequential(O.ZScoreLayer(mean, std), torch.nn.Identity()), **kw)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.add_(0.3 * torch.randn_like(p) * (p.abs().mean() + 0.05))
+    model = InverseAffineAutoregressiveModel(dx, D, hidden_dims=hidden, num_transforms=3, shuffle=False, **kw)
+    model.embedding_net = torch.nn.Sequential(ZScoreLayer(mean, std), model.embedding_net)
+    model.load_state_dict(ref.state_dict())
+    x = torch.randn(B, dx) * std + mean
+    return ref.eval(), model.to(dev).eval(), x
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
+def test_full_shape_pipeline_vs_oracle(shape, dev):
+    from oracle import rbi_oracle as O
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+
+    ref, model, x = _fresh(SHAPES[shape], dev)
+    B, D = x.shape[0], SHAPES[shape]["D"]
+    eps = float(0.5 * x.std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+    nb, S, S_eval = 10, 5, 32
+    g = torch.Generator().manual_seed(3)
+    zs = [torch.randn(S, B, D, generator=g) for _ in range(nb)]
+    z_eval = torch.randn(S_eval, B, D, generator=g)
+    d0 = O.adv.clamp_by_pnorm(torch.randn(B, x.shape[1], generator=g), 2, eps)
+    d0 = O.adv.clamp(x + d0, cmin, cmax) - x
+    with O.injected_base_noise(zs):
+        xa_ref = O.l2pgd_perturb(ref, x, O.ReverseKLLoss(mc_samples=S), eps, nb, eps / 10, cmin, cmax, delta0=d0)
+    with O.injected_base_noise([z_eval]):
+        kl_ref = O.rkl_rob_metric(ref, x, xa_ref, S_eval)
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=S), eps=eps, nb_iter=nb, eps_iter=eps / 10,
+                      clip_min=cmin, clip_max=cmax)
+    with noise.injected(zs):
+        xa = atk.perturb(x.to(dev), delta_init=d0.to(dev))
+    assert rel_err(xa.cpu() - x, xa_ref - x) < 2 * RTOL
+    with torch.no_grad(), noise.injected([z_eval]):
+        kl = ReverseKLLoss(mc_samples=S_eval, reduction=None)(model(xa_ref.to(dev)), model(x.to(dev)))
+    with torch.no_grad():
+        lp_scale = float(ref(x).log_prob(ref(x).sample()).abs().max())
+    assert float((kl.cpu() - kl_ref).abs().max()) < RTOL * max(lp_scale, float(kl_ref.abs().max()))
+
+
+def test_size_independent_properties_at_config2_scale(dev):
+    """BASELINE config 2 sizes (LV shapes, B=1000 chunk, S=256): properties that need no oracle run.
+    KL(q,q) == 0 exactly when both arguments are the same conditioned object; ||x~ - x|| <= eps and inside the clip
+    box; log_prob(rsample) through the density pass equals the sampling pass' own log-density."""
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+
+    _, model, _ = _fresh(SHAPES["lotka_volterra"], dev, seed=5)
+    torch.manual_seed(11)
+    x = torch.randn(1000, 100, device=dev)
+    with torch.no_grad():
+        q = model(x)
+        kl_same = ReverseKLLoss(mc_samples=256, reduction=None)(q, q)
+        assert float(kl_same.abs().max()) < 2e-4  # same weights, same context: only fp32 re-association noise
+        th = q.rsample((64,))
+        lp_free = q.log_prob(th)
+        lp_dens = q.log_prob(th.clone())
+        assert torch.isfinite(lp_free).all()
+        assert float((lp_free - lp_dens).abs().max()) < 1e-4 * float(lp_free.abs().max())
+    eps = float(0.5 * x.std(1).mean())
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=5), eps=eps, nb_iter=20, eps_iter=eps / 10,
+                      clip_min=float(x.min()), clip_max=float(x.max()))
+    xa = atk.perturb(x)
+    assert xa.shape == x.shape and (xa != x).any()
+    assert float((xa - x).norm(dim=-1).max()) <= eps * (1 + 1e-5)
+    assert float(xa.min()) >= float(x.min()) and float(xa.max()) <= float(x.max())
+    with torch.no_grad():
+        kl_adv = ReverseKLLoss(mc_samples=256, reduction=None)(model(xa), model(x))
+        kl_rand = ReverseKLLoss(mc_samples=256, reduction=None)(
+            model(x + eps * torch.nn.functional.normalize(torch.randn_like(x), dim=-1)), model(x))
+    assert float(kl_adv.mean()) > float(kl_rand.mean())  # the attack beats a random direction of the same norm
