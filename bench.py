@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: attacked (x, MC-sample) MAF posterior evals/sec.
+
+One "step" = one pass of the robustness hot path over one shard of synthetic observations, exactly the work
+``rbibm ... eval_rob/attack=l2pgd eval_rob/metric=rKL`` does per epsilon: for every observation row an
+L2-PGD attack (nb_iter=200 iterations x S=5 MC samples, reverse-KL loss) followed by the robustness metric
+KL(q(.|x~) || q(.|x)) with S=256 samples.  Workload = BASELINE config 2 (lotka_volterra shapes: dx=C=100, D=4,
+hidden [100,100], K=3, z-score embedding), 10 000 observations per GPU => 12.56 M (x, MC-sample) pairs per step per
+GPU.  Data are synthetic (x ~ N(0, I), seed 0; default nn.Linear init perturbed with seeded noise) because the
+simulators need packages that are not installed and there is no network.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by the driver under torchrun, one rank per GPU; observations are sharded by rank (weak scaling,
+no data-path collective); the only exchange is the final all_gather of the per-observation losses (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "lotka_volterra_l2pgd_rkl": dict(dx=100, D=4, hidden=[100, 100], K=3, rows=10000, chunk=1000, nb_iter=200,
+                                     S_att=5, S_eval=256),
+}
+METRIC = "attacked (x, MC-sample) MAF posterior evals/sec"
+UNIT = "pairs/s"
+
+
+def pairs_per_row(w):
+    return w["nb_iter"] * w["S_att"] + w["S_eval"]
+
+
+# ------------------------------------------------------------------------------------------------ model / data
+def make_weights(w, seed=0):
+    """state_dict of the MAF (reference layout) + z-score stats + observations; CPU tensors."""
+    from rabi_b200.models import InverseAffineAutoregressiveModel
+
+    torch.manual_seed(seed)
+    m = InverseAffineAutoregressiveModel(w["dx"], w["D"], hidden_dims=w["hidden"], num_transforms=w["K"], shuffle=False,
+                                         log_scale_min_clip=-7, log_scale_max_clip=5, stable=False)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():  # non-trivial means / log-scales (plain init gives a nearly Gaussian posterior)
+        for p in m.parameters():
+            p.add_(0.25 * torch.randn(p.shape, generator=g) * (p.abs().mean() + 0.05))
+    return m
+
+
+def make_rows(w, rank, n_rows):
+    g = torch.Generator().manual_seed(1000 + rank)
+    return torch.randn(n_rows, w["dx"], generator=g)
+
+
+def algorithmic_flops(model, w):
+    """FLOPs per attack / eval pair as SURVEY 8d defines them: masked MACs only, sampling = one pass-equivalent.
+    X = context projection (shared by the S samples of a row), R = rest (per sample)."""
+    X = R = 0
+    for k in range(w["K"]):
+        layers = getattr(model, f"t{k}").nn.layers
+        C = model.context_dim
+        m0 = layers[0].mask
+        X += int(m0[:, :C].sum())
+        R += int(m0[:, C:].sum()) + sum(int(l.mask.sum()) for l in layers[1:])
+    att = 2.0 * (4 * R + 2 * X / w["S_att"])
+    ev = 2.0 * (2 * R + 2 * X / w["S_eval"])
+    pair_kernel_att = 2.0 * 4 * R  # what one launch of the per-pair fwd+bwd kernel covers (X is in the projection kernels)
+    return dict(attack_pair=att, eval_pair=ev, pair_kernel_attack=pair_kernel_att, X=X / w["K"], R=R / w["K"])
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_reference_sample(w, model_state, threads, it_sample=10, seed=0):
+    """Times the oracle (op-for-op restatement of the reference's Pyro/advertorch path) on one 1000-row chunk:
+    ``it_sample`` PGD iterations + the S_eval metric, and extrapolates to the chunk's full nb_iter (iterations are
+    identical in cost; chunks are independent).  Returns pairs/s and a description."""
+    from oracle import rbi_oracle as O
+
+    torch.set_num_threads(threads)
+    ref = O.OracleMAF(w["dx"], w["D"], hidden_dims=w["hidden"], num_transforms=w["K"], shuffle=False,
+                      embedding_net=torch.nn.Sequential(O.ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])),
+                                                        torch.nn.Identity()),
+                      log_scale_min_clip=-7, log_scale_max_clip=5, stable=False)
+    sd = {k: v for k, v in model_state.items()}
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    x = make_rows(w, 0, w["chunk"])
+    eps = float(0.5 * x.std(1).mean())
+    torch.manual_seed(seed)
+    t0 = time.perf_counter()
+    xa = O.l2pgd_perturb(ref, x, O.ReverseKLLoss(mc_samples=w["S_att"]), eps, it_sample, eps / 10, float(x.min()),
+                         float(x.max()))
+    t_att = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.rkl_rob_metric(ref, x, xa, w["S_eval"])
+    t_eval = time.perf_counter() - t0
+    t_chunk = t_att / it_sample * w["nb_iter"] + t_eval
+    pairs = w["chunk"] * pairs_per_row(w)
+    sample = (f"oracle (PyTorch restatement of the reference path) on one {w['chunk']}-row chunk: {it_sample} of "
+              f"{w['nb_iter']} PGD iterations ({t_att:.2f} s) + S={w['S_eval']} metric ({t_eval:.2f} s), extrapolated "
+              f"linearly to {w['nb_iter']} iterations")
+    return pairs / t_chunk, sample, t_att + t_eval
+
+
+def run_reference_arm(args, w, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from rabi_b200.models import ZScoreLayer
+
+    model = make_weights(w)
+    model.embedding_net = torch.nn.Sequential(ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])), model.embedding_net)
+    threads = os.cpu_count() or 1
+    vals, secs = [], []
+    for i in range(args.warmup + args.steps):
+        v, sample, dt = cpu_reference_sample(w, model.state_dict(), threads, it_sample=3, seed=i)
+        if i >= args.warmup:
+            vals.append(v)
+            secs.append(dt)
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wname, **{k: w[k] for k in ("dx", "D", "hidden", "K", "chunk", "nb_iter", "S_att", "S_eval")}},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference (pyro/advertorch/sbi) cannot be installed here; this arm times the oracle port of its "
+                "CPU path on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="rabi_b200", choices=["rabi_b200", "reference"])
+    ap.add_argument("--workload", default="lotka_volterra_l2pgd_rkl", choices=list(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=None, help="observations per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.rows:
+        w["rows"] = args.rows
+    if args.impl == "reference":
+        return run_reference_arm(args, w, args.workload)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+
+    from rabi_b200 import _lib
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+    from rabi_b200.metric import ReverseKLRobMetric
+    from rabi_b200.models import ZScoreLayer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl rabi_b200) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.build()
+
+    model = make_weights(w)
+    state_cpu = {k: v.clone() for k, v in model.state_dict().items()}
+    model.embedding_net = torch.nn.Sequential(ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])), model.embedding_net)
+    flops = algorithmic_flops(model, w)
+    model = model.to(dev).eval()
+    x_host = make_rows(w, rank, w["rows"]).pin_memory()
+    x_dev = x_host.to(dev)
+    eps = float(0.5 * x_host.std(1).mean())
+    cmin, cmax = float(x_host.min()), float(x_host.max())
+
+    attack = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=w["S_att"]), eps=eps, nb_iter=w["nb_iter"],
+                         eps_iter=eps / 10, clip_min=cmin, clip_max=cmax, targeted=False)
+    metric = ReverseKLRobMetric(model, attack, mc_samples=w["S_eval"], attack_attemps=1, device=dev,
+                                batch_size=w["chunk"], reduction=None)
+    eng = model.engine()
+
+    def step_device():
+        metric._cached_x = metric._cached_xs_tilde = metric._cached_losses = None
+        losses = metric._eval(x_dev)
+        if world > 1:  # the path's one exchange step: gather the per-observation losses for the quantile summary
+            out = [torch.empty_like(losses) for _ in range(world)]
+            dist.all_gather(out, losses)
+            losses = torch.cat(out)
+        return losses
+
+    loss_host = torch.empty(w["rows"] * world, dtype=torch.float32).pin_memory()
+    xadv_host = torch.empty_like(x_host).pin_memory()
+
+    def step_e2e():
+        metric._cached_x = metric._cached_xs_tilde = metric._cached_losses = None
+        xd = x_host.to(dev, non_blocking=True)
+        losses = metric._eval(xd)
+        if world > 1:
+            out = [torch.empty_like(losses) for _ in range(world)]
+            dist.all_gather(out, losses)
+            losses = torch.cat(out)
+        loss_host.copy_(losses, non_blocking=True)
+        xadv_host.copy_(metric._cached_xs_tilde, non_blocking=True)
+        torch.cuda.synchronize()
+        return loss_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    fma_peak = float(_lib.lib().rabi_fma_peak_tflops(local, 5))
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = eng.launches
+    eng.profile(True)
+    with ClockSampler(local) as clocks:
+        ms = timed(step_device, args.steps)
+    kern_ms, kern_n = eng.profile_read()
+    eng.profile(False)
+    launches = eng.launches - launches0
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    pairs_step = w["rows"] * pairs_per_row(w) * world
+    value = pairs_step * args.steps / (ms * 1e-3)
+    e2e = pairs_step * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel: per-pair rKL forward+backward (one launch per PGD iteration)
+    pairs_launch = w["rows"] * w["S_att"]
+    achieved = pairs_launch * flops["pair_kernel_attack"] / (kern_ms / max(kern_n, 1) * 1e-3) / 1e12 if kern_n else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp32_fma", "kernel": "k_pairs<RKL_GRAD>", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s",
+        "frac": (achieved / fma_peak) if (achieved and fma_peak > 0) else None, "traffic": None,
+        "peak_source": "rabi_fma_peak_tflops (register-only FFMA microbenchmark run in this process; "
+                       "MEASURED_PEAKS.json has no fp32 entry)",
+        "flop_per_launch": pairs_launch * flops["pair_kernel_attack"],
+        "kernel_ms_avg": kern_ms / max(kern_n, 1), "kernel_launches_timed": kern_n,
+        "kernel_share_of_step": kern_ms / ms if ms else None,
+        "whole_step_tflops": (w["rows"] * (w["nb_iter"] * w["S_att"] * flops["attack_pair"] + w["S_eval"] * flops["eval_pair"])
+                              * args.steps / (ms * 1e-3) / 1e12),
+        "hbm_gbs_measured_peak": peaks.get("hbm_gbs"),
+    }
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample, _ = cpu_reference_sample(w, state_cpu_with_zscore(state_cpu, w), os.cpu_count() or 1, it_sample=10)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "rows_per_gpu": w["rows"], "chunk": w["chunk"], "nb_iter": w["nb_iter"],
+                   "S_att": w["S_att"], "S_eval": w["S_eval"], "dx": w["dx"], "D": w["D"], "hidden": w["hidden"], "K": w["K"],
+                   "pairs_per_step": pairs_step, "parallelism": f"rows sharded over {world} GPU(s), no data-path collective",
+                   "l2": "per-step inputs (fresh base noise, 160 MB) exceed the 126 MB L2",
+                   "flop_per_attack_pair": flops["attack_pair"], "flop_per_eval_pair": flops["eval_pair"]},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+                "d2h_bytes_per_step": int(loss_host.numel() * 4 + xadv_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def state_cpu_with_zscore(state, w):
+    s = dict(state)
+    s["embedding_net.0.mean"] = torch.zeros(w["dx"])
+    s["embedding_net.0.std"] = torch.ones(w["dx"])
+    return s
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,15 @@ int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const 
                      float eps_iter, float clip_min, float clip_max, float inv_B, float norm_floor,
                      float* x_adv_dev, rabi_stream_t s);
 
+/* Measurement support (bench.py): CUDA-event timing of the dominant kernel (the per-pair rKL forward+backward
+ * kernel) on the stream it is launched on.  rabi_profile_read synchronises the device, returns the summed duration
+ * and the number of timed launches since the last read, and resets the counters. */
+int rabi_profile(rabi_maf_t* h, int enable);
+int rabi_profile_read(rabi_maf_t* h, double* total_ms, unsigned long long* launches);
+/* Measured fp32 FMA-pipe peak of `device` in TFLOP/s (best of `repeats` runs of a register-only FFMA kernel);
+ * the roofline denominator of the FMA-bound kernels.  < 0 on error. */
+double rabi_fma_peak_tflops(int device, int repeats);
+
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 unsigned long long rabi_launch_count(const rabi_maf_t* h);
 

@@ -27,6 +27,7 @@ EXPORTS = [
     "rabi_maf_set_mask", "rabi_maf_set_post_permutation", "rabi_maf_finalize_structure", "rabi_maf_set_weights", "rabi_maf_ctx_project",
     "rabi_maf_ctx_project_bwd", "rabi_maf_log_prob_fwd", "rabi_maf_rsample_fwd", "rabi_rkl_fwd",
     "rabi_rkl_input_grad", "rabi_rkl_pgd_step", "rabi_rkl_pgd_run", "rabi_launch_count",
+    "rabi_profile", "rabi_profile_read", "rabi_fma_peak_tflops",
 ]
 
 
@@ -101,9 +102,13 @@ def lib() -> ctypes.CDLL:
                                     c_float, c_float, vp, vp]
     L.rabi_rkl_pgd_run.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
                                    c_float, c_float, vp, vp]
+    L.rabi_profile.argtypes = [vp, c_int]
+    L.rabi_profile_read.argtypes = [vp, POINTER(ctypes.c_double), POINTER(c_ulonglong)]
+    L.rabi_fma_peak_tflops.argtypes = [c_int, c_int]
+    L.rabi_fma_peak_tflops.restype = ctypes.c_double
     for name in EXPORTS:
         fn = getattr(L, name)
-        if fn.restype is c_int or name.startswith(("rabi_maf_", "rabi_rkl_")):
+        if name.startswith(("rabi_maf_", "rabi_rkl_", "rabi_profile")):
             fn.restype = c_int
     _lib = L
     return L

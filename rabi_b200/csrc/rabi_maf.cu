@@ -33,6 +33,10 @@ struct rabi_maf {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     unsigned long long launches = 0;
+    // optional CUDA-event timing of the dominant kernel (k_pairs<RKL_GRAD>) on its launch stream
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
     std::string err;
     int sm_count = 148;
     int max_smem_optin = 0;
@@ -105,6 +109,10 @@ extern "C" int rabi_maf_destroy(rabi_maf_t* h) {
     if (h->f_dev) cudaFree(h->f_dev);
     if (h->m_dev) cudaFree(h->m_dev);
     if (h->ws) cudaFree(h->ws);
+    for (auto& e : h->prof_events) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
     delete h;
     return 0;
 }
@@ -607,9 +615,89 @@ static int launch_pairs(rabi_maf* h, const PairArgs& a, cudaStream_t st) {
     size_t smem = (size_t)T * per_thread;
     CU_OK(h, cudaFuncSetAttribute(k_pairs<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long nblk = (npairs + T - 1) / T;
+    const bool prof = h->profiling && MODE == MODE_RKL_GRAD;
+    if (prof) {
+        if (h->prof_used == h->prof_events.size()) {
+            cudaEvent_t e0, e1;
+            CU_OK(h, cudaEventCreate(&e0));
+            CU_OK(h, cudaEventCreate(&e1));
+            h->prof_events.push_back({e0, e1});
+        }
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].first, st));
+    }
     k_pairs<MODE><<<(unsigned)nblk, T, smem, st>>>(h->img, a);
     LAUNCH_CHECK(h);
+    if (prof) {
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].second, st));
+        h->prof_used++;
+    }
     return 0;
+}
+
+extern "C" int rabi_profile(rabi_maf_t* h, int enable) {
+    if (!h) return 1;
+    h->profiling = enable != 0;
+    h->prof_used = 0;
+    return 0;
+}
+
+extern "C" int rabi_profile_read(rabi_maf_t* h, double* total_ms, unsigned long long* launches) {
+    if (!h) return 1;
+    CU_OK(h, cudaSetDevice(h->device));
+    CU_OK(h, cudaDeviceSynchronize());
+    double tot = 0.0;
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        float ms = 0.f;
+        CU_OK(h, cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = h->prof_used;
+    h->prof_used = 0;
+    return 0;
+}
+
+// fp32 FMA-pipe peak (roofline denominator for the FMA-bound kernels; MEASURED_PEAKS.json has no fp32 entry)
+__global__ void k_fma_peak(float* out, int iters, float a, float b) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = (float)(threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(acc[j], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += acc[j];
+    if (s == 12345.678f) out[0] = s;
+}
+
+extern "C" double rabi_fma_peak_tflops(int device, int repeats) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    float* out = nullptr;
+    if (cudaMalloc(&out, 4) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_fma_peak<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);  // warm-up
+    double best = 0.0;
+    for (int r = 0; r < (repeats > 0 ? repeats : 5); ++r) {
+        cudaEventRecord(e0);
+        k_fma_peak<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError() == cudaSuccess ? best : -1.0;
 }
 
 extern "C" int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const float* theta_dev, int S, int B,

@@ -69,6 +69,15 @@ class MafEngine:
     def launches(self) -> int:
         return int(self.L.rabi_launch_count(self.h))
 
+    def profile(self, enable: bool):
+        self._check(self.L.rabi_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """-> (summed duration in ms of the timed dominant-kernel launches, number of launches); synchronises."""
+        ms, n = ctypes.c_double(), ctypes.c_ulonglong()
+        self._check(self.L.rabi_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, int(n.value)
+
     # ------------------------------------------------------------------ structure / weights
     def set_structure(self, perms: List[torch.Tensor], masks: List[List[torch.Tensor]],
                       post_perms: Optional[List[Optional[torch.Tensor]]] = None):
