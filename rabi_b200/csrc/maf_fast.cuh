@@ -1,0 +1,565 @@
+// Fast path for two-hidden-layer MADE conditioners (config/model/maf_pyro.yaml: hidden_dims [100, 100]) whose
+// per-transform weights fit in shared memory: fused MC reverse-KL forward (+ reverse-mode input gradient).
+//
+// Layout / schedule (DESIGN.md "k_fast"):
+//  * a CTA owns a tile of pairs; every thread owns RP pairs (slots tid, tid+T, ...) and keeps ONE private
+//    activation buffer per pair in shared memory ([slot][AS], AS/4 odd => conflict-free 128-bit access);
+//  * the weights of ONE transform (theta part of layer 0, layer 1, unit-major output layer) are staged in shared
+//    memory and read as warp-broadcast 128-bit loads; phases visit the transforms in the order
+//    p0 p1 p2 | q2 q1 q0 | q0' q1' q2' | p2' p1' p0'  so that only 9 of 12 phase changes reload weights;
+//  * layer 1 is never stored: each block of NR units is produced in registers (packed fma.rn.f32x2 along the
+//    dot-product direction), ReLU'd into a bit mask and folded straight into the 2D output accumulators;
+//  * the sequential sampling pass evaluates, at step j, only the units of MADE degree j (one pass-equivalent);
+//  * reverse mode is pull-style: the buffer holds the layer-1 cotangents, layer-0 cotangents are produced in
+//    registers per block, pushed into d/dy and reduced over the S samples of a row with shared-memory atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "maf_image.h"
+
+namespace rabi {
+
+struct FastArgs {
+    const float* A_p;
+    const float* A_q;
+    const float* z;     // [S,B,D]
+    float* diff;        // [S,B] log p - log q (optional in GRAD mode)
+    float* gA;          // GRAD: [K,H0,B] d loss / d A_p (plain stores: every row belongs to exactly one tile)
+    int S, B;
+    float w;
+    int TB;             // GRAD: rows per tile; FWD: unused
+    int NP;             // FWD: pairs per tile
+    int ntiles;
+    int AS, VS, BWS;    // per-slot strides: activations (floats), vectors (floats), relu bit words
+    int wfloats, wints; // per-transform weight / index block sizes (identical for all transforms)
+    int TBp;            // padded row count of the gA tile
+};
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd; }\n"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+// out[r][c] = sum_{i<e4} W[(min(c,cmax))*ld + i] * act_r[i]     (NR rows x RP pairs, e4 multiple of 4)
+template <int RP, int NR>
+__device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld, int cmax, int e4,
+                                          float* const (&actp)[RP], float (&out)[RP][NR]) {
+    float2 acc[RP][NR];
+#pragma unroll
+    for (int r = 0; r < RP; ++r)
+#pragma unroll
+        for (int c = 0; c < NR; ++c) acc[r][c] = make_float2(0.f, 0.f);
+    const float* wr[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) wr[c] = W + (size_t)min(c, cmax) * ld;
+#pragma unroll 2
+    for (int i = 0; i < e4; i += 4) {
+        float4 h[RP];
+#pragma unroll
+        for (int r = 0; r < RP; ++r) h[r] = *reinterpret_cast<const float4*>(actp[r] + i);
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(wr[c] + i);
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                acc[r][c] = ffma2(make_float2(w.x, w.y), make_float2(h[r].x, h[r].y), acc[r][c]);
+                acc[r][c] = ffma2(make_float2(w.z, w.w), make_float2(h[r].z, h[r].w), acc[r][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RP; ++r)
+#pragma unroll
+        for (int c = 0; c < NR; ++c) out[r][c] = acc[r][c].x + acc[r][c].y;
+}
+
+// out[r][c] = sum_{v in [va4, vb4)} W[v*ld + c] * g_r[v]     (NC columns x RP pairs; W offset to the first column;
+// va4/vb4 multiples of 4; rows >= the layer's width are zero padding)
+template <int RP, int NC>
+__device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld, int va4, int vb4,
+                                           float* const (&gp)[RP], float (&out)[RP][NC]) {
+    float2 acc[RP][NC / 2];
+#pragma unroll
+    for (int r = 0; r < RP; ++r)
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) acc[r][c] = make_float2(0.f, 0.f);
+    for (int v = va4; v < vb4; v += 4) {
+        float4 g4[RP];
+#pragma unroll
+        for (int r = 0; r < RP; ++r) g4[r] = *reinterpret_cast<const float4*>(gp[r] + v);
+#pragma unroll
+        for (int dv = 0; dv < 4; ++dv) {
+            const float* wrow = W + (size_t)(v + dv) * ld;
+#pragma unroll
+            for (int cc = 0; cc < NC / 4; ++cc) {
+                const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * cc);
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    const float gv = dv == 0 ? g4[r].x : dv == 1 ? g4[r].y : dv == 2 ? g4[r].z : g4[r].w;
+                    const float2 gg = make_float2(gv, gv);
+                    acc[r][2 * cc] = ffma2(make_float2(w.x, w.y), gg, acc[r][2 * cc]);
+                    acc[r][2 * cc + 1] = ffma2(make_float2(w.z, w.w), gg, acc[r][2 * cc + 1]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RP; ++r)
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) {
+            out[r][2 * c] = acc[r][c].x;
+            out[r][2 * c + 1] = acc[r][c].y;
+        }
+}
+
+enum FastMode { FAST_FWD = 0, FAST_GRAD = 1 };
+
+// Relative offsets (floats / ints) of the sections inside one transform's staged block.
+struct FastRel {
+    int W0t, b1, W1, ld1, WoT, bo;                  // floats, relative to t.W0t
+    int perm, permy, deg0, pre1, grp0, grp1, first1; // ints, relative to t.perm
+};
+
+template <int MODE, int RP, int DP>
+__global__ void __launch_bounds__(256, 1) k_fast(const MafImg g, const FastArgs a, const FastRel rel) {
+    extern __shared__ __align__(16) float sm[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int K = g.K, D = g.D, H0 = g.H[0], H1 = g.H[1];
+    const int WL = (g.Hmax + 31) >> 5;
+    float* Ws = sm;
+    int* Ms = reinterpret_cast<int*>(Ws + a.wfloats);
+    float* gAt = reinterpret_cast<float*>(Ms + a.wints);                    // [H0][TBp]  (GRAD only)
+    float* act = gAt + (MODE == FAST_GRAD ? (((size_t)H0 * a.TBp + 3) & ~(size_t)3) : 0);  // [RP*T][AS], 16-B aligned
+    float* vec = act + (size_t)RP * T * a.AS;                               // [RP*T][VS]
+    uint32_t* bits = reinterpret_cast<uint32_t*>(vec + (size_t)RP * T * a.VS);  // [RP*T][BWS] (GRAD only)
+
+    const float* W0t = Ws + rel.W0t;
+    const float* b1 = Ws + rel.b1;
+    const float* W1 = Ws + rel.W1;
+    const float* WoT = Ws + rel.WoT;   // [H1][2*DP]: m-weights of positions 0..DP-1, then s-weights
+    const float* bo = Ws + rel.bo;     // [2*DP]
+    const int ld1 = rel.ld1;
+    const int* perm = Ms + rel.perm;
+    const int* permy = Ms + rel.permy;
+    const int* pre1 = Ms + rel.pre1;
+    const int* grp0 = Ms + rel.grp0;
+    const int* grp1 = Ms + rel.grp1;
+    const int* first1 = Ms + rel.first1;
+
+    float* actp[RP];
+    float* vecp[RP];
+    uint32_t* bitp[RP];
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+        const int slot = tid + r * T;
+        actp[r] = act + (size_t)slot * a.AS;
+        vecp[r] = vec + (size_t)slot * a.VS;
+        bitp[r] = bits + (size_t)slot * a.BWS;
+        for (int i = 0; i < a.AS; ++i) actp[r][i] = 0.f;
+    }
+    // vec slots (floats)
+    const int oV = 0;                 // v_k, k = 0..K     (variable space)
+    const int oU = (K + 1) * D;       // u_k, k = 0..K-1
+    const int oSHP = (2 * K + 1) * D; // clamped log-scales, sampling pass (order space)
+    const int oSHQ = (3 * K + 1) * D; // clamped log-scales, density pass
+    const int oG = (4 * K + 1) * D;   // running cotangent (variable space)
+    const float HALF_LOG_2PI = 0.91893853320467274178f;
+
+    int resident = -1;
+    auto ensure_weights = [&](int k) {
+        if (resident == k) return;
+        __syncthreads();
+        const float4* src = reinterpret_cast<const float4*>(g.f + g.t[k].W0t);
+        float4* dst = reinterpret_cast<float4*>(Ws);
+        const int n4 = a.wfloats >> 2;
+        for (int i = tid; i < n4; i += T) dst[i] = __ldg(src + i);
+        const int* msrc = g.m + g.t[k].perm;
+        for (int i = tid; i < a.wints; i += T) Ms[i] = __ldg(msrc + i);
+        __syncthreads();
+        resident = k;
+    };
+
+    // ---- building blocks ------------------------------------------------------------------------------
+    // layer-0 units [ua, ub): act = relu(A[u] + W0t[u] . y); records ReLU bits into running words w0
+    auto layer0 = [&](int ua, int ub, const float* const (&Aptr)[RP], const bool (&live)[RP],
+                      const float (&y)[RP][DP], uint32_t (&w0)[RP], int bslot) {
+        for (int u = ua; u < ub; ++u) {
+            float wrow[DP];
+#pragma unroll
+            for (int q4 = 0; q4 < DP / 4; ++q4) {
+                const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
+                wrow[4 * q4] = w.x; wrow[4 * q4 + 1] = w.y; wrow[4 * q4 + 2] = w.z; wrow[4 * q4 + 3] = w.w;
+            }
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                float pre = live[r] ? __ldg(Aptr[r] + (size_t)u * a.B) : 0.f;
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) pre = fmaf(wrow[jj], y[r][jj], pre);
+                const bool on = pre > 0.f;
+                actp[r][u] = on ? pre : 0.f;
+                if (MODE == FAST_GRAD) {
+                    if (on) w0[r] |= 1u << (u & 31);
+                    if ((u & 31) == 31 || u == H0 - 1) {
+                        bitp[r][bslot * WL + (u >> 5)] = w0[r];
+                        w0[r] = 0u;
+                    }
+                }
+            }
+        }
+    };
+
+    // layer-1 units [va, vb) with common prefix e (rounded up to 4) -> ReLU bits + output accumulators
+    auto layer1_block = [&](auto NRtag, int v0, int nv, int e4, float (&om)[RP][DP], float (&os)[RP][DP],
+                            uint32_t (&w1)[RP], int bslot) {
+        constexpr int NR = decltype(NRtag)::value;
+        float h[RP][NR];
+        dot_block<RP, NR>(W1 + (size_t)v0 * ld1, ld1, nv - 1, e4, actp, h);
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+            if (c < nv) {
+                const int v = v0 + c;
+                const float bias = b1[v];
+                const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
+                float wm[DP], ws[DP];
+#pragma unroll
+                for (int q4 = 0; q4 < DP / 4; ++q4) {
+                    const float4 m4 = wo[q4], s4 = wo[DP / 4 + q4];
+                    wm[4 * q4] = m4.x; wm[4 * q4 + 1] = m4.y; wm[4 * q4 + 2] = m4.z; wm[4 * q4 + 3] = m4.w;
+                    ws[4 * q4] = s4.x; ws[4 * q4 + 1] = s4.y; ws[4 * q4 + 2] = s4.z; ws[4 * q4 + 3] = s4.w;
+                }
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    const float val = h[r][c] + bias;
+                    const bool on = val > 0.f;
+                    const float hv = on ? val : 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < DP; ++jj) {
+                        om[r][jj] = fmaf(wm[jj], hv, om[r][jj]);
+                        os[r][jj] = fmaf(ws[jj], hv, os[r][jj]);
+                    }
+                    if (MODE == FAST_GRAD) {
+                        if (on) w1[r] |= 1u << (v & 31);
+                        if ((v & 31) == 31 || v == H1 - 1) {
+                            bitp[r][bslot * WL + (v >> 5)] = w1[r];
+                            w1[r] = 0u;
+                        }
+                    }
+                }
+            }
+        }
+    };
+    auto layer1_range = [&](int va, int vb, int e4, float (&om)[RP][DP], float (&os)[RP][DP], uint32_t (&w1)[RP],
+                            int bslot) {
+        int v = va;
+        for (; v + 16 <= vb; v += 16) layer1_block(std::integral_constant<int, 16>{}, v, 16, e4, om, os, w1, bslot);
+        if (v + 8 <= vb) { layer1_block(std::integral_constant<int, 8>{}, v, 8, e4, om, os, w1, bslot); v += 8; }
+        if (v + 4 <= vb) { layer1_block(std::integral_constant<int, 4>{}, v, 4, e4, om, os, w1, bslot); v += 4; }
+        if (v < vb) layer1_block(std::integral_constant<int, 4>{}, v, vb - v, e4, om, os, w1, bslot);
+    };
+
+    // layer-1 cotangents of units [va, vb): g = relu'(.) * (WoT[v] . (mbar, sbar)) -> buffer
+    auto layer1_cot = [&](int va, int vb, const float (&mb)[RP][DP], const float (&sb)[RP][DP], int bslot) {
+        for (int v = va; v < vb; ++v) {
+            const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
+            float wm[DP], ws[DP];
+#pragma unroll
+            for (int q4 = 0; q4 < DP / 4; ++q4) {
+                const float4 m4 = wo[q4], s4 = wo[DP / 4 + q4];
+                wm[4 * q4] = m4.x; wm[4 * q4 + 1] = m4.y; wm[4 * q4 + 2] = m4.z; wm[4 * q4 + 3] = m4.w;
+                ws[4 * q4] = s4.x; ws[4 * q4 + 1] = s4.y; ws[4 * q4 + 2] = s4.z; ws[4 * q4 + 3] = s4.w;
+            }
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                float gsum = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) gsum = fmaf(ws[jj], sb[r][jj], fmaf(wm[jj], mb[r][jj], gsum));
+                const bool on = (bitp[r][bslot * WL + (v >> 5)] >> (v & 31)) & 1u;
+                actp[r][v] = on ? gsum : 0.f;
+            }
+        }
+    };
+
+    // layer-0 cotangents of the aligned column block [u0, u0+NC) restricted to units [ua, ub):
+    // g0 = relu'(.) * sum_{v in [va4, vb4)} W1[v][u] g1[v];  ybar += W0t[u]^T g0;  gA tile += g0
+    auto layer0_cot_block = [&](auto NCtag, int u0, int ua, int ub, int va4, int vb4, float (&yb)[RP][DP], int bslot,
+                                const bool (&live)[RP], const int (&rrow)[RP], bool want_gA) {
+        constexpr int NC = decltype(NCtag)::value;
+        float g0[RP][NC];
+        tdot_block<RP, NC>(W1 + u0, ld1, va4, vb4, actp, g0);
+        uint32_t wb[RP];
+#pragma unroll
+        for (int r = 0; r < RP; ++r) wb[r] = bitp[r][bslot * WL + (u0 >> 5)] >> (u0 & 31);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int u = u0 + c;
+            if (u >= ua && u < ub) {
+                float wrow[DP];
+#pragma unroll
+                for (int q4 = 0; q4 < DP / 4; ++q4) {
+                    const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
+                    wrow[4 * q4] = w.x; wrow[4 * q4 + 1] = w.y; wrow[4 * q4 + 2] = w.z; wrow[4 * q4 + 3] = w.w;
+                }
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    const float gv = ((wb[r] >> c) & 1u) ? g0[r][c] : 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < DP; ++jj) yb[r][jj] = fmaf(wrow[jj], gv, yb[r][jj]);
+                    if (want_gA && live[r]) atomicAdd(gAt + (size_t)u * a.TBp + rrow[r], gv);
+                }
+            }
+        }
+    };
+    auto layer0_cot_range = [&](int ua, int ub, int va4, int vb4, float (&yb)[RP][DP], int bslot,
+                                const bool (&live)[RP], const int (&rrow)[RP], bool want_gA) {
+        int u = ua & ~3;
+        const int uend = (ub + 3) & ~3;
+        // 16-wide blocks must not straddle a 32-bit mask word: u % 16 == 0 is not guaranteed, 4-alignment is;
+        // use 16 only when the block stays inside one word
+        while (u < uend) {
+            const int left = uend - u;
+            if (left >= 16 && ((u & 31) + 16 <= 32)) {
+                layer0_cot_block(std::integral_constant<int, 16>{}, u, ua, ub, va4, vb4, yb, bslot, live, rrow, want_gA);
+                u += 16;
+            } else if (left >= 8 && ((u & 31) + 8 <= 32)) {
+                layer0_cot_block(std::integral_constant<int, 8>{}, u, ua, ub, va4, vb4, yb, bslot, live, rrow, want_gA);
+                u += 8;
+            } else {
+                layer0_cot_block(std::integral_constant<int, 4>{}, u, ua, ub, va4, vb4, yb, bslot, live, rrow, want_gA);
+                u += 4;
+            }
+        }
+    };
+
+    // -------------------------------------------------------------------------------------------------------
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        bool live[RP];
+        int rrow[RP];                 // row inside the tile (GRAD)
+        long long pidx[RP];           // flat pair index s*B + b
+        const float* Ap[RP];
+        const float* Aq[RP];
+        int rows_here = 0, b0 = 0;
+        if (MODE == FAST_GRAD) {
+            b0 = tile * a.TB;
+            rows_here = min(a.TB, a.B - b0);
+        }
+#pragma unroll
+        for (int r = 0; r < RP; ++r) {
+            const int q = tid + r * T;
+            if (MODE == FAST_GRAD) {
+                live[r] = q < rows_here * a.S;
+                const int s = live[r] ? q / rows_here : 0;
+                rrow[r] = live[r] ? q % rows_here : 0;
+                pidx[r] = (long long)s * a.B + b0 + rrow[r];
+            } else {
+                const long long p = (long long)tile * a.NP + q;
+                live[r] = q < a.NP && p < (long long)a.S * a.B;
+                pidx[r] = live[r] ? p : 0;
+                rrow[r] = 0;
+            }
+            const int b = (int)(pidx[r] % a.B);
+            Ap[r] = a.A_p + b;
+            Aq[r] = a.A_q + b;
+        }
+        if (MODE == FAST_GRAD) {
+            __syncthreads();
+            for (int i = tid; i < H0 * a.TBp; i += T) gAt[i] = 0.f;
+        }
+        float logp[RP], logq[RP];
+#pragma unroll
+        for (int r = 0; r < RP; ++r) {
+            float ssq = 0.f;
+            for (int d = 0; d < D; ++d) {
+                const float zv = live[r] ? a.z[(size_t)pidx[r] * D + d] : 0.f;
+                vecp[r][oV + d] = zv;
+                ssq = fmaf(zv, zv, ssq);
+            }
+            logp[r] = -0.5f * ssq - (float)D * HALF_LOG_2PI;
+            logq[r] = 0.f;
+        }
+
+        // ================= sampling chain under A_p =================
+        for (int k = 0; k < K; ++k) {
+            ensure_weights(k);
+            const float* Aptr[RP];
+            float zos[RP][DP], y[RP][DP], om[RP][DP], os[RP][DP];
+            uint32_t w0[RP], w1[RP];
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                Aptr[r] = Ap[r] + (size_t)k * H0 * a.B;
+                w0[r] = w1[r] = 0u;
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) {
+                    zos[r][jj] = jj < D ? vecp[r][oV + k * D + perm[jj]] : 0.f;
+                    y[r][jj] = 0.f;
+                    om[r][jj] = jj < D ? bo[jj] : 0.f;
+                    os[r][jj] = jj < D ? bo[DP + jj] : 0.f;
+                }
+            }
+            const int bs = (0 * K + k) * 2;
+            for (int j = 0; j < D; ++j) {
+                layer0(grp0[j], grp0[j + 1], Aptr, live, y, w0, bs);
+                layer1_range(grp1[j], grp1[j + 1], (grp0[j + 1] + 3) & ~3, om, os, w1, bs + 1);
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    float m = 0.f, s = 0.f, zj = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < DP; ++jj) {
+                        m = jj == j ? om[r][jj] : m;
+                        s = jj == j ? os[r][jj] : s;
+                        zj = jj == j ? zos[r][jj] : zj;
+                    }
+                    const float sh = fminf(fmaxf(s, g.lo), g.hi);
+                    const float yj = (zj - m) * expf(-sh);
+#pragma unroll
+                    for (int jj = 0; jj < DP; ++jj) y[r][jj] = jj == j ? yj : y[r][jj];
+                    logp[r] += sh;
+                    vecp[r][oSHP + k * D + j] = sh;
+                    vecp[r][oV + (k + 1) * D + permy[j]] = yj;
+                }
+            }
+        }
+
+        // ================= density chain under A_q =================
+        for (int k = K - 1; k >= 0; --k) {
+            ensure_weights(k);
+            const float* Aptr[RP];
+            float y[RP][DP], om[RP][DP], os[RP][DP];
+            uint32_t w0[RP], w1[RP];
+            const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                Aptr[r] = Aq[r] + (size_t)k * H0 * a.B;
+                w0[r] = w1[r] = 0u;
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) {
+                    y[r][jj] = jj < D ? vecp[r][src + permy[jj]] : 0.f;
+                    om[r][jj] = jj < D ? bo[jj] : 0.f;
+                    os[r][jj] = jj < D ? bo[DP + jj] : 0.f;
+                }
+            }
+            const int bs = (1 * K + k) * 2;
+            layer0(0, H0, Aptr, live, y, w0, bs);
+            for (int j = 0; j < D; ++j)  // blocks never straddle degree groups: one common prefix per call
+                layer1_range(grp1[j], grp1[j + 1], (grp0[j + 1] + 3) & ~3, om, os, w1, bs + 1);
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) {
+                    if (jj < D) {
+                        const float sh = fminf(fmaxf(os[r][jj], g.lo), g.hi);
+                        vecp[r][oSHQ + k * D + jj] = sh;
+                        logq[r] += sh;
+                        vecp[r][oU + k * D + perm[jj]] = fmaf(expf(sh), y[r][jj], om[r][jj]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RP; ++r) {
+            float ssq = 0.f;
+            for (int d = 0; d < D; ++d) {
+                const float u = vecp[r][oU + d];
+                ssq = fmaf(u, u, ssq);
+            }
+            logq[r] += -0.5f * ssq - (float)D * HALF_LOG_2PI;
+            if (a.diff && live[r]) a.diff[pidx[r]] = logp[r] - logq[r];
+        }
+        if (MODE != FAST_GRAD) continue;
+
+        // ================= reverse mode =================
+        const float w = a.w;
+#pragma unroll
+        for (int r = 0; r < RP; ++r)
+            for (int d = 0; d < D; ++d) vecp[r][oG + d] = w * vecp[r][oU + d];  // d(-w log q)/d u_0
+        for (int k = 0; k < K; ++k) {
+            ensure_weights(k);
+            const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
+            float mb[RP][DP], sb[RP][DP], yb[RP][DP];
+#pragma unroll
+            for (int r = 0; r < RP; ++r)
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) {
+                    if (jj < D) {
+                        const float ub = vecp[r][oG + perm[jj]];
+                        const float es = expf(vecp[r][oSHQ + k * D + jj]);
+                        const float yin = vecp[r][src + permy[jj]];
+                        mb[r][jj] = ub;
+                        sb[r][jj] = fmaf(ub * es, yin, -w);
+                        yb[r][jj] = ub * es;
+                    } else {
+                        mb[r][jj] = sb[r][jj] = yb[r][jj] = 0.f;
+                    }
+                }
+            const int bs = (1 * K + k) * 2;
+            layer1_cot(0, H1, mb, sb, bs + 1);
+            for (int j = 0; j < D; ++j) {  // layer-0 units of degree j are consumed by layer-1 rows >= grp1[j]
+                const int ua = grp0[j], ub = grp0[j + 1];
+                if (ua < ub) layer0_cot_range(ua, ub, grp1[j] & ~3, (H1 + 3) & ~3, yb, bs, live, rrow, false);
+            }
+#pragma unroll
+            for (int r = 0; r < RP; ++r)
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj)
+                    if (jj < D) vecp[r][oG + permy[jj]] = yb[r][jj];
+        }
+        for (int k = K - 1; k >= 0; --k) {
+            ensure_weights(k);
+            float yb[RP][DP], yv[RP][DP], sh[RP][DP], mb[RP][DP], sb[RP][DP], zb[RP][DP];
+#pragma unroll
+            for (int r = 0; r < RP; ++r)
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) {
+                    yb[r][jj] = jj < D ? vecp[r][oG + permy[jj]] : 0.f;
+                    yv[r][jj] = jj < D ? vecp[r][oV + (k + 1) * D + permy[jj]] : 0.f;
+                    sh[r][jj] = jj < D ? vecp[r][oSHP + k * D + jj] : 0.f;
+                    mb[r][jj] = sb[r][jj] = zb[r][jj] = 0.f;
+                }
+            const int bs = (0 * K + k) * 2;
+            for (int j = D - 1; j >= 0; --j) {
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    float ybj = 0.f, shj = 0.f, yj = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < DP; ++jj) {
+                        ybj = jj == j ? yb[r][jj] : ybj;
+                        shj = jj == j ? sh[r][jj] : shj;
+                        yj = jj == j ? yv[r][jj] : yj;
+                    }
+                    const float zbj = ybj * expf(-shj);
+#pragma unroll
+                    for (int jj = 0; jj < DP; ++jj) {
+                        zb[r][jj] = jj == j ? zbj : zb[r][jj];
+                        mb[r][jj] = jj == j ? -zbj : mb[r][jj];
+                        sb[r][jj] = jj == j ? fmaf(-ybj, yj, w) : sb[r][jj];
+                    }
+                }
+                layer1_cot(grp1[j], grp1[j + 1], mb, sb, bs + 1);
+                const int ua = grp0[j], ub = grp0[j + 1];
+                if (ua < ub) layer0_cot_range(ua, ub, grp1[j] & ~3, (H1 + 3) & ~3, yb, bs, live, rrow, true);
+            }
+#pragma unroll
+            for (int r = 0; r < RP; ++r)
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj)
+                    if (jj < D) vecp[r][oG + perm[jj]] = zb[r][jj];
+            // flush the gA tile of this transform (rows of this tile are owned by this CTA alone)
+            __syncthreads();
+            for (int i = tid; i < H0 * rows_here; i += T) {
+                const int u = i / rows_here, rr = i % rows_here;
+                a.gA[((size_t)k * H0 + u) * a.B + b0 + rr] = gAt[(size_t)u * a.TBp + rr];
+                gAt[(size_t)u * a.TBp + rr] = 0.f;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace rabi

@@ -22,6 +22,10 @@ struct TImg {
     int b0;        // [H0p+4]
     int W[RABI_MAXL], ld[RABI_MAXL], b[RABI_MAXL];  // hidden layer l = 1..L-1: [Hlp+4][ld[l]]
     int Wo, ldo, bo;                                // [2D (+pad)][ldo]: row j = mean, row D+j = log-scale of position j
+    int WoT, boF;   // unit-major copy of the output layer for k_fast: WoT[v][0..ldt) = mean weights of the positions,
+                    // WoT[v][ldt..2ldt) = log-scale weights; boF[0..ldt) / boF[ldt..2ldt) the biases
+    int fast_end;   // end (floats) of the contiguous block [W0t, fast_end) staged by k_fast
+    int meta_fast_end;  // end (ints) of the contiguous index block [perm, meta_fast_end) staged by k_fast
     // int offsets into MafImg::m
     int perm;             // [D]   variable index of position j on the base-noise side (input of T_k)
     int permy;            // [D]   index of position j on the theta side (output of T_k, after an optional

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -11,6 +12,7 @@
 #include "../../include/rabi_b200.h"
 #include "maf_image.h"
 #include "maf_pairs.cuh"
+#include "maf_fast.cuh"
 
 using namespace rabi;
 
@@ -209,14 +211,18 @@ extern "C" int rabi_maf_finalize_structure(rabi_maf_t* h) {
         const std::vector<int64_t>& perm = h->perm[k];
         t.ldc = round4(C);
         t.W0c = falloc((size_t)(H0p + 4) * t.ldc);
+        // [fast block: W0t, b[1], W[1], WoT, boF] is contiguous so that k_fast stages it with one copy
         t.ldt = round4(D);
         t.W0t = falloc((size_t)(H0p + 4) * t.ldt);
-        t.b0 = falloc(H0p + 4);
         for (int l = 1; l < L; ++l) {
             t.ld[l] = round4(h->H[l - 1]);
-            t.W[l] = falloc((size_t)(round4(h->H[l]) + 4) * t.ld[l]);
             t.b[l] = falloc(round4(h->H[l]) + 4);
+            t.W[l] = falloc((size_t)(round4(h->H[l]) + 4) * t.ld[l]);
         }
+        t.WoT = falloc((size_t)(round4(h->H[L - 1]) + 4) * 2 * t.ldt);
+        t.boF = falloc(2 * t.ldt);
+        t.fast_end = (int)nf;
+        t.b0 = falloc(H0p + 4);
         t.ldo = round4(h->H[L - 1]);
         t.Wo = falloc((size_t)(round4(2 * D) + 4) * t.ldo);
         t.bo = falloc(round4(2 * D) + 4);
@@ -305,6 +311,7 @@ extern "C" int rabi_maf_finalize_structure(rabi_maf_t* h) {
         {
             const int HL = h->H[L - 1];
             const std::vector<float>& m = h->masks[k][L];
+            t.meta_fast_end = (int)meta.size();
             t.preo = ialloc(D);
             for (int j = 0; j < D; ++j) {
                 int e = meta[t.grp[L - 1] + j + 1];
@@ -380,8 +387,13 @@ __global__ void k_pack_out(MafImg g, int k, const float* __restrict__ W, const f
     int r = idx / HL, v = idx % HL;
     int half = r / D, j = r % D;
     int src = half * D + g.m[t.perm + j];
-    f[t.Wo + (size_t)r * t.ldo + v] = (v < g.m[t.preo + j]) ? W[(size_t)src * HL + v] : 0.f;
-    if (v == 0) f[t.bo + r] = b[src];
+    const float wv = (v < g.m[t.preo + j]) ? W[(size_t)src * HL + v] : 0.f;
+    f[t.Wo + (size_t)r * t.ldo + v] = wv;
+    f[t.WoT + (size_t)v * 2 * t.ldt + half * t.ldt + j] = wv;
+    if (v == 0) {
+        f[t.bo + r] = b[src];
+        f[t.boF + half * t.ldt + j] = b[src];
+    }
 }
 
 #define REQUIRE_READY(h)                                                               \
@@ -725,6 +737,121 @@ extern "C" int rabi_maf_rsample_fwd(rabi_maf_t* h, const float* A_dev, const flo
     return launch_pairs<MODE_RSAMPLE>(h, a, (cudaStream_t)s);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// fast path launcher (maf_fast.cuh).  Returns 0 = launched, 1 = error, 2 = configuration not eligible (caller
+// falls back to the generic per-pair kernel).
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int MODE, int RP, int DP>
+static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel, int grid, int T, size_t smem,
+                            cudaStream_t st) {
+    CU_OK(h, cudaFuncSetAttribute(k_fast<MODE, RP, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = h->profiling && MODE == FAST_GRAD;
+    if (prof) {
+        if (h->prof_used == h->prof_events.size()) {
+            cudaEvent_t e0, e1;
+            CU_OK(h, cudaEventCreate(&e0));
+            CU_OK(h, cudaEventCreate(&e1));
+            h->prof_events.push_back({e0, e1});
+        }
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].first, st));
+    }
+    k_fast<MODE, RP, DP><<<grid, T, smem, st>>>(h->img, fa, rel);
+    LAUNCH_CHECK(h);
+    if (prof) {
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].second, st));
+        h->prof_used++;
+    }
+    return 0;
+}
+
+template <int MODE>
+static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
+    if (env_int("RABI_DISABLE_FAST", 0)) return 2;
+    if (h->L != 2 || h->D > 12) return 2;
+    const MafImg& g = h->img;
+    const TImg& t0 = g.t[0];
+    const int K = h->K, D = h->D, H0 = h->H[0], H1 = h->H[1];
+    const int DP = round4(D);
+    FastRel rel;
+    rel.W0t = 0;
+    rel.b1 = t0.b[1] - t0.W0t;
+    rel.W1 = t0.W[1] - t0.W0t;
+    rel.ld1 = t0.ld[1];
+    rel.WoT = t0.WoT - t0.W0t;
+    rel.bo = t0.boF - t0.W0t;
+    rel.perm = 0;
+    rel.permy = t0.permy - t0.perm;
+    rel.deg0 = t0.deg0 - t0.perm;
+    rel.pre1 = t0.pre[1] - t0.perm;
+    rel.grp0 = t0.grp[0] - t0.perm;
+    rel.grp1 = t0.grp[1] - t0.perm;
+    rel.first1 = t0.first[1] - t0.perm;
+    fa.wfloats = t0.fast_end - t0.W0t;
+    fa.wints = (t0.meta_fast_end - t0.perm + 3) & ~3;
+    int AS = std::max(round4(H0), round4(H1)) + 4;
+    if (((AS / 4) & 1) == 0) AS += 4;  // AS/4 odd: 128-bit accesses of consecutive slots hit distinct bank groups
+    fa.AS = AS;
+    fa.VS = ((4 * K + 2) * D) | 1;
+    const int WL = (g.Hmax + 31) / 32;
+    fa.BWS = MODE == FAST_GRAD ? ((2 * K * 2 * WL) | 1) : 0;
+    const int RP = env_int("RABI_FAST_RP", 2) == 1 ? 1 : 2;
+    const size_t per_slot = (size_t)(fa.AS + fa.VS + fa.BWS) * sizeof(float);
+    const size_t fixed = (size_t)(fa.wfloats + fa.wints) * sizeof(float);
+    const size_t budget = (size_t)h->max_smem_optin - 1024;
+    int T = env_int("RABI_FAST_T", 256);
+    T = std::max(32, std::min(256, (T / 32) * 32));
+    int grid = 0;
+    size_t smem = 0;
+    const long long npairs = (long long)fa.S * fa.B;
+    if (MODE == FAST_GRAD) {
+        // largest T whose slots (+ the gA tile for the rows they hold) fit
+        for (;; T -= 32) {
+            if (T < 32) return 2;
+            int slots = RP * T;
+            int tb = slots / fa.S;
+            if (tb < 1) return 2;  // one row's samples do not fit in a tile
+            fa.TBp = tb | 1;
+            smem = fixed + (((size_t)H0 * fa.TBp + 3) & ~(size_t)3) * sizeof(float) + (size_t)slots * per_slot;
+            if (smem <= budget) break;
+        }
+        int tb_cap = (RP * T) / fa.S;
+        int ntiles = (fa.B + tb_cap - 1) / tb_cap;
+        int waves = (ntiles + h->sm_count - 1) / h->sm_count;
+        int want = std::min(fa.B, waves * h->sm_count);           // balanced: every SM gets `waves` tiles
+        fa.TB = std::min(tb_cap, (fa.B + want - 1) / want);
+        fa.ntiles = (fa.B + fa.TB - 1) / fa.TB;
+        int Tneed = ((fa.TB * fa.S + RP - 1) / RP + 31) & ~31;     // no idle warps
+        T = std::min(T, std::max(32, Tneed));
+        fa.TBp = fa.TB | 1;
+        smem = fixed + (((size_t)H0 * fa.TBp + 3) & ~(size_t)3) * sizeof(float) + (size_t)RP * T * per_slot;
+        grid = std::min(fa.ntiles, h->sm_count);
+    } else {
+        for (;; T -= 32) {
+            if (T < 32) return 2;
+            smem = fixed + (size_t)RP * T * per_slot;
+            if (smem <= budget) break;
+        }
+        fa.NP = RP * T;
+        fa.TBp = 0;
+        long long nt = (npairs + fa.NP - 1) / fa.NP;
+        if (nt > 0x7fffffff) return 2;
+        fa.ntiles = (int)nt;
+        grid = (int)std::min<long long>(nt, h->sm_count);
+    }
+#define RABI_FAST_CASE(RPv, DPv) \
+    if (RP == RPv && DP == DPv) return launch_fast_inst<MODE, RPv, DPv>(h, fa, rel, grid, T, smem, st);
+    RABI_FAST_CASE(2, 4)
+    RABI_FAST_CASE(2, 8)
+    RABI_FAST_CASE(2, 12)
+    RABI_FAST_CASE(1, 4)
+#undef RABI_FAST_CASE
+    return 2;
+}
+
 extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_q_dev, const float* z_dev, int S, int B,
                             float* kl_dev, rabi_stream_t s) {
     REQUIRE_READY(h);
@@ -738,7 +865,18 @@ extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_
     a.out_lp = (float*)h->ws;
     a.S = S;
     a.B = B;
-    if (launch_pairs<MODE_RKL_FWD>(h, a, st)) return 1;
+    {
+        FastArgs fa = {};
+        fa.A_p = A_p_dev;
+        fa.A_q = A_q_dev;
+        fa.z = z_dev;
+        fa.diff = (float*)h->ws;
+        fa.S = S;
+        fa.B = B;
+        int rc = launch_fast<FAST_FWD>(h, fa, st);
+        if (rc == 1) return 1;
+        if (rc == 2 && launch_pairs<MODE_RKL_FWD>(h, a, st)) return 1;
+    }
     k_mean_over_s<<<(B + 127) / 128, 128, 0, st>>>((const float*)h->ws, S, B, kl_dev);
     LAUNCH_CHECK(h);
     return 0;
@@ -754,17 +892,30 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
     float* gx = gA + nA;
     float* diff = gx + (size_t)B * h->C;
     if (launch_ctx_project(h, x, delta, zm, zs, B, A_p, st)) return 1;
-    CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
-    PairArgs a = {};
-    a.A_p = A_p;
-    a.A_q = A_q;
-    a.in = z;
-    a.out_lp = kl ? diff : nullptr;
-    a.gA = gA;
-    a.S = S;
-    a.B = B;
-    a.w = inv_B / (float)S;
-    if (launch_pairs<MODE_RKL_GRAD>(h, a, st)) return 1;
+    FastArgs fa = {};
+    fa.A_p = A_p;
+    fa.A_q = A_q;
+    fa.z = z;
+    fa.diff = kl ? diff : nullptr;
+    fa.gA = gA;
+    fa.S = S;
+    fa.B = B;
+    fa.w = inv_B / (float)S;
+    int rc = launch_fast<FAST_GRAD>(h, fa, st);
+    if (rc == 1) return 1;
+    if (rc == 2) {  // generic per-pair kernel (accumulates gA with atomics)
+        CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
+        PairArgs a = {};
+        a.A_p = A_p;
+        a.A_q = A_q;
+        a.in = z;
+        a.out_lp = kl ? diff : nullptr;
+        a.gA = gA;
+        a.S = S;
+        a.B = B;
+        a.w = inv_B / (float)S;
+        if (launch_pairs<MODE_RKL_GRAD>(h, a, st)) return 1;
+    }
     if (launch_ctx_project_bwd(h, gA, zs, B, gx, 0, st)) return 1;
     if (!delta) {  // gradient-only mode (rabi_rkl_input_grad)
         if (kl) {
