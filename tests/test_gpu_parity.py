@@ -4,7 +4,8 @@
 import pytest
 import torch
 
-from tests.util import CASES, RTOL, build_oracle, build_product, load_golden, rel_err
+from tests.util import (CASES, RTOL, assert_trajectories_match, build_oracle, build_product, load_golden,
+                        rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -97,7 +98,7 @@ def test_l2pgd_matches_reference(case, dev, n_it):
         xa = atk.perturb(x, delta_init=p["delta0"].to(dev))
     ref = p[f"x_adv_{n_it}"]
     # compare the perturbations (x~ - x), relative to their size
-    assert rel_err(xa.cpu() - g["x"], ref - g["x"]) < (RTOL if n_it <= 5 else 5 * RTOL)
+    assert_trajectories_match(xa.cpu() - g["x"], ref - g["x"], RTOL if n_it <= 5 else 5 * RTOL)
     assert float((xa.cpu() - g["x"]).norm(dim=-1).max()) <= p["eps"] * (1 + 1e-5)
     assert float(xa.min()) >= p["clip_min"] - 1e-6 and float(xa.max()) <= p["clip_max"] + 1e-6
 
@@ -156,7 +157,7 @@ def test_full_shape_pipeline_vs_oracle(shape, dev):
                       clip_min=cmin, clip_max=cmax)
     with noise.injected(zs):
         xa = atk.perturb(x.to(dev), delta_init=d0.to(dev))
-    assert rel_err(xa.cpu() - x, xa_ref - x) < 2 * RTOL
+    assert_trajectories_match(xa.cpu() - x, xa_ref - x, 2 * RTOL)
     with torch.no_grad(), noise.injected([z_eval]):
         kl = ReverseKLLoss(mc_samples=S_eval, reduction=None)(model(xa_ref.to(dev)), model(x.to(dev)))
     with torch.no_grad():

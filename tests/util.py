@@ -26,6 +26,26 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a[finite] - b[finite]).abs().max() / scale)
 
 
+def row_rel_err(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """per-row ||a - b|| / ||b||"""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).norm(dim=-1) / b.norm(dim=-1).clamp_min(1e-30)
+
+
+def assert_trajectories_match(delta, delta_ref, tol, max_flip_frac=0.05):
+    """Multi-step PGD perturbations, compared per observation row.
+
+    A ReLU network is only piecewise smooth: when a pre-activation lands within rounding distance of 0 (observed:
+    |pre| = 4.8e-8 against a typical row minimum of 1.6e-5), ANY change of fp32 summation order flips that unit's
+    mask, the input gradient jumps and that row's trajectory departs by O(1e-2) while every other row agrees to
+    O(1e-6).  Such events are inherent to fp32 (the reference on a different BLAS shows them too), so a small
+    fraction of rows may deviate; all other rows must meet the tolerance and the typical error must be tiny."""
+    e = row_rel_err(delta, delta_ref)
+    n_bad = int((e > tol).sum())
+    assert n_bad <= max(1, int(max_flip_frac * e.numel())), f"{n_bad}/{e.numel()} rows differ by more than {tol}: {e.max():.3e}"
+    assert float(e.median()) < tol / 10, float(e.median())
+
+
 def load_golden(name):
     g = torch.load(os.path.join(GOLDEN, f"{name}.pt"), weights_only=False)
     g["state_dict"] = {k: (v.float() if v.dtype == torch.bool else v) for k, v in g["state_dict"].items()}
