@@ -129,7 +129,7 @@ struct FastRel {
 };
 
 template <int MODE, int RP, int DP>
-__global__ void __launch_bounds__(256, 1) k_fast(const MafImg g, const FastArgs a, const FastRel rel) {
+__global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g, const FastArgs a, const FastRel rel) {
     extern __shared__ __align__(16) float sm[];
     const int T = blockDim.x, tid = threadIdx.x;
     const int K = g.K, D = g.D, H0 = g.H[0], H1 = g.H[1];
@@ -149,10 +149,8 @@ __global__ void __launch_bounds__(256, 1) k_fast(const MafImg g, const FastArgs 
     const int ld1 = rel.ld1;
     const int* perm = Ms + rel.perm;
     const int* permy = Ms + rel.permy;
-    const int* pre1 = Ms + rel.pre1;
     const int* grp0 = Ms + rel.grp0;
     const int* grp1 = Ms + rel.grp1;
-    const int* first1 = Ms + rel.first1;
 
     float* actp[RP];
     float* vecp[RP];
@@ -177,165 +175,24 @@ __global__ void __launch_bounds__(256, 1) k_fast(const MafImg g, const FastArgs 
     auto ensure_weights = [&](int k) {
         if (resident == k) return;
         __syncthreads();
-        const float4* src = reinterpret_cast<const float4*>(g.f + g.t[k].W0t);
-        float4* dst = reinterpret_cast<float4*>(Ws);
-        const int n4 = a.wfloats >> 2;
-        for (int i = tid; i < n4; i += T) dst[i] = __ldg(src + i);
-        const int* msrc = g.m + g.t[k].perm;
-        for (int i = tid; i < a.wints; i += T) Ms[i] = __ldg(msrc + i);
+        {
+            const float4* src = reinterpret_cast<const float4*>(g.f + g.t[k].W0t);
+            float4* dst = reinterpret_cast<float4*>(Ws);
+            const int n4 = a.wfloats >> 2;
+            for (int base = tid; base < n4; base += 8 * T) {  // 8 loads in flight per thread
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (base + q * T < n4) v[q] = __ldg(src + base + q * T);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (base + q * T < n4) dst[base + q * T] = v[q];
+            }
+            const int* msrc = g.m + g.t[k].perm;
+            for (int i = tid; i < a.wints; i += T) Ms[i] = __ldg(msrc + i);
+        }
         __syncthreads();
         resident = k;
-    };
-
-    // ---- building blocks ------------------------------------------------------------------------------
-    // layer-0 units [ua, ub): act = relu(A[u] + W0t[u] . y); records ReLU bits into running words w0
-    auto layer0 = [&](int ua, int ub, const float* const (&Aptr)[RP], const bool (&live)[RP],
-                      const float (&y)[RP][DP], uint32_t (&w0)[RP], int bslot) {
-        for (int u = ua; u < ub; ++u) {
-            float wrow[DP];
-#pragma unroll
-            for (int q4 = 0; q4 < DP / 4; ++q4) {
-                const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
-                wrow[4 * q4] = w.x; wrow[4 * q4 + 1] = w.y; wrow[4 * q4 + 2] = w.z; wrow[4 * q4 + 3] = w.w;
-            }
-#pragma unroll
-            for (int r = 0; r < RP; ++r) {
-                float pre = live[r] ? __ldg(Aptr[r] + (size_t)u * a.B) : 0.f;
-#pragma unroll
-                for (int jj = 0; jj < DP; ++jj) pre = fmaf(wrow[jj], y[r][jj], pre);
-                const bool on = pre > 0.f;
-                actp[r][u] = on ? pre : 0.f;
-                if (MODE == FAST_GRAD) {
-                    if (on) w0[r] |= 1u << (u & 31);
-                    if ((u & 31) == 31 || u == H0 - 1) {
-                        bitp[r][bslot * WL + (u >> 5)] = w0[r];
-                        w0[r] = 0u;
-                    }
-                }
-            }
-        }
-    };
-
-    // layer-1 units [va, vb) with common prefix e (rounded up to 4) -> ReLU bits + output accumulators
-    auto layer1_block = [&](auto NRtag, int v0, int nv, int e4, float (&om)[RP][DP], float (&os)[RP][DP],
-                            uint32_t (&w1)[RP], int bslot) {
-        constexpr int NR = decltype(NRtag)::value;
-        float h[RP][NR];
-        dot_block<RP, NR>(W1 + (size_t)v0 * ld1, ld1, nv - 1, e4, actp, h);
-#pragma unroll
-        for (int c = 0; c < NR; ++c) {
-            if (c < nv) {
-                const int v = v0 + c;
-                const float bias = b1[v];
-                const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
-                float wm[DP], ws[DP];
-#pragma unroll
-                for (int q4 = 0; q4 < DP / 4; ++q4) {
-                    const float4 m4 = wo[q4], s4 = wo[DP / 4 + q4];
-                    wm[4 * q4] = m4.x; wm[4 * q4 + 1] = m4.y; wm[4 * q4 + 2] = m4.z; wm[4 * q4 + 3] = m4.w;
-                    ws[4 * q4] = s4.x; ws[4 * q4 + 1] = s4.y; ws[4 * q4 + 2] = s4.z; ws[4 * q4 + 3] = s4.w;
-                }
-#pragma unroll
-                for (int r = 0; r < RP; ++r) {
-                    const float val = h[r][c] + bias;
-                    const bool on = val > 0.f;
-                    const float hv = on ? val : 0.f;
-#pragma unroll
-                    for (int jj = 0; jj < DP; ++jj) {
-                        om[r][jj] = fmaf(wm[jj], hv, om[r][jj]);
-                        os[r][jj] = fmaf(ws[jj], hv, os[r][jj]);
-                    }
-                    if (MODE == FAST_GRAD) {
-                        if (on) w1[r] |= 1u << (v & 31);
-                        if ((v & 31) == 31 || v == H1 - 1) {
-                            bitp[r][bslot * WL + (v >> 5)] = w1[r];
-                            w1[r] = 0u;
-                        }
-                    }
-                }
-            }
-        }
-    };
-    auto layer1_range = [&](int va, int vb, int e4, float (&om)[RP][DP], float (&os)[RP][DP], uint32_t (&w1)[RP],
-                            int bslot) {
-        int v = va;
-        for (; v + 16 <= vb; v += 16) layer1_block(std::integral_constant<int, 16>{}, v, 16, e4, om, os, w1, bslot);
-        if (v + 8 <= vb) { layer1_block(std::integral_constant<int, 8>{}, v, 8, e4, om, os, w1, bslot); v += 8; }
-        if (v + 4 <= vb) { layer1_block(std::integral_constant<int, 4>{}, v, 4, e4, om, os, w1, bslot); v += 4; }
-        if (v < vb) layer1_block(std::integral_constant<int, 4>{}, v, vb - v, e4, om, os, w1, bslot);
-    };
-
-    // layer-1 cotangents of units [va, vb): g = relu'(.) * (WoT[v] . (mbar, sbar)) -> buffer
-    auto layer1_cot = [&](int va, int vb, const float (&mb)[RP][DP], const float (&sb)[RP][DP], int bslot) {
-        for (int v = va; v < vb; ++v) {
-            const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
-            float wm[DP], ws[DP];
-#pragma unroll
-            for (int q4 = 0; q4 < DP / 4; ++q4) {
-                const float4 m4 = wo[q4], s4 = wo[DP / 4 + q4];
-                wm[4 * q4] = m4.x; wm[4 * q4 + 1] = m4.y; wm[4 * q4 + 2] = m4.z; wm[4 * q4 + 3] = m4.w;
-                ws[4 * q4] = s4.x; ws[4 * q4 + 1] = s4.y; ws[4 * q4 + 2] = s4.z; ws[4 * q4 + 3] = s4.w;
-            }
-#pragma unroll
-            for (int r = 0; r < RP; ++r) {
-                float gsum = 0.f;
-#pragma unroll
-                for (int jj = 0; jj < DP; ++jj) gsum = fmaf(ws[jj], sb[r][jj], fmaf(wm[jj], mb[r][jj], gsum));
-                const bool on = (bitp[r][bslot * WL + (v >> 5)] >> (v & 31)) & 1u;
-                actp[r][v] = on ? gsum : 0.f;
-            }
-        }
-    };
-
-    // layer-0 cotangents of the aligned column block [u0, u0+NC) restricted to units [ua, ub):
-    // g0 = relu'(.) * sum_{v in [va4, vb4)} W1[v][u] g1[v];  ybar += W0t[u]^T g0;  gA tile += g0
-    auto layer0_cot_block = [&](auto NCtag, int u0, int ua, int ub, int va4, int vb4, float (&yb)[RP][DP], int bslot,
-                                const bool (&live)[RP], const int (&rrow)[RP], bool want_gA) {
-        constexpr int NC = decltype(NCtag)::value;
-        float g0[RP][NC];
-        tdot_block<RP, NC>(W1 + u0, ld1, va4, vb4, actp, g0);
-        uint32_t wb[RP];
-#pragma unroll
-        for (int r = 0; r < RP; ++r) wb[r] = bitp[r][bslot * WL + (u0 >> 5)] >> (u0 & 31);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const int u = u0 + c;
-            if (u >= ua && u < ub) {
-                float wrow[DP];
-#pragma unroll
-                for (int q4 = 0; q4 < DP / 4; ++q4) {
-                    const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
-                    wrow[4 * q4] = w.x; wrow[4 * q4 + 1] = w.y; wrow[4 * q4 + 2] = w.z; wrow[4 * q4 + 3] = w.w;
-                }
-#pragma unroll
-                for (int r = 0; r < RP; ++r) {
-                    const float gv = ((wb[r] >> c) & 1u) ? g0[r][c] : 0.f;
-#pragma unroll
-                    for (int jj = 0; jj < DP; ++jj) yb[r][jj] = fmaf(wrow[jj], gv, yb[r][jj]);
-                    if (want_gA && live[r]) atomicAdd(gAt + (size_t)u * a.TBp + rrow[r], gv);
-                }
-            }
-        }
-    };
-    auto layer0_cot_range = [&](int ua, int ub, int va4, int vb4, float (&yb)[RP][DP], int bslot,
-                                const bool (&live)[RP], const int (&rrow)[RP], bool want_gA) {
-        int u = ua & ~3;
-        const int uend = (ub + 3) & ~3;
-        // 16-wide blocks must not straddle a 32-bit mask word: u % 16 == 0 is not guaranteed, 4-alignment is;
-        // use 16 only when the block stays inside one word
-        while (u < uend) {
-            const int left = uend - u;
-            if (left >= 16 && ((u & 31) + 16 <= 32)) {
-                layer0_cot_block(std::integral_constant<int, 16>{}, u, ua, ub, va4, vb4, yb, bslot, live, rrow, want_gA);
-                u += 16;
-            } else if (left >= 8 && ((u & 31) + 8 <= 32)) {
-                layer0_cot_block(std::integral_constant<int, 8>{}, u, ua, ub, va4, vb4, yb, bslot, live, rrow, want_gA);
-                u += 8;
-            } else {
-                layer0_cot_block(std::integral_constant<int, 4>{}, u, ua, ub, va4, vb4, yb, bslot, live, rrow, want_gA);
-                u += 4;
-            }
-        }
     };
 
     // -------------------------------------------------------------------------------------------------------
@@ -385,179 +242,320 @@ __global__ void __launch_bounds__(256, 1) k_fast(const MafImg g, const FastArgs 
             logq[r] = 0.f;
         }
 
-        // ================= sampling chain under A_p =================
-        for (int k = 0; k < K; ++k) {
+        // One loop over the 2K (forward) / 4K (forward + reverse) phases; every building block below is
+        // instantiated exactly once.  kind: 0 = sampling pass under A_p (k ascending), 1 = density pass under A_q
+        // (k descending), 2 = reverse of the density pass (k ascending), 3 = reverse of the sampling pass.
+        const int nphase = (MODE == FAST_GRAD ? 4 : 2) * K;
+        for (int ph = 0; ph < nphase; ++ph) {
+            const int kind = ph / K;
+            const int idx = ph - kind * K;
+            const int k = (kind == 0 || kind == 2) ? idx : K - 1 - idx;
             ensure_weights(k);
-            const float* Aptr[RP];
-            float zos[RP][DP], y[RP][DP], om[RP][DP], os[RP][DP];
-            uint32_t w0[RP], w1[RP];
-#pragma unroll
-            for (int r = 0; r < RP; ++r) {
-                Aptr[r] = Ap[r] + (size_t)k * H0 * a.B;
-                w0[r] = w1[r] = 0u;
-#pragma unroll
-                for (int jj = 0; jj < DP; ++jj) {
-                    zos[r][jj] = jj < D ? vecp[r][oV + k * D + perm[jj]] : 0.f;
-                    y[r][jj] = 0.f;
-                    om[r][jj] = jj < D ? bo[jj] : 0.f;
-                    os[r][jj] = jj < D ? bo[DP + jj] : 0.f;
-                }
-            }
-            const int bs = (0 * K + k) * 2;
-            for (int j = 0; j < D; ++j) {
-                layer0(grp0[j], grp0[j + 1], Aptr, live, y, w0, bs);
-                layer1_range(grp1[j], grp1[j + 1], (grp0[j + 1] + 3) & ~3, om, os, w1, bs + 1);
+            const bool seq = (kind == 0 || kind == 3);
+            const int bs = ((kind == 0 || kind == 3) ? k : K + k) * 2;  // relu-bit slot of (pass, k)
+
+            if (kind < 2) {
+                // ===================== forward pass of transform k =====================
+                const float* Aptr[RP];
+                float zos[RP][DP], y[RP][DP], om[RP][DP], os[RP][DP];
+                uint32_t w0[RP], w1[RP];
+                const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
 #pragma unroll
                 for (int r = 0; r < RP; ++r) {
-                    float m = 0.f, s = 0.f, zj = 0.f;
+                    Aptr[r] = (seq ? Ap[r] : Aq[r]) + (size_t)k * H0 * a.B;
+                    w0[r] = w1[r] = 0u;
 #pragma unroll
                     for (int jj = 0; jj < DP; ++jj) {
-                        m = jj == j ? om[r][jj] : m;
-                        s = jj == j ? os[r][jj] : s;
-                        zj = jj == j ? zos[r][jj] : zj;
-                    }
-                    const float sh = fminf(fmaxf(s, g.lo), g.hi);
-                    const float yj = (zj - m) * expf(-sh);
-#pragma unroll
-                    for (int jj = 0; jj < DP; ++jj) y[r][jj] = jj == j ? yj : y[r][jj];
-                    logp[r] += sh;
-                    vecp[r][oSHP + k * D + j] = sh;
-                    vecp[r][oV + (k + 1) * D + permy[j]] = yj;
-                }
-            }
-        }
-
-        // ================= density chain under A_q =================
-        for (int k = K - 1; k >= 0; --k) {
-            ensure_weights(k);
-            const float* Aptr[RP];
-            float y[RP][DP], om[RP][DP], os[RP][DP];
-            uint32_t w0[RP], w1[RP];
-            const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
-#pragma unroll
-            for (int r = 0; r < RP; ++r) {
-                Aptr[r] = Aq[r] + (size_t)k * H0 * a.B;
-                w0[r] = w1[r] = 0u;
-#pragma unroll
-                for (int jj = 0; jj < DP; ++jj) {
-                    y[r][jj] = jj < D ? vecp[r][src + permy[jj]] : 0.f;
-                    om[r][jj] = jj < D ? bo[jj] : 0.f;
-                    os[r][jj] = jj < D ? bo[DP + jj] : 0.f;
-                }
-            }
-            const int bs = (1 * K + k) * 2;
-            layer0(0, H0, Aptr, live, y, w0, bs);
-            for (int j = 0; j < D; ++j)  // blocks never straddle degree groups: one common prefix per call
-                layer1_range(grp1[j], grp1[j + 1], (grp0[j + 1] + 3) & ~3, om, os, w1, bs + 1);
-#pragma unroll
-            for (int r = 0; r < RP; ++r) {
-#pragma unroll
-                for (int jj = 0; jj < DP; ++jj) {
-                    if (jj < D) {
-                        const float sh = fminf(fmaxf(os[r][jj], g.lo), g.hi);
-                        vecp[r][oSHQ + k * D + jj] = sh;
-                        logq[r] += sh;
-                        vecp[r][oU + k * D + perm[jj]] = fmaf(expf(sh), y[r][jj], om[r][jj]);
+                        zos[r][jj] = (seq && jj < D) ? vecp[r][oV + k * D + perm[jj]] : 0.f;
+                        y[r][jj] = (!seq && jj < D) ? vecp[r][src + permy[jj]] : 0.f;
+                        om[r][jj] = jj < D ? bo[jj] : 0.f;
+                        os[r][jj] = jj < D ? bo[DP + jj] : 0.f;
                     }
                 }
-            }
-        }
+                for (int j = 0; j < D; ++j) {
+                    // ---- layer-0 units of degree j: act = relu(A[u] + W0t[u] . y), 4 units per batch
+                    {
+                        const int ua = grp0[j], ub = grp0[j + 1];
+                        for (int u0 = ua; u0 < ub; u0 += 4) {
+                            float pre[RP][4];
 #pragma unroll
-        for (int r = 0; r < RP; ++r) {
-            float ssq = 0.f;
-            for (int d = 0; d < D; ++d) {
-                const float u = vecp[r][oU + d];
-                ssq = fmaf(u, u, ssq);
-            }
-            logq[r] += -0.5f * ssq - (float)D * HALF_LOG_2PI;
-            if (a.diff && live[r]) a.diff[pidx[r]] = logp[r] - logq[r];
-        }
-        if (MODE != FAST_GRAD) continue;
-
-        // ================= reverse mode =================
-        const float w = a.w;
+                            for (int c = 0; c < 4; ++c) {
+                                const int u = min(u0 + c, ub - 1);
 #pragma unroll
-        for (int r = 0; r < RP; ++r)
-            for (int d = 0; d < D; ++d) vecp[r][oG + d] = w * vecp[r][oU + d];  // d(-w log q)/d u_0
-        for (int k = 0; k < K; ++k) {
-            ensure_weights(k);
-            const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
-            float mb[RP][DP], sb[RP][DP], yb[RP][DP];
+                                for (int r = 0; r < RP; ++r) pre[r][c] = live[r] ? __ldg(Aptr[r] + (size_t)u * a.B) : 0.f;
+                            }
 #pragma unroll
-            for (int r = 0; r < RP; ++r)
+                            for (int c = 0; c < 4; ++c) {
+                                const int u = min(u0 + c, ub - 1);
 #pragma unroll
-                for (int jj = 0; jj < DP; ++jj) {
-                    if (jj < D) {
-                        const float ub = vecp[r][oG + perm[jj]];
-                        const float es = expf(vecp[r][oSHQ + k * D + jj]);
-                        const float yin = vecp[r][src + permy[jj]];
-                        mb[r][jj] = ub;
-                        sb[r][jj] = fmaf(ub * es, yin, -w);
-                        yb[r][jj] = ub * es;
-                    } else {
-                        mb[r][jj] = sb[r][jj] = yb[r][jj] = 0.f;
+                                for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                    const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
+#pragma unroll
+                                    for (int r = 0; r < RP; ++r) {
+                                        pre[r][c] = fmaf(w.x, y[r][4 * q4], pre[r][c]);
+                                        pre[r][c] = fmaf(w.y, y[r][4 * q4 + 1], pre[r][c]);
+                                        pre[r][c] = fmaf(w.z, y[r][4 * q4 + 2], pre[r][c]);
+                                        pre[r][c] = fmaf(w.w, y[r][4 * q4 + 3], pre[r][c]);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int u = u0 + c;
+                                if (u < ub) {
+#pragma unroll
+                                    for (int r = 0; r < RP; ++r) {
+                                        const bool on = pre[r][c] > 0.f;
+                                        actp[r][u] = on ? pre[r][c] : 0.f;
+                                        if (MODE == FAST_GRAD) {
+                                            if (on) w0[r] |= 1u << (u & 31);
+                                            if ((u & 31) == 31 || u == H0 - 1) {
+                                                bitp[r][bs * WL + (u >> 5)] = w0[r];
+                                                w0[r] = 0u;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    // ---- layer-1 units of degree j (prefix grp0[j+1]) -> relu bits + output accumulators
+                    {
+                        const int va = grp1[j], vb = grp1[j + 1];
+                        const int e4 = (grp0[j + 1] + 3) & ~3;
+                        auto block = [&](auto NRtag, int v0, int nv) {
+                            constexpr int NR = decltype(NRtag)::value;
+                            float h[RP][NR];
+                            dot_block<RP, NR>(W1 + (size_t)v0 * ld1, ld1, nv - 1, e4, actp, h);
+#pragma unroll
+                            for (int c = 0; c < NR; ++c) {
+                                if (c < nv) {
+                                    const int v = v0 + c;
+                                    const float bias = b1[v];
+                                    const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
+                                    float wm[DP], ws[DP];
+#pragma unroll
+                                    for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                        const float4 m4 = wo[q4], s4 = wo[DP / 4 + q4];
+                                        wm[4 * q4] = m4.x; wm[4 * q4 + 1] = m4.y; wm[4 * q4 + 2] = m4.z; wm[4 * q4 + 3] = m4.w;
+                                        ws[4 * q4] = s4.x; ws[4 * q4 + 1] = s4.y; ws[4 * q4 + 2] = s4.z; ws[4 * q4 + 3] = s4.w;
+                                    }
+#pragma unroll
+                                    for (int r = 0; r < RP; ++r) {
+                                        const float val = h[r][c] + bias;
+                                        const bool on = val > 0.f;
+                                        const float hv = on ? val : 0.f;
+#pragma unroll
+                                        for (int jj = 0; jj < DP; ++jj) {
+                                            om[r][jj] = fmaf(wm[jj], hv, om[r][jj]);
+                                            os[r][jj] = fmaf(ws[jj], hv, os[r][jj]);
+                                        }
+                                        if (MODE == FAST_GRAD) {
+                                            if (on) w1[r] |= 1u << (v & 31);
+                                            if ((v & 31) == 31 || v == H1 - 1) {
+                                                bitp[r][(bs + 1) * WL + (v >> 5)] = w1[r];
+                                                w1[r] = 0u;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        };
+                        int v = va;
+                        for (; v + 16 <= vb; v += 16) block(std::integral_constant<int, 16>{}, v, 16);
+                        if (v + 8 <= vb) { block(std::integral_constant<int, 8>{}, v, 8); v += 8; }
+                        for (; v < vb; v += 4) block(std::integral_constant<int, 4>{}, v, min(4, vb - v));
+                    }
+                    if (seq) {  // position j is final: y_j = (z_j - m_j) exp(-clamp(s_j))
+#pragma unroll
+                        for (int r = 0; r < RP; ++r) {
+                            float m = 0.f, s = 0.f, zj = 0.f;
+#pragma unroll
+                            for (int jj = 0; jj < DP; ++jj) {
+                                m = jj == j ? om[r][jj] : m;
+                                s = jj == j ? os[r][jj] : s;
+                                zj = jj == j ? zos[r][jj] : zj;
+                            }
+                            const float sh = fminf(fmaxf(s, g.lo), g.hi);
+                            const float yj = (zj - m) * expf(-sh);
+#pragma unroll
+                            for (int jj = 0; jj < DP; ++jj) y[r][jj] = jj == j ? yj : y[r][jj];
+                            logp[r] += sh;
+                            vecp[r][oSHP + k * D + j] = sh;
+                            vecp[r][oV + (k + 1) * D + permy[j]] = yj;
+                        }
                     }
                 }
-            const int bs = (1 * K + k) * 2;
-            layer1_cot(0, H1, mb, sb, bs + 1);
-            for (int j = 0; j < D; ++j) {  // layer-0 units of degree j are consumed by layer-1 rows >= grp1[j]
-                const int ua = grp0[j], ub = grp0[j + 1];
-                if (ua < ub) layer0_cot_range(ua, ub, grp1[j] & ~3, (H1 + 3) & ~3, yb, bs, live, rrow, false);
-            }
+                if (!seq) {  // u_k = exp(clamp(s)) * u_{k+1} + m
 #pragma unroll
-            for (int r = 0; r < RP; ++r)
+                    for (int r = 0; r < RP; ++r) {
 #pragma unroll
-                for (int jj = 0; jj < DP; ++jj)
-                    if (jj < D) vecp[r][oG + permy[jj]] = yb[r][jj];
-        }
-        for (int k = K - 1; k >= 0; --k) {
-            ensure_weights(k);
-            float yb[RP][DP], yv[RP][DP], sh[RP][DP], mb[RP][DP], sb[RP][DP], zb[RP][DP];
+                        for (int jj = 0; jj < DP; ++jj) {
+                            if (jj < D) {
+                                const float sh = fminf(fmaxf(os[r][jj], g.lo), g.hi);
+                                vecp[r][oSHQ + k * D + jj] = sh;
+                                logq[r] += sh;
+                                vecp[r][oU + k * D + perm[jj]] = fmaf(expf(sh), y[r][jj], om[r][jj]);
+                            }
+                        }
+                    }
+                    if (k == 0) {  // end of the density chain: base log-density, KL term, reverse-mode seed
 #pragma unroll
-            for (int r = 0; r < RP; ++r)
-#pragma unroll
-                for (int jj = 0; jj < DP; ++jj) {
-                    yb[r][jj] = jj < D ? vecp[r][oG + permy[jj]] : 0.f;
-                    yv[r][jj] = jj < D ? vecp[r][oV + (k + 1) * D + permy[jj]] : 0.f;
-                    sh[r][jj] = jj < D ? vecp[r][oSHP + k * D + jj] : 0.f;
-                    mb[r][jj] = sb[r][jj] = zb[r][jj] = 0.f;
+                        for (int r = 0; r < RP; ++r) {
+                            float ssq = 0.f;
+                            for (int d = 0; d < D; ++d) {
+                                const float u = vecp[r][oU + d];
+                                ssq = fmaf(u, u, ssq);
+                                if (MODE == FAST_GRAD) vecp[r][oG + d] = a.w * u;  // d(-w log q)/d u_0
+                            }
+                            logq[r] += -0.5f * ssq - (float)D * HALF_LOG_2PI;
+                            if (a.diff && live[r]) a.diff[pidx[r]] = logp[r] - logq[r];
+                        }
+                    }
                 }
-            const int bs = (0 * K + k) * 2;
-            for (int j = D - 1; j >= 0; --j) {
+            } else {
+                // ===================== reverse pass of transform k =====================
+                const float w = a.w;
+                float yb[RP][DP], yv[RP][DP], sh[RP][DP], mb[RP][DP], sb[RP][DP], zb[RP][DP];
+                const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
 #pragma unroll
-                for (int r = 0; r < RP; ++r) {
-                    float ybj = 0.f, shj = 0.f, yj = 0.f;
+                for (int r = 0; r < RP; ++r)
 #pragma unroll
                     for (int jj = 0; jj < DP; ++jj) {
-                        ybj = jj == j ? yb[r][jj] : ybj;
-                        shj = jj == j ? sh[r][jj] : shj;
-                        yj = jj == j ? yv[r][jj] : yj;
+                        zb[r][jj] = 0.f;
+                        if (seq) {
+                            yb[r][jj] = jj < D ? vecp[r][oG + permy[jj]] : 0.f;
+                            yv[r][jj] = jj < D ? vecp[r][oV + (k + 1) * D + permy[jj]] : 0.f;
+                            sh[r][jj] = jj < D ? vecp[r][oSHP + k * D + jj] : 0.f;
+                            mb[r][jj] = sb[r][jj] = 0.f;
+                        } else if (jj < D) {
+                            const float ub = vecp[r][oG + perm[jj]];
+                            const float es = expf(vecp[r][oSHQ + k * D + jj]);
+                            const float yin = vecp[r][src + permy[jj]];
+                            mb[r][jj] = ub;
+                            sb[r][jj] = fmaf(ub * es, yin, -w);
+                            yb[r][jj] = ub * es;
+                            yv[r][jj] = sh[r][jj] = 0.f;
+                        } else {
+                            mb[r][jj] = sb[r][jj] = yb[r][jj] = yv[r][jj] = sh[r][jj] = 0.f;
+                        }
                     }
-                    const float zbj = ybj * expf(-shj);
+                for (int j = D - 1; j >= 0; --j) {
+                    if (seq) {
 #pragma unroll
-                    for (int jj = 0; jj < DP; ++jj) {
-                        zb[r][jj] = jj == j ? zbj : zb[r][jj];
-                        mb[r][jj] = jj == j ? -zbj : mb[r][jj];
-                        sb[r][jj] = jj == j ? fmaf(-ybj, yj, w) : sb[r][jj];
+                        for (int r = 0; r < RP; ++r) {
+                            float ybj = 0.f, shj = 0.f, yj = 0.f;
+#pragma unroll
+                            for (int jj = 0; jj < DP; ++jj) {
+                                ybj = jj == j ? yb[r][jj] : ybj;
+                                shj = jj == j ? sh[r][jj] : shj;
+                                yj = jj == j ? yv[r][jj] : yj;
+                            }
+                            const float zbj = ybj * expf(-shj);
+#pragma unroll
+                            for (int jj = 0; jj < DP; ++jj) {
+                                zb[r][jj] = jj == j ? zbj : zb[r][jj];
+                                mb[r][jj] = jj == j ? -zbj : mb[r][jj];
+                                sb[r][jj] = jj == j ? fmaf(-ybj, yj, w) : sb[r][jj];
+                            }
+                        }
+                    }
+                    // ---- layer-1 cotangents of the degree-j units: g = relu'(.) * (WoT[v] . (mbar, sbar)) -> buffer
+                    {
+                        const int va = grp1[j], vb = grp1[j + 1];
+                        for (int v0 = va; v0 < vb; v0 += 4) {
+                            float gs[RP][4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int v = min(v0 + c, vb - 1);
+                                const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
+#pragma unroll
+                                for (int r = 0; r < RP; ++r) gs[r][c] = 0.f;
+#pragma unroll
+                                for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                    const float4 m4 = wo[q4], s4 = wo[DP / 4 + q4];
+#pragma unroll
+                                    for (int r = 0; r < RP; ++r) {
+                                        float t0 = fmaf(s4.x, sb[r][4 * q4], m4.x * mb[r][4 * q4]);
+                                        float t1 = fmaf(s4.y, sb[r][4 * q4 + 1], m4.y * mb[r][4 * q4 + 1]);
+                                        float t2 = fmaf(s4.z, sb[r][4 * q4 + 2], m4.z * mb[r][4 * q4 + 2]);
+                                        float t3 = fmaf(s4.w, sb[r][4 * q4 + 3], m4.w * mb[r][4 * q4 + 3]);
+                                        gs[r][c] += (t0 + t1) + (t2 + t3);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int v = v0 + c;
+                                if (v < vb) {
+#pragma unroll
+                                    for (int r = 0; r < RP; ++r) {
+                                        const bool on = (bitp[r][(bs + 1) * WL + (v >> 5)] >> (v & 31)) & 1u;
+                                        actp[r][v] = on ? gs[r][c] : 0.f;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    // ---- layer-0 cotangents of the degree-j units (consumed by layer-1 rows >= grp1[j])
+                    {
+                        const int ua = grp0[j], ub = grp0[j + 1];
+                        const int va4 = grp1[j] & ~3, vb4 = (H1 + 3) & ~3;
+                        auto cblock = [&](auto NCtag, int u0) {
+                            constexpr int NC = decltype(NCtag)::value;
+                            float g0[RP][NC];
+                            tdot_block<RP, NC>(W1 + u0, ld1, va4, vb4, actp, g0);
+                            uint32_t wb[RP];
+#pragma unroll
+                            for (int r = 0; r < RP; ++r) wb[r] = bitp[r][bs * WL + (u0 >> 5)] >> (u0 & 31);
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                const int u = u0 + c;
+                                if (u >= ua && u < ub) {
+                                    float wrow[DP];
+#pragma unroll
+                                    for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                        const float4 w4 = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
+                                        wrow[4 * q4] = w4.x; wrow[4 * q4 + 1] = w4.y; wrow[4 * q4 + 2] = w4.z; wrow[4 * q4 + 3] = w4.w;
+                                    }
+#pragma unroll
+                                    for (int r = 0; r < RP; ++r) {
+                                        const float gv = ((wb[r] >> c) & 1u) ? g0[r][c] : 0.f;
+#pragma unroll
+                                        for (int jj = 0; jj < DP; ++jj) yb[r][jj] = fmaf(wrow[jj], gv, yb[r][jj]);
+                                        if (seq && live[r]) atomicAdd(gAt + (size_t)u * a.TBp + rrow[r], gv);
+                                    }
+                                }
+                            }
+                        };
+                        int u = ua & ~3;
+                        const int uend = (ub + 3) & ~3;
+                        while (u < uend) {  // wide blocks only where they stay inside one 32-bit mask word
+                            const int left = uend - u;
+                            if (left >= 16 && ((u & 31) + 16 <= 32)) { cblock(std::integral_constant<int, 16>{}, u); u += 16; }
+                            else if (left >= 8 && ((u & 31) + 8 <= 32)) { cblock(std::integral_constant<int, 8>{}, u); u += 8; }
+                            else { cblock(std::integral_constant<int, 4>{}, u); u += 4; }
+                        }
                     }
                 }
-                layer1_cot(grp1[j], grp1[j + 1], mb, sb, bs + 1);
-                const int ua = grp0[j], ub = grp0[j + 1];
-                if (ua < ub) layer0_cot_range(ua, ub, grp1[j] & ~3, (H1 + 3) & ~3, yb, bs, live, rrow, true);
-            }
 #pragma unroll
-            for (int r = 0; r < RP; ++r)
+                for (int r = 0; r < RP; ++r)
 #pragma unroll
-                for (int jj = 0; jj < DP; ++jj)
-                    if (jj < D) vecp[r][oG + perm[jj]] = zb[r][jj];
-            // flush the gA tile of this transform (rows of this tile are owned by this CTA alone)
-            __syncthreads();
-            for (int i = tid; i < H0 * rows_here; i += T) {
-                const int u = i / rows_here, rr = i % rows_here;
-                a.gA[((size_t)k * H0 + u) * a.B + b0 + rr] = gAt[(size_t)u * a.TBp + rr];
-                gAt[(size_t)u * a.TBp + rr] = 0.f;
+                    for (int jj = 0; jj < DP; ++jj)
+                        if (jj < D) {
+                            if (seq) vecp[r][oG + perm[jj]] = zb[r][jj];
+                            else vecp[r][oG + permy[jj]] = yb[r][jj];
+                        }
+                if (seq) {  // flush the gA tile of this transform (rows of this tile are owned by this CTA alone)
+                    __syncthreads();
+                    for (int i = tid; i < H0 * rows_here; i += T) {
+                        const int u = i / rows_here, rr = i % rows_here;
+                        a.gA[((size_t)k * H0 + u) * a.B + b0 + rr] = gAt[(size_t)u * a.TBp + rr];
+                        gAt[(size_t)u * a.TBp + rr] = 0.f;
+                    }
+                    __syncthreads();
+                }
             }
-            __syncthreads();
         }
     }
 }

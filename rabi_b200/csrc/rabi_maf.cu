@@ -792,18 +792,19 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     rel.first1 = t0.first[1] - t0.perm;
     fa.wfloats = t0.fast_end - t0.W0t;
     fa.wints = (t0.meta_fast_end - t0.perm + 3) & ~3;
-    int AS = std::max(round4(H0), round4(H1)) + 4;
+    int AS = std::max(round4(H0), round4(H1));
     if (((AS / 4) & 1) == 0) AS += 4;  // AS/4 odd: 128-bit accesses of consecutive slots hit distinct bank groups
     fa.AS = AS;
     fa.VS = ((4 * K + 2) * D) | 1;
     const int WL = (g.Hmax + 31) / 32;
     fa.BWS = MODE == FAST_GRAD ? ((2 * K * 2 * WL) | 1) : 0;
-    const int RP = env_int("RABI_FAST_RP", 2) == 1 ? 1 : 2;
+    const int RP = env_int("RABI_FAST_RP", 1) == 2 ? 2 : 1;
     const size_t per_slot = (size_t)(fa.AS + fa.VS + fa.BWS) * sizeof(float);
     const size_t fixed = (size_t)(fa.wfloats + fa.wints) * sizeof(float);
     const size_t budget = (size_t)h->max_smem_optin - 1024;
-    int T = env_int("RABI_FAST_T", 256);
-    T = std::max(32, std::min(256, (T / 32) * 32));
+    const int Tmax = RP == 1 ? 384 : 256;  // matches __launch_bounds__ of k_fast
+    int T = env_int("RABI_FAST_T", Tmax);
+    T = std::max(32, std::min(Tmax, (T / 32) * 32));
     int grid = 0;
     size_t smem = 0;
     const long long npairs = (long long)fa.S * fa.B;
