@@ -36,6 +36,7 @@ struct FastArgs {
     int AS, VS, BWS;    // per-slot strides: activations (floats), vectors (floats), relu bit words
     int wfloats, wints; // per-transform weight / index block sizes (identical for all transforms)
     int TBp;            // padded row count of the gA tile
+    int tm_cols;        // TMEM columns to allocate (power of two >= 32) when the activations live in tensor memory
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -48,10 +49,51 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
-// out[r][c] = sum_{i<e4} W[(min(c,cmax))*ld + i] * act_r[i]     (NR rows x RP pairs, e4 multiple of 4)
-template <int RP, int NR>
+// ---- activation buffer of one pair: shared memory, or a private row of TMEM columns -----------------------
+// TMEM (tensor memory, 512 columns x 128 lanes x 32 bit per SM) is idle in this FMA-bound kernel; .32x32b accesses
+// give every thread of a warp its own lane, so a column range is a thread-private array with 128-bit vector access.
+// Keeping the activations there frees ~45% of the per-pair shared memory => twice the resident warps.
+template <bool TM>
+struct ActBuf;
+template <>
+struct ActBuf<false> {
+    float* p;
+    __device__ __forceinline__ float4 ld4(int i) const { return *reinterpret_cast<const float4*>(p + i); }
+    __device__ __forceinline__ void st4(int i, float4 v) const { *reinterpret_cast<float4*>(p + i) = v; }
+    __device__ __forceinline__ void st1(int i, float v) const { p[i] = v; }
+    __device__ __forceinline__ static void wait_ld(float4&) {}
+    __device__ __forceinline__ static void wait_st() {}
+};
+template <>
+struct ActBuf<true> {
+    uint32_t t;  // TMEM address of column 0 of this thread's row: (lane quadrant base << 16) | first column
+    __device__ __forceinline__ float4 ld4(int i) const {
+        float4 v;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(t + (uint32_t)i)
+                     : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void st4(int i, float4 v) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t + (uint32_t)i), "f"(v.x),
+                     "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+    __device__ __forceinline__ void st1(int i, float v) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(t + (uint32_t)i), "f"(v) : "memory");
+    }
+    // the loaded registers are only valid after wait::ld; tie them to the wait so nothing is scheduled above it
+    __device__ __forceinline__ static void wait_ld(float4& v) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)::"memory");
+    }
+    __device__ __forceinline__ static void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+
+// out[r][c] = sum_{i<e4} W[(min(c,cmax))*ld + i] * act_r[i]     (NR rows x RP pairs, e4 multiple of 4, e4 >= 4)
+template <int RP, int NR, bool TM>
 __device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld, int cmax, int e4,
-                                          float* const (&actp)[RP], float (&out)[RP][NR]) {
+                                          const ActBuf<TM> (&ab)[RP], float (&out)[RP][NR]) {
     float2 acc[RP][NR];
 #pragma unroll
     for (int r = 0; r < RP; ++r)
@@ -60,11 +102,21 @@ __device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld, i
     const float* wr[NR];
 #pragma unroll
     for (int c = 0; c < NR; ++c) wr[c] = W + (size_t)min(c, cmax) * ld;
+    float4 hn[RP];
+#pragma unroll
+    for (int r = 0; r < RP; ++r) hn[r] = ab[r].ld4(0);
 #pragma unroll 2
     for (int i = 0; i < e4; i += 4) {
         float4 h[RP];
 #pragma unroll
-        for (int r = 0; r < RP; ++r) h[r] = *reinterpret_cast<const float4*>(actp[r] + i);
+        for (int r = 0; r < RP; ++r) {
+            ActBuf<TM>::wait_ld(hn[r]);
+            h[r] = hn[r];
+        }
+        if (i + 4 < e4) {
+#pragma unroll
+            for (int r = 0; r < RP; ++r) hn[r] = ab[r].ld4(i + 4);
+        }
 #pragma unroll
         for (int c = 0; c < NR; ++c) {
             const float4 w = *reinterpret_cast<const float4*>(wr[c] + i);
@@ -82,19 +134,29 @@ __device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld, i
 }
 
 // out[r][c] = sum_{v in [va4, vb4)} W[v*ld + c] * g_r[v]     (NC columns x RP pairs; W offset to the first column;
-// va4/vb4 multiples of 4; rows >= the layer's width are zero padding)
-template <int RP, int NC>
+// va4 < vb4 multiples of 4; rows >= the layer's width are zero padding)
+template <int RP, int NC, bool TM>
 __device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld, int va4, int vb4,
-                                           float* const (&gp)[RP], float (&out)[RP][NC]) {
+                                           const ActBuf<TM> (&ab)[RP], float (&out)[RP][NC]) {
     float2 acc[RP][NC / 2];
 #pragma unroll
     for (int r = 0; r < RP; ++r)
 #pragma unroll
         for (int c = 0; c < NC / 2; ++c) acc[r][c] = make_float2(0.f, 0.f);
+    float4 gn[RP];
+#pragma unroll
+    for (int r = 0; r < RP; ++r) gn[r] = ab[r].ld4(va4);
     for (int v = va4; v < vb4; v += 4) {
         float4 g4[RP];
 #pragma unroll
-        for (int r = 0; r < RP; ++r) g4[r] = *reinterpret_cast<const float4*>(gp[r] + v);
+        for (int r = 0; r < RP; ++r) {
+            ActBuf<TM>::wait_ld(gn[r]);
+            g4[r] = gn[r];
+        }
+        if (v + 4 < vb4) {
+#pragma unroll
+            for (int r = 0; r < RP; ++r) gn[r] = ab[r].ld4(v + 4);
+        }
 #pragma unroll
         for (int dv = 0; dv < 4; ++dv) {
             const float* wrow = W + (size_t)(v + dv) * ld;
@@ -128,7 +190,7 @@ struct FastRel {
     int perm, permy, deg0, pre1, grp0, grp1, first1; // ints, relative to t.perm
 };
 
-template <int MODE, int RP, int DP>
+template <int MODE, int RP, int DP, bool TM>
 __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g, const FastArgs a, const FastRel rel) {
     extern __shared__ __align__(16) float sm[];
     const int T = blockDim.x, tid = threadIdx.x;
@@ -138,7 +200,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
     int* Ms = reinterpret_cast<int*>(Ws + a.wfloats);
     float* gAt = reinterpret_cast<float*>(Ms + a.wints);                    // [H0][TBp]  (GRAD only)
     float* act = gAt + (MODE == FAST_GRAD ? (((size_t)H0 * a.TBp + 3) & ~(size_t)3) : 0);  // [RP*T][AS], 16-B aligned
-    float* vec = act + (size_t)RP * T * a.AS;                               // [RP*T][VS]
+    float* vec = act + (TM ? 0 : (size_t)RP * T * a.AS);                    // [RP*T][VS]  (TM: no smem activations)
     uint32_t* bits = reinterpret_cast<uint32_t*>(vec + (size_t)RP * T * a.VS);  // [RP*T][BWS] (GRAD only)
 
     const float* W0t = Ws + rel.W0t;
@@ -152,17 +214,36 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
     const int* grp0 = Ms + rel.grp0;
     const int* grp1 = Ms + rel.grp1;
 
-    float* actp[RP];
+    __shared__ uint32_t tmem_base_s;
+    if (TM) {  // one warp allocates the tensor-memory columns for the whole CTA
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(&tmem_base_s)),
+                         "r"((uint32_t)a.tm_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    ActBuf<TM> ab[RP];
     float* vecp[RP];
     uint32_t* bitp[RP];
 #pragma unroll
     for (int r = 0; r < RP; ++r) {
         const int slot = tid + r * T;
-        actp[r] = act + (size_t)slot * a.AS;
+        if constexpr (TM) {
+            const int warp = tid >> 5;  // lanes 32*(warp%4).. ; columns ((warp/4)*RP + r)*AS ..
+            ab[r].t = tmem_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(((warp >> 2) * RP + r) * a.AS);
+        } else {
+            ab[r].p = act + (size_t)slot * a.AS;
+        }
         vecp[r] = vec + (size_t)slot * a.VS;
         bitp[r] = bits + (size_t)slot * a.BWS;
-        for (int i = 0; i < a.AS; ++i) actp[r][i] = 0.f;
+        for (int i = 0; i < a.AS; i += 4) ab[r].st4(i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
+    ActBuf<TM>::wait_st();
     // vec slots (floats)
     const int oV = 0;                 // v_k, k = 0..K     (variable space)
     const int oU = (K + 1) * D;       // u_k, k = 0..K-1
@@ -272,21 +353,42 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                         os[r][jj] = jj < D ? bo[DP + jj] : 0.f;
                     }
                 }
+                // ---- the context projection of this transform goes into the activation buffer first (16 loads in
+                // flight per pair); layer 0 then updates it in place, so the hot loop has no global-memory dependence
+                for (int u0 = 0; u0 < H0; u0 += 16) {
+                    float av[RP][16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const int u = min(u0 + c, H0 - 1);
+#pragma unroll
+                        for (int r = 0; r < RP; ++r) av[r][c] = live[r] ? __ldg(Aptr[r] + (size_t)u * a.B) : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (u0 + 4 * q < H0) {
+#pragma unroll
+                            for (int r = 0; r < RP; ++r)
+                                ab[r].st4(u0 + 4 * q, make_float4(av[r][4 * q], av[r][4 * q + 1], av[r][4 * q + 2], av[r][4 * q + 3]));
+                        }
+                }
+                ActBuf<TM>::wait_st();
                 for (int j = 0; j < D; ++j) {
-                    // ---- layer-0 units of degree j: act = relu(A[u] + W0t[u] . y), 4 units per batch
+                    // ---- layer-0 units of degree j: act = relu(A[u] + W0t[u] . y), aligned quads updated in place
                     {
                         const int ua = grp0[j], ub = grp0[j + 1];
-                        for (int u0 = ua; u0 < ub; u0 += 4) {
+                        for (int u0 = ua & ~3; u0 < ub; u0 += 4) {
+                            float4 av[RP];
+#pragma unroll
+                            for (int r = 0; r < RP; ++r) av[r] = ab[r].ld4(u0);
                             float pre[RP][4];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const int u = min(u0 + c, ub - 1);
-#pragma unroll
-                                for (int r = 0; r < RP; ++r) pre[r][c] = live[r] ? __ldg(Aptr[r] + (size_t)u * a.B) : 0.f;
+                            for (int r = 0; r < RP; ++r) {
+                                ActBuf<TM>::wait_ld(av[r]);
+                                pre[r][0] = av[r].x; pre[r][1] = av[r].y; pre[r][2] = av[r].z; pre[r][3] = av[r].w;
                             }
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                const int u = min(u0 + c, ub - 1);
+                                const int u = min(u0 + c, H0 - 1);
 #pragma unroll
                                 for (int q4 = 0; q4 < DP / 4; ++q4) {
                                     const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
@@ -300,13 +402,14 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                                 }
                             }
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const int u = u0 + c;
-                                if (u < ub) {
+                            for (int r = 0; r < RP; ++r) {
+                                float nv[4] = {av[r].x, av[r].y, av[r].z, av[r].w};
 #pragma unroll
-                                    for (int r = 0; r < RP; ++r) {
+                                for (int c = 0; c < 4; ++c) {
+                                    const int u = u0 + c;
+                                    if (u >= ua && u < ub) {
                                         const bool on = pre[r][c] > 0.f;
-                                        actp[r][u] = on ? pre[r][c] : 0.f;
+                                        nv[c] = on ? pre[r][c] : 0.f;
                                         if (MODE == FAST_GRAD) {
                                             if (on) w0[r] |= 1u << (u & 31);
                                             if ((u & 31) == 31 || u == H0 - 1) {
@@ -316,8 +419,10 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                                         }
                                     }
                                 }
+                                ab[r].st4(u0, make_float4(nv[0], nv[1], nv[2], nv[3]));
                             }
                         }
+                        ActBuf<TM>::wait_st();
                     }
                     // ---- layer-1 units of degree j (prefix grp0[j+1]) -> relu bits + output accumulators
                     {
@@ -326,7 +431,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                         auto block = [&](auto NRtag, int v0, int nv) {
                             constexpr int NR = decltype(NRtag)::value;
                             float h[RP][NR];
-                            dot_block<RP, NR>(W1 + (size_t)v0 * ld1, ld1, nv - 1, e4, actp, h);
+                            dot_block<RP, NR, TM>(W1 + (size_t)v0 * ld1, ld1, nv - 1, e4, ab, h);
 #pragma unroll
                             for (int c = 0; c < NR; ++c) {
                                 if (c < nv) {
@@ -491,11 +596,12 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
 #pragma unroll
                                     for (int r = 0; r < RP; ++r) {
                                         const bool on = (bitp[r][(bs + 1) * WL + (v >> 5)] >> (v & 31)) & 1u;
-                                        actp[r][v] = on ? gs[r][c] : 0.f;
+                                        ab[r].st1(v, on ? gs[r][c] : 0.f);
                                     }
                                 }
                             }
                         }
+                        ActBuf<TM>::wait_st();
                     }
                     // ---- layer-0 cotangents of the degree-j units (consumed by layer-1 rows >= grp1[j])
                     {
@@ -504,7 +610,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                         auto cblock = [&](auto NCtag, int u0) {
                             constexpr int NC = decltype(NCtag)::value;
                             float g0[RP][NC];
-                            tdot_block<RP, NC>(W1 + u0, ld1, va4, vb4, actp, g0);
+                            tdot_block<RP, NC, TM>(W1 + u0, ld1, va4, vb4, ab, g0);
                             uint32_t wb[RP];
 #pragma unroll
                             for (int r = 0; r < RP; ++r) wb[r] = bitp[r][bs * WL + (u0 >> 5)] >> (u0 & 31);
@@ -557,6 +663,13 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                 }
             }
         }
+    }
+    if (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"((uint32_t)a.tm_cols)
+                         : "memory");
     }
 }
 

@@ -745,10 +745,10 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-template <int MODE, int RP, int DP>
+template <int MODE, int RP, int DP, bool TM>
 static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel, int grid, int T, size_t smem,
                             cudaStream_t st) {
-    CU_OK(h, cudaFuncSetAttribute(k_fast<MODE, RP, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_OK(h, cudaFuncSetAttribute(k_fast<MODE, RP, DP, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool prof = h->profiling && MODE == FAST_GRAD;
     if (prof) {
         if (h->prof_used == h->prof_events.size()) {
@@ -759,7 +759,7 @@ static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel,
         }
         CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].first, st));
     }
-    k_fast<MODE, RP, DP><<<grid, T, smem, st>>>(h->img, fa, rel);
+    k_fast<MODE, RP, DP, TM><<<grid, T, smem, st>>>(h->img, fa, rel);
     LAUNCH_CHECK(h);
     if (prof) {
         CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].second, st));
@@ -792,22 +792,28 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     rel.first1 = t0.first[1] - t0.perm;
     fa.wfloats = t0.fast_end - t0.W0t;
     fa.wints = (t0.meta_fast_end - t0.perm + 3) & ~3;
+    const int RP = env_int("RABI_FAST_RP", 1) == 2 ? 2 : 1;
+    // activations in tensor memory (default) or in shared memory
+    const bool TM = RP == 1 && env_int("RABI_FAST_TMEM", 1) != 0 && std::max(round4(H0), round4(H1)) <= 512;
     int AS = std::max(round4(H0), round4(H1));
-    if (((AS / 4) & 1) == 0) AS += 4;  // AS/4 odd: 128-bit accesses of consecutive slots hit distinct bank groups
+    if (!TM && ((AS / 4) & 1) == 0) AS += 4;  // AS/4 odd: 128-bit accesses of consecutive slots hit distinct bank groups
     fa.AS = AS;
     fa.VS = ((4 * K + 2) * D) | 1;
     const int WL = (g.Hmax + 31) / 32;
     fa.BWS = MODE == FAST_GRAD ? ((2 * K * 2 * WL) | 1) : 0;
-    const int RP = env_int("RABI_FAST_RP", 1) == 2 ? 2 : 1;
-    const size_t per_slot = (size_t)(fa.AS + fa.VS + fa.BWS) * sizeof(float);
+    const size_t per_slot = (size_t)((TM ? 0 : fa.AS) + fa.VS + fa.BWS) * sizeof(float);
     const size_t fixed = (size_t)(fa.wfloats + fa.wints) * sizeof(float);
     const size_t budget = (size_t)h->max_smem_optin - 1024;
     const int Tmax = RP == 1 ? 384 : 256;  // matches __launch_bounds__ of k_fast
     int T = env_int("RABI_FAST_T", Tmax);
     T = std::max(32, std::min(Tmax, (T / 32) * 32));
+    if (TM) {  // every group of 4 warps needs RP*AS of the 512 tensor-memory columns
+        while (T > 32 && ((T / 32 + 3) / 4) * RP * AS > 512) T -= 32;
+    }
     int grid = 0;
     size_t smem = 0;
     const long long npairs = (long long)fa.S * fa.B;
+    auto gat_bytes = [&](int tbp) { return (((size_t)H0 * tbp + 3) & ~(size_t)3) * sizeof(float); };
     if (MODE == FAST_GRAD) {
         // largest T whose slots (+ the gA tile for the rows they hold) fit
         for (;; T -= 32) {
@@ -815,8 +821,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
             int slots = RP * T;
             int tb = slots / fa.S;
             if (tb < 1) return 2;  // one row's samples do not fit in a tile
-            fa.TBp = tb | 1;
-            smem = fixed + (((size_t)H0 * fa.TBp + 3) & ~(size_t)3) * sizeof(float) + (size_t)slots * per_slot;
+            smem = fixed + gat_bytes(tb | 1) + (size_t)slots * per_slot;
             if (smem <= budget) break;
         }
         int tb_cap = (RP * T) / fa.S;
@@ -828,7 +833,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
         int Tneed = ((fa.TB * fa.S + RP - 1) / RP + 31) & ~31;     // no idle warps
         T = std::min(T, std::max(32, Tneed));
         fa.TBp = fa.TB | 1;
-        smem = fixed + (((size_t)H0 * fa.TBp + 3) & ~(size_t)3) * sizeof(float) + (size_t)RP * T * per_slot;
+        smem = fixed + gat_bytes(fa.TBp) + (size_t)RP * T * per_slot;
         grid = std::min(fa.ntiles, h->sm_count);
     } else {
         for (;; T -= 32) {
@@ -843,12 +848,18 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
         fa.ntiles = (int)nt;
         grid = (int)std::min<long long>(nt, h->sm_count);
     }
-#define RABI_FAST_CASE(RPv, DPv) \
-    if (RP == RPv && DP == DPv) return launch_fast_inst<MODE, RPv, DPv>(h, fa, rel, grid, T, smem, st);
-    RABI_FAST_CASE(2, 4)
-    RABI_FAST_CASE(2, 8)
-    RABI_FAST_CASE(2, 12)
-    RABI_FAST_CASE(1, 4)
+    fa.tm_cols = 32;
+    if (TM) {
+        int need = ((T / 32 + 3) / 4) * RP * AS;
+        while (fa.tm_cols < need) fa.tm_cols *= 2;
+    }
+#define RABI_FAST_CASE(RPv, DPv, TMv) \
+    if (RP == RPv && DP == DPv && TM == TMv) return launch_fast_inst<MODE, RPv, DPv, TMv>(h, fa, rel, grid, T, smem, st);
+    RABI_FAST_CASE(1, 4, true)
+    RABI_FAST_CASE(1, 8, true)
+    RABI_FAST_CASE(1, 12, true)
+    RABI_FAST_CASE(1, 4, false)
+    RABI_FAST_CASE(2, 4, false)
 #undef RABI_FAST_CASE
     return 2;
 }
