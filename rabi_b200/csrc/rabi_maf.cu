@@ -445,15 +445,23 @@ static int ensure_ws(rabi_maf* h, size_t bytes) {
 
 // ---------------------------------------------------------------------------------------------------------
 // context projection:  A[k,u,b] = b0_k[u] + sum_c W0_k[u,c] * ((x[b,c] (+ delta[b,c]) - mean[c]) / std[c])
-constexpr int CP_ROWS = 8;
-__global__ void k_ctx_project(MafImg g, const float* __restrict__ x, const float* __restrict__ delta,
-                              const float* __restrict__ zmean, const float* __restrict__ zstd, int B,
-                              float* __restrict__ A) {
-    extern __shared__ float cs[];  // [C][CP_ROWS]
-    const int C = g.C, K = g.K, H0 = g.H[0];
+// Register-tiled, shared-memory-staged GEMMs (4 rows x 8 outputs per thread, packed fma.rn.f32x2):
+//   forward : A[k,u,b] = b0_k[u] + sum_c W0_k[u,c] * ctx[b,c],  ctx = ((x (+ delta)) - mean) / std     (grid.y = k)
+//   backward: gx[b,c]  = (1/std[c]) * sum_{k,u} W0_k[u,c] * gA[k,u,b]
+constexpr int CP_ROWS = 64;   // rows per block
+constexpr int CP_RG = 16;     // row groups of 4 rows
+__global__ void __launch_bounds__(256) k_ctx_project(MafImg g, const float* __restrict__ x, const float* __restrict__ delta,
+                                                     const float* __restrict__ zmean, const float* __restrict__ zstd, int B,
+                                                     float* __restrict__ A) {
+    extern __shared__ __align__(16) float sm[];
+    const int C = g.C, H0 = g.H[0], k = blockIdx.y;
+    const int ldw = g.ldKH;                  // W0cT: [C][ldKH], column k*H0p + u
+    const int Hp8 = (H0 + 7) & ~7;
+    float* Xs = sm;                          // [C][CP_ROWS]
+    float* Wsm = sm + (size_t)C * CP_ROWS;   // [C][Hp8]
     const int b0 = blockIdx.x * CP_ROWS;
     for (int i = threadIdx.x; i < C * CP_ROWS; i += blockDim.x) {
-        int r = i / C, c = i % C;
+        int r = i / C, c = i % C;  // coalesced over c
         int b = b0 + r;
         float v = 0.f;
         if (b < B) {
@@ -461,80 +469,128 @@ __global__ void k_ctx_project(MafImg g, const float* __restrict__ x, const float
             if (delta) v += delta[(size_t)b * C + c];
             if (zmean) v = (v - zmean[c]) / zstd[c];
         }
-        cs[c * CP_ROWS + r] = v;
+        Xs[c * CP_ROWS + r] = v;
+    }
+    for (int i = threadIdx.x; i < C * Hp8; i += blockDim.x) {
+        int c = i / Hp8, u = i % Hp8;
+        Wsm[i] = (u < H0) ? __ldg(g.f + g.W0cT + (size_t)c * ldw + k * g.H0p + u) : 0.f;
     }
     __syncthreads();
-    const int ncol = K * g.H0p;
-    for (int col = threadIdx.x; col < ncol; col += blockDim.x) {
-        int k = col / g.H0p, u = col % g.H0p;
-        if (u >= H0) continue;
-        float acc[CP_ROWS];
-        float bias = g.f[g.t[k].b0 + u];
+    const int ng = Hp8 / 8;  // unit groups of 8
+    for (int t = threadIdx.x; t < ng * CP_RG; t += blockDim.x) {
+        const int rg = t % CP_RG, ug = t / CP_RG;
+        float2 acc[4][4];
 #pragma unroll
-        for (int r = 0; r < CP_ROWS; ++r) acc[r] = bias;
-        const float* w = g.f + g.W0cT + col;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 4
         for (int c = 0; c < C; ++c) {
-            float wv = __ldg(w + (size_t)c * g.ldKH);
-            const float4 c0 = *reinterpret_cast<const float4*>(cs + c * CP_ROWS);
-            const float4 c1 = *reinterpret_cast<const float4*>(cs + c * CP_ROWS + 4);
-            acc[0] = fmaf(wv, c0.x, acc[0]);
-            acc[1] = fmaf(wv, c0.y, acc[1]);
-            acc[2] = fmaf(wv, c0.z, acc[2]);
-            acc[3] = fmaf(wv, c0.w, acc[3]);
-            acc[4] = fmaf(wv, c1.x, acc[4]);
-            acc[5] = fmaf(wv, c1.y, acc[5]);
-            acc[6] = fmaf(wv, c1.z, acc[6]);
-            acc[7] = fmaf(wv, c1.w, acc[7]);
-        }
-        float* out = A + ((size_t)k * H0 + u) * B + b0;
+            const float4 xv = *reinterpret_cast<const float4*>(Xs + c * CP_ROWS + 4 * rg);
+            const float4 w0 = *reinterpret_cast<const float4*>(Wsm + c * Hp8 + 8 * ug);
+            const float4 w1 = *reinterpret_cast<const float4*>(Wsm + c * Hp8 + 8 * ug + 4);
+            const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-        for (int r = 0; r < CP_ROWS; ++r)
-            if (b0 + r < B) out[r] = acc[r];
+            for (int i = 0; i < 4; ++i) {
+                const float2 xx = make_float2(xr[i], xr[i]);
+                acc[i][0] = ffma2(make_float2(w0.x, w0.y), xx, acc[i][0]);
+                acc[i][1] = ffma2(make_float2(w0.z, w0.w), xx, acc[i][1]);
+                acc[i][2] = ffma2(make_float2(w1.x, w1.y), xx, acc[i][2]);
+                acc[i][3] = ffma2(make_float2(w1.z, w1.w), xx, acc[i][3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int u = 8 * ug + j;
+            if (u >= H0) continue;
+            const float bias = g.f[g.t[k].b0 + u];
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = bias + ((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x);
+            float* out = A + ((size_t)k * H0 + u) * B + b0 + 4 * rg;
+            if (b0 + 4 * rg + 3 < B && (B & 3) == 0) {
+                *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (b0 + 4 * rg + i < B) out[i] = o[i];
+            }
+        }
     }
 }
 
-// transposed projection: gx[b,c] = (1/std[c]) * sum_{k,u} W0_k[u,c] * gA[k,u,b]
-__global__ void k_ctx_project_bwd(MafImg g, const float* __restrict__ gA, const float* __restrict__ zstd, int B,
-                                  float* __restrict__ gx, int accumulate) {
-    extern __shared__ float gs[];  // [K*H0][CP_ROWS]
+__global__ void __launch_bounds__(256) k_ctx_project_bwd(MafImg g, const float* __restrict__ gA,
+                                                         const float* __restrict__ zstd, int B, float* __restrict__ gx,
+                                                         int accumulate) {
+    extern __shared__ __align__(16) float sm[];
     const int C = g.C, K = g.K, H0 = g.H[0];
+    const int Cp8 = (C + 7) & ~7;
+    float* Gs = sm;                           // [H0][CP_ROWS]
+    float* Wsm = sm + (size_t)H0 * CP_ROWS;   // [H0][Cp8]
     const int b0 = blockIdx.x * CP_ROWS;
-    const int n = K * H0;
-    for (int i = threadIdx.x; i < n * CP_ROWS; i += blockDim.x) {
-        int ku = i / CP_ROWS, r = i % CP_ROWS;
-        gs[i] = (b0 + r < B) ? gA[(size_t)ku * B + b0 + r] : 0.f;
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc[CP_ROWS];
+    const int ng = Cp8 / 8;
+    // each thread owns up to two (row group, column group) tiles so that the k loop can reuse the staging buffers
+    float2 acc[2][4][4];
 #pragma unroll
-        for (int r = 0; r < CP_ROWS; ++r) acc[r] = 0.f;
-        for (int k = 0; k < K; ++k) {
-            const float* w = g.f + g.t[k].W0c + c;
-            const int ldc = g.t[k].ldc;
-            const float* gk = gs + (size_t)k * H0 * CP_ROWS;
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[s][i][j] = make_float2(0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < H0 * CP_ROWS; i += blockDim.x) {
+            int u = i / CP_ROWS, r = i % CP_ROWS;  // coalesced over rows
+            Gs[i] = (b0 + r < B) ? gA[((size_t)k * H0 + u) * B + b0 + r] : 0.f;
+        }
+        const float* W = g.f + g.t[k].W0c;
+        const int ldc = g.t[k].ldc;
+        for (int i = threadIdx.x; i < H0 * Cp8; i += blockDim.x) {
+            int u = i / Cp8, c = i % Cp8;
+            Wsm[i] = (c < C) ? __ldg(W + (size_t)u * ldc + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int t = threadIdx.x + s * blockDim.x;
+            if (t >= ng * CP_RG) continue;
+            const int rg = t % CP_RG, cg = t / CP_RG;
+#pragma unroll 4
             for (int u = 0; u < H0; ++u) {
-                float wv = __ldg(w + (size_t)u * ldc);
-                const float4 c0 = *reinterpret_cast<const float4*>(gk + u * CP_ROWS);
-                const float4 c1 = *reinterpret_cast<const float4*>(gk + u * CP_ROWS + 4);
-                acc[0] = fmaf(wv, c0.x, acc[0]);
-                acc[1] = fmaf(wv, c0.y, acc[1]);
-                acc[2] = fmaf(wv, c0.z, acc[2]);
-                acc[3] = fmaf(wv, c0.w, acc[3]);
-                acc[4] = fmaf(wv, c1.x, acc[4]);
-                acc[5] = fmaf(wv, c1.y, acc[5]);
-                acc[6] = fmaf(wv, c1.z, acc[6]);
-                acc[7] = fmaf(wv, c1.w, acc[7]);
+                const float4 gv = *reinterpret_cast<const float4*>(Gs + u * CP_ROWS + 4 * rg);
+                const float4 w0 = *reinterpret_cast<const float4*>(Wsm + u * Cp8 + 8 * cg);
+                const float4 w1 = *reinterpret_cast<const float4*>(Wsm + u * Cp8 + 8 * cg + 4);
+                const float gr[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 gg = make_float2(gr[i], gr[i]);
+                    acc[s][i][0] = ffma2(make_float2(w0.x, w0.y), gg, acc[s][i][0]);
+                    acc[s][i][1] = ffma2(make_float2(w0.z, w0.w), gg, acc[s][i][1]);
+                    acc[s][i][2] = ffma2(make_float2(w1.x, w1.y), gg, acc[s][i][2]);
+                    acc[s][i][3] = ffma2(make_float2(w1.z, w1.w), gg, acc[s][i][3]);
+                }
             }
         }
-        float inv = zstd ? 1.f / zstd[c] : 1.f;
+    }
 #pragma unroll
-        for (int r = 0; r < CP_ROWS; ++r)
-            if (b0 + r < B) {
-                float v = acc[r] * inv;
-                float* o = gx + (size_t)(b0 + r) * C + c;
+    for (int s = 0; s < 2; ++s) {
+        const int t = threadIdx.x + s * blockDim.x;
+        if (t >= ng * CP_RG) continue;
+        const int rg = t % CP_RG, cg = t / CP_RG;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = b0 + 4 * rg + i;
+            if (b >= B) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = 8 * cg + j;
+                if (c >= C) continue;
+                float v = (j & 1) ? acc[s][i][j >> 1].y : acc[s][i][j >> 1].x;
+                if (zstd) v /= zstd[c];
+                float* o = gx + (size_t)b * C + c;
                 *o = accumulate ? *o + v : v;
             }
+        }
     }
 }
 
@@ -583,9 +639,12 @@ __global__ void k_clamp_add(const float* __restrict__ x, const float* __restrict
 static int launch_ctx_project(rabi_maf* h, const float* x, const float* delta, const float* zm, const float* zs, int B,
                               float* A, cudaStream_t st) {
     if ((zm == nullptr) != (zs == nullptr)) return fail(h, "zs_mean and zs_std must both be given or both be NULL");
-    size_t smem = (size_t)h->C * CP_ROWS * sizeof(float);
-    if (smem > 48 * 1024) CU_OK(h, cudaFuncSetAttribute(k_ctx_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ctx_project<<<(B + CP_ROWS - 1) / CP_ROWS, 128, smem, st>>>(h->img, x, delta, zm, zs, B, A);
+    const int Hp8 = (h->H[0] + 7) & ~7;
+    size_t smem = ((size_t)h->C * CP_ROWS + (size_t)h->C * Hp8) * sizeof(float);
+    if (smem > (size_t)h->max_smem_optin) return fail(h, "context dimension %d too large for the projection kernel", h->C);
+    CU_OK(h, cudaFuncSetAttribute(k_ctx_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((B + CP_ROWS - 1) / CP_ROWS, h->K);
+    k_ctx_project<<<grid, 256, smem, st>>>(h->img, x, delta, zm, zs, B, A);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -599,10 +658,12 @@ extern "C" int rabi_maf_ctx_project(rabi_maf_t* h, const float* x_dev, const flo
 
 static int launch_ctx_project_bwd(rabi_maf* h, const float* gA, const float* zs, int B, float* gx, int accumulate,
                                   cudaStream_t st) {
-    size_t smem = (size_t)h->K * h->H[0] * CP_ROWS * sizeof(float);
-    if (smem > 48 * 1024)
-        CU_OK(h, cudaFuncSetAttribute(k_ctx_project_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ctx_project_bwd<<<(B + CP_ROWS - 1) / CP_ROWS, 128, smem, st>>>(h->img, gA, zs, B, gx, accumulate);
+    const int Cp8 = (h->C + 7) & ~7;
+    if ((Cp8 / 8) * CP_RG > 512) return fail(h, "context dimension %d too large for the projection kernel", h->C);
+    size_t smem = ((size_t)h->H[0] * CP_ROWS + (size_t)h->H[0] * Cp8) * sizeof(float);
+    if (smem > (size_t)h->max_smem_optin) return fail(h, "context dimension %d too large for the projection kernel", h->C);
+    CU_OK(h, cudaFuncSetAttribute(k_ctx_project_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ctx_project_bwd<<<(B + CP_ROWS - 1) / CP_ROWS, 256, smem, st>>>(h->img, gA, zs, B, gx, accumulate);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -794,7 +855,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     fa.wints = (t0.meta_fast_end - t0.perm + 3) & ~3;
     const int RP = env_int("RABI_FAST_RP", 1) == 2 ? 2 : 1;
     // activations in tensor memory (default) or in shared memory
-    const bool TM = RP == 1 && env_int("RABI_FAST_TMEM", 1) != 0 && std::max(round4(H0), round4(H1)) <= 512;
+    const bool TM = env_int("RABI_FAST_TMEM", 1) != 0 && RP * std::max(round4(H0), round4(H1)) <= 512 && (RP == 1 || DP == 4);
     int AS = std::max(round4(H0), round4(H1));
     if (!TM && ((AS / 4) & 1) == 0) AS += 4;  // AS/4 odd: 128-bit accesses of consecutive slots hit distinct bank groups
     fa.AS = AS;
@@ -860,6 +921,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     RABI_FAST_CASE(1, 12, true)
     RABI_FAST_CASE(1, 4, false)
     RABI_FAST_CASE(2, 4, false)
+    RABI_FAST_CASE(2, 4, true)
 #undef RABI_FAST_CASE
     return 2;
 }
