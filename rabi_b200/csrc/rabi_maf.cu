@@ -448,37 +448,64 @@ static int ensure_ws(rabi_maf* h, size_t bytes) {
 // Register-tiled, shared-memory-staged GEMMs (4 rows x 8 outputs per thread, packed fma.rn.f32x2):
 //   forward : A[k,u,b] = b0_k[u] + sum_c W0_k[u,c] * ctx[b,c],  ctx = ((x (+ delta)) - mean) / std     (grid.y = k)
 //   backward: gx[b,c]  = (1/std[c]) * sum_{k,u} W0_k[u,c] * gA[k,u,b]
-constexpr int CP_ROWS = 64;   // rows per block
-constexpr int CP_RG = 16;     // row groups of 4 rows
+constexpr int CP_MAXROWS = 80;  // max rows per block (forward); the launcher picks a multiple of 4 that fills one wave
+constexpr int CP_LD = 84;       // padded row stride of the transposed x tile
+constexpr int CPB_ROWS = 32;    // rows per block (backward)
 __global__ void __launch_bounds__(256) k_ctx_project(MafImg g, const float* __restrict__ x, const float* __restrict__ delta,
                                                      const float* __restrict__ zmean, const float* __restrict__ zstd, int B,
-                                                     float* __restrict__ A) {
+                                                     float* __restrict__ A, int rows) {
     extern __shared__ __align__(16) float sm[];
     const int C = g.C, H0 = g.H[0], k = blockIdx.y;
     const int ldw = g.ldKH;                  // W0cT: [C][ldKH], column k*H0p + u
     const int Hp8 = (H0 + 7) & ~7;
-    float* Xs = sm;                          // [C][CP_ROWS]
-    float* Wsm = sm + (size_t)C * CP_ROWS;   // [C][Hp8]
-    const int b0 = blockIdx.x * CP_ROWS;
-    for (int i = threadIdx.x; i < C * CP_ROWS; i += blockDim.x) {
-        int r = i / C, c = i % C;  // coalesced over c
-        int b = b0 + r;
-        float v = 0.f;
-        if (b < B) {
-            v = x[(size_t)b * C + c];
-            if (delta) v += delta[(size_t)b * C + c];
-            if (zmean) v = (v - zmean[c]) / zstd[c];
+    float* Xs = sm;                          // [C][CP_LD]   ctx tile, transposed
+    float* Wsm = sm + (size_t)C * CP_LD;     // [C][Hp8]
+    const int b0 = blockIdx.x * rows;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+    // x tile: lanes walk the context dimension (coalesced), warps walk the rows; loads are issued in batches of 10
+    for (int c = tx; c < C; c += 32) {
+        const float mu = zmean ? zmean[c] : 0.f, sd = zmean ? zstd[c] : 1.f;
+        float v[CP_MAXROWS / 8];
+#pragma unroll
+        for (int it = 0; it < CP_MAXROWS / 8; ++it) {
+            const int r = ty + 8 * it, b = b0 + r;
+            v[it] = (r < rows && b < B) ? x[(size_t)b * C + c] : 0.f;
         }
-        Xs[c * CP_ROWS + r] = v;
+        if (delta) {
+#pragma unroll
+            for (int it = 0; it < CP_MAXROWS / 8; ++it) {
+                const int r = ty + 8 * it, b = b0 + r;
+                if (r < rows && b < B) v[it] += delta[(size_t)b * C + c];
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < CP_MAXROWS / 8; ++it) {
+            const int r = ty + 8 * it;
+            if (r < rows) Xs[c * CP_LD + r] = (b0 + r < B) ? (zmean ? (v[it] - mu) / sd : v[it]) : 0.f;
+        }
     }
-    for (int i = threadIdx.x; i < C * Hp8; i += blockDim.x) {
-        int c = i / Hp8, u = i % Hp8;
-        Wsm[i] = (u < H0) ? __ldg(g.f + g.W0cT + (size_t)c * ldw + k * g.H0p + u) : 0.f;
+    // weight slice of transform k, 128-bit rows, 13 loads in flight per thread
+    const int n4 = Hp8 >> 2, h4 = g.H0p >> 2;
+    for (int q = tx; q < n4; q += 32) {
+        for (int c0 = ty; c0 < C; c0 += 8 * 13) {
+            float4 w[13];
+#pragma unroll
+            for (int it = 0; it < 13; ++it) {
+                const int c = c0 + 8 * it;
+                w[it] = (c < C && q < h4) ? __ldg(reinterpret_cast<const float4*>(g.f + g.W0cT + (size_t)c * ldw + k * g.H0p) + q)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < 13; ++it) {
+                const int c = c0 + 8 * it;
+                if (c < C) reinterpret_cast<float4*>(Wsm + (size_t)c * Hp8)[q] = w[it];
+            }
+        }
     }
     __syncthreads();
-    const int ng = Hp8 / 8;  // unit groups of 8
-    for (int t = threadIdx.x; t < ng * CP_RG; t += blockDim.x) {
-        const int rg = t % CP_RG, ug = t / CP_RG;
+    const int ng = Hp8 / 8, RG = rows >> 2;  // unit groups of 8, row groups of 4
+    for (int t = threadIdx.x; t < ng * RG; t += blockDim.x) {
+        const int rg = t % RG, ug = t / RG;
         float2 acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -486,7 +513,7 @@ __global__ void __launch_bounds__(256) k_ctx_project(MafImg g, const float* __re
             for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 #pragma unroll 4
         for (int c = 0; c < C; ++c) {
-            const float4 xv = *reinterpret_cast<const float4*>(Xs + c * CP_ROWS + 4 * rg);
+            const float4 xv = *reinterpret_cast<const float4*>(Xs + c * CP_LD + 4 * rg);
             const float4 w0 = *reinterpret_cast<const float4*>(Wsm + c * Hp8 + 8 * ug);
             const float4 w1 = *reinterpret_cast<const float4*>(Wsm + c * Hp8 + 8 * ug + 4);
             const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -519,17 +546,18 @@ __global__ void __launch_bounds__(256) k_ctx_project(MafImg g, const float* __re
     }
 }
 
-__global__ void __launch_bounds__(256) k_ctx_project_bwd(MafImg g, const float* __restrict__ gA,
+__global__ void __launch_bounds__(128) k_ctx_project_bwd(MafImg g, const float* __restrict__ gA,
                                                          const float* __restrict__ zstd, int B, float* __restrict__ gx,
                                                          int accumulate) {
     extern __shared__ __align__(16) float sm[];
     const int C = g.C, K = g.K, H0 = g.H[0];
     const int Cp8 = (C + 7) & ~7;
-    float* Gs = sm;                           // [H0][CP_ROWS]
-    float* Wsm = sm + (size_t)H0 * CP_ROWS;   // [H0][Cp8]
-    const int b0 = blockIdx.x * CP_ROWS;
-    const int ng = Cp8 / 8;
-    // each thread owns up to two (row group, column group) tiles so that the k loop can reuse the staging buffers
+    float* Gs = sm;                            // [H0][CPB_ROWS]
+    float* Wsm = sm + (size_t)H0 * CPB_ROWS;   // [H0][Cp8]
+    const int b0 = blockIdx.x * CPB_ROWS;
+    const int ng = Cp8 / 8, RG = CPB_ROWS / 4;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 4 warps
+    // each thread owns up to two (row group, column group) tiles (covers C <= 256 with 128 threads)
     float2 acc[2][4][4];
 #pragma unroll
     for (int s = 0; s < 2; ++s)
@@ -539,25 +567,47 @@ __global__ void __launch_bounds__(256) k_ctx_project_bwd(MafImg g, const float* 
             for (int j = 0; j < 4; ++j) acc[s][i][j] = make_float2(0.f, 0.f);
     for (int k = 0; k < K; ++k) {
         __syncthreads();
-        for (int i = threadIdx.x; i < H0 * CP_ROWS; i += blockDim.x) {
-            int u = i / CP_ROWS, r = i % CP_ROWS;  // coalesced over rows
-            Gs[i] = (b0 + r < B) ? gA[((size_t)k * H0 + u) * B + b0 + r] : 0.f;
+        // cotangent tile: lanes walk the rows (coalesced); all loads of a thread are issued before the stores
+        for (int u0 = ty; u0 < H0; u0 += 4 * 13) {
+            float gv[13];
+#pragma unroll
+            for (int it = 0; it < 13; ++it) {
+                const int u = u0 + 4 * it;
+                gv[it] = (u < H0 && b0 + tx < B) ? gA[((size_t)k * H0 + u) * B + b0 + tx] : 0.f;
+            }
+#pragma unroll
+            for (int it = 0; it < 13; ++it) {
+                const int u = u0 + 4 * it;
+                if (u < H0) Gs[u * CPB_ROWS + tx] = gv[it];
+            }
         }
         const float* W = g.f + g.t[k].W0c;
-        const int ldc = g.t[k].ldc;
-        for (int i = threadIdx.x; i < H0 * Cp8; i += blockDim.x) {
-            int u = i / Cp8, c = i % Cp8;
-            Wsm[i] = (c < C) ? __ldg(W + (size_t)u * ldc + c) : 0.f;
+        const int ldc = g.t[k].ldc, n4 = Cp8 >> 2, c4 = ldc >> 2;
+        for (int q = tx; q < n4; q += 32) {
+            for (int u0 = ty; u0 < H0; u0 += 4 * 13) {
+                float4 w[13];
+#pragma unroll
+                for (int it = 0; it < 13; ++it) {
+                    const int u = u0 + 4 * it;
+                    w[it] = (u < H0 && q < c4) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)u * ldc) + q)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int it = 0; it < 13; ++it) {
+                    const int u = u0 + 4 * it;
+                    if (u < H0) reinterpret_cast<float4*>(Wsm + (size_t)u * Cp8)[q] = w[it];
+                }
+            }
         }
         __syncthreads();
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int t = threadIdx.x + s * blockDim.x;
-            if (t >= ng * CP_RG) continue;
-            const int rg = t % CP_RG, cg = t / CP_RG;
+            if (t >= ng * RG) continue;
+            const int rg = t % RG, cg = t / RG;
 #pragma unroll 4
             for (int u = 0; u < H0; ++u) {
-                const float4 gv = *reinterpret_cast<const float4*>(Gs + u * CP_ROWS + 4 * rg);
+                const float4 gv = *reinterpret_cast<const float4*>(Gs + u * CPB_ROWS + 4 * rg);
                 const float4 w0 = *reinterpret_cast<const float4*>(Wsm + u * Cp8 + 8 * cg);
                 const float4 w1 = *reinterpret_cast<const float4*>(Wsm + u * Cp8 + 8 * cg + 4);
                 const float gr[4] = {gv.x, gv.y, gv.z, gv.w};
@@ -575,8 +625,8 @@ __global__ void __launch_bounds__(256) k_ctx_project_bwd(MafImg g, const float* 
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int t = threadIdx.x + s * blockDim.x;
-        if (t >= ng * CP_RG) continue;
-        const int rg = t % CP_RG, cg = t / CP_RG;
+        if (t >= ng * RG) continue;
+        const int rg = t % RG, cg = t / RG;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int b = b0 + 4 * rg + i;
@@ -640,11 +690,20 @@ static int launch_ctx_project(rabi_maf* h, const float* x, const float* delta, c
                               float* A, cudaStream_t st) {
     if ((zm == nullptr) != (zs == nullptr)) return fail(h, "zs_mean and zs_std must both be given or both be NULL");
     const int Hp8 = (h->H[0] + 7) & ~7;
-    size_t smem = ((size_t)h->C * CP_ROWS + (size_t)h->C * Hp8) * sizeof(float);
+    size_t smem = ((size_t)h->C * CP_LD + (size_t)h->C * Hp8) * sizeof(float);
     if (smem > (size_t)h->max_smem_optin) return fail(h, "context dimension %d too large for the projection kernel", h->C);
     CU_OK(h, cudaFuncSetAttribute(k_ctx_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((B + CP_ROWS - 1) / CP_ROWS, h->K);
-    k_ctx_project<<<grid, 256, smem, st>>>(h->img, x, delta, zm, zs, B, A);
+    // rows per block: a multiple of 4 such that grid.x * K blocks fill whole waves (blocks resident per SM from smem)
+    const int per_sm = std::max(1, (int)((size_t)(h->max_smem_optin) / (smem + 1024)));
+    const int slots = std::max(1, h->sm_count * per_sm / h->K);
+    int rows = 64;
+    {
+        int waves = (B + slots * 64 - 1) / (slots * 64);
+        int tiles = std::max(1, waves * slots);
+        rows = std::min(CP_MAXROWS, std::max(4, ((B + tiles - 1) / tiles + 3) & ~3));
+    }
+    dim3 grid((B + rows - 1) / rows, h->K);
+    k_ctx_project<<<grid, 256, smem, st>>>(h->img, x, delta, zm, zs, B, A, rows);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -659,11 +718,11 @@ extern "C" int rabi_maf_ctx_project(rabi_maf_t* h, const float* x_dev, const flo
 static int launch_ctx_project_bwd(rabi_maf* h, const float* gA, const float* zs, int B, float* gx, int accumulate,
                                   cudaStream_t st) {
     const int Cp8 = (h->C + 7) & ~7;
-    if ((Cp8 / 8) * CP_RG > 512) return fail(h, "context dimension %d too large for the projection kernel", h->C);
-    size_t smem = ((size_t)h->H[0] * CP_ROWS + (size_t)h->H[0] * Cp8) * sizeof(float);
+    if ((Cp8 / 8) * (CPB_ROWS / 4) > 256) return fail(h, "context dimension %d too large for the projection kernel", h->C);
+    size_t smem = ((size_t)h->H[0] * CPB_ROWS + (size_t)h->H[0] * Cp8) * sizeof(float);
     if (smem > (size_t)h->max_smem_optin) return fail(h, "context dimension %d too large for the projection kernel", h->C);
     CU_OK(h, cudaFuncSetAttribute(k_ctx_project_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ctx_project_bwd<<<(B + CP_ROWS - 1) / CP_ROWS, 256, smem, st>>>(h->img, gA, zs, B, gx, accumulate);
+    k_ctx_project_bwd<<<(B + CPB_ROWS - 1) / CPB_ROWS, 128, smem, st>>>(h->img, gA, zs, B, gx, accumulate);
     LAUNCH_CHECK(h);
     return 0;
 }
