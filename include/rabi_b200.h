@@ -120,6 +120,15 @@ int rabi_profile_read(rabi_maf_t* h, double* total_ms, unsigned long long* launc
  * the roofline denominator of the FMA-bound kernels.  < 0 on error. */
 double rabi_fma_peak_tflops(int device, int repeats);
 
+/* fp32 GEMM primitive of the differentiable (training-side) path: C[M,N] = beta*C + op(A) * op(B); row-major with
+ * leading dimensions, op = transpose when trans* != 0.  It carries every matrix product of the first- and second-
+ * order gradients torch autograd builds for TrainLoss / FIMTraceRegularizer / L2PGDrKLTrades (rbi/rbi/loss/base.py:
+ * 142-175, defenses/fisher_regularization.py:67-95, defenses/trades_regularizers.py:58-64); the masked products
+ * F.linear(x, W*mask, b) of Pyro's MaskedLinear are instances of it. */
+int rabi_sgemm(int device, int transA, int transB, int M, int N, int K, const float* A_dev, int lda,
+               const float* B_dev, int ldb, float* C_dev, int ldc, float beta, rabi_stream_t s);
+unsigned long long rabi_sgemm_launch_count(void);
+
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 unsigned long long rabi_launch_count(const rabi_maf_t* h);
 

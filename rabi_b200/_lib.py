@@ -27,7 +27,7 @@ EXPORTS = [
     "rabi_maf_set_mask", "rabi_maf_set_post_permutation", "rabi_maf_finalize_structure", "rabi_maf_set_weights", "rabi_maf_ctx_project",
     "rabi_maf_ctx_project_bwd", "rabi_maf_log_prob_fwd", "rabi_maf_rsample_fwd", "rabi_rkl_fwd",
     "rabi_rkl_input_grad", "rabi_rkl_pgd_step", "rabi_rkl_pgd_run", "rabi_launch_count",
-    "rabi_profile", "rabi_profile_read", "rabi_fma_peak_tflops",
+    "rabi_profile", "rabi_profile_read", "rabi_fma_peak_tflops", "rabi_sgemm", "rabi_sgemm_launch_count",
 ]
 
 
@@ -106,6 +106,10 @@ def lib() -> ctypes.CDLL:
     L.rabi_profile_read.argtypes = [vp, POINTER(ctypes.c_double), POINTER(c_ulonglong)]
     L.rabi_fma_peak_tflops.argtypes = [c_int, c_int]
     L.rabi_fma_peak_tflops.restype = ctypes.c_double
+    L.rabi_sgemm.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, vp, c_int, vp, c_int, vp, c_int, c_float, vp]
+    L.rabi_sgemm.restype = c_int
+    L.rabi_sgemm_launch_count.argtypes = []
+    L.rabi_sgemm_launch_count.restype = c_ulonglong
     for name in EXPORTS:
         fn = getattr(L, name)
         if name.startswith(("rabi_maf_", "rabi_rkl_", "rabi_profile")):

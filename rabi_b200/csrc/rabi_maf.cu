@@ -1126,3 +1126,82 @@ extern "C" int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_
     }
     return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// General fp32 GEMM primitive for the differentiable (training-side) path: C[M,N] = op(A) * op(B), row-major with
+// leading dimensions (so sliced views of the masked weights / activation prefixes need no copies).  64x64 tile,
+// 16-deep K chunks in shared memory, 4x4 outputs per thread.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda,
+                                               const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                               float beta) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        for (int i = threadIdx.x; i < BM * BK; i += 256) {
+            int mm, kk;
+            if (TA) { mm = i % BM; kk = i / BM; } else { kk = i % BK; mm = i / BK; }
+            const int m = m0 + mm, k = k0 + kk;
+            As[kk][mm] = (m < M && k < K) ? (TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
+        }
+        for (int i = threadIdx.x; i < BN * BK; i += 256) {
+            int nn, kk;
+            if (TB) { kk = i % BK; nn = i / BK; } else { nn = i % BN; kk = i / BN; }
+            const int n = n0 + nn, k = k0 + kk;
+            Bs[kk][nn] = (n < N && k < K) ? (TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][4 * ty]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][4 * tx]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + 4 * ty + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 4 * tx + j;
+            if (n < N) {
+                float* c = C + (size_t)m * ldc + n;
+                *c = beta != 0.f ? beta * *c + acc[i][j] : acc[i][j];
+            }
+        }
+    }
+}
+
+static unsigned long long g_sgemm_launches = 0;
+extern "C" unsigned long long rabi_sgemm_launch_count(void) { return g_sgemm_launches; }
+
+extern "C" int rabi_sgemm(int device, int transA, int transB, int M, int N, int K, const float* A_dev, int lda,
+                          const float* B_dev, int ldb, float* C_dev, int ldc, float beta, rabi_stream_t s) {
+    if (M <= 0 || N <= 0) return 0;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, "cudaSetDevice(%d) failed", device);
+    cudaStream_t st = (cudaStream_t)s;
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    if (transA && transB) k_sgemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A_dev, lda, B_dev, ldb, C_dev, ldc, beta);
+    else if (transA) k_sgemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A_dev, lda, B_dev, ldb, C_dev, ldc, beta);
+    else if (transB) k_sgemm<false, true><<<grid, 256, 0, st>>>(M, N, K, A_dev, lda, B_dev, ldb, C_dev, ldc, beta);
+    else k_sgemm<false, false><<<grid, 256, 0, st>>>(M, N, K, A_dev, lda, B_dev, ldb, C_dev, ldc, beta);
+    g_sgemm_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, "sgemm launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}

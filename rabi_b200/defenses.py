@@ -1,0 +1,166 @@
+"""Defenses of the hot path, mirroring ``rbi.defenses`` (hydra: ``defense_module: rabi_b200.defenses``).
+
+* ``AdditiveRegularizer``            rbi/rbi/defenses/base.py:38-128   (post-loss regulariser registry on TrainLoss)
+* ``FIMTraceRegularizer``            rbi/rbi/defenses/fisher_regularization.py:15-95   (config/defense/fisher_trace.yaml)
+* ``TradesAdversarialRegularizer`` / ``L2PGDrKLTrades``   rbi/rbi/defenses/trades_regularizers.py:26-64,101-133
+                                                          (config/defense/l2pgdTrades_rKL.yaml)
+The inner L2-PGD of TRADES runs on the fused attack kernels; the regulariser values and their (first/second order)
+weight gradients run through rabi_b200/autograd.py.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+from torch import Tensor
+from torch.distributions import Distribution
+from torch.nn import Module
+
+from .attacks import Attack, L2PGDAttack
+from .fisher import ExponentialMovingAverageEstimator, monte_carlo_fisher
+from .loss import EvalLoss, ReverseKLLoss, TrainLoss
+
+
+class Defense:
+    def __init__(self, model: Module, loss_fn: Callable) -> None:
+        self.model = model
+        self.loss_fn = loss_fn
+
+    def activate(self, **kwargs):
+        raise NotImplementedError("Defense not implemented")
+
+    def deactivate(self, **kwargs):
+        raise NotImplementedError("Defense not implemented")
+
+
+class AdditiveRegularizer(Defense):
+    """Adds a regularisation term to the loss through ``TrainLoss.register_post_loss_regularizer``."""
+
+    def __init__(self, model: Module, loss_fn: Callable, reduce: str = "mean") -> None:
+        super().__init__(model, loss_fn)
+        self.reduce = reduce
+        self._regularizer = None
+        self._algorithm = None
+
+    @property
+    def regularizer(self) -> Callable:
+        if self._regularizer is None:
+            raise NotImplementedError("Your regularizer is not implemented...")
+        return self._regularizer
+
+    @property
+    def algorithm(self) -> str:
+        if self._algorithm is None:
+            raise NotImplementedError("No algorithm to compute the regularizer is implemeneted")
+        return self._algorithm
+
+    @algorithm.setter
+    def algorithm(self, method):
+        self._set_algorithm(method)
+
+    def _set_algorithm(self, method):
+        pass
+
+    def _reduce(self, reg: Tensor):
+        if self.reduce in ("mean", "sum"):  # the reference returns the mean for "sum" as well (base.py:109-110)
+            return torch.mean(reg)
+        if self.reduce == "max":
+            return torch.max(reg)
+        if self.reduce == "min":
+            return torch.min(reg)
+        raise NotImplementedError()
+
+    def activate(self, algorithm=None, **kwargs):
+        if algorithm is not None:
+            self.algorithm = algorithm
+        self.loss_fn.register_post_loss_regularizer(self.__class__.__name__, self.regularizer)
+
+    def deactivate(self):
+        self.loss_fn.remove_post_loss_regularizer(self.__class__.__name__)
+
+
+class FIMTraceRegularizer(AdditiveRegularizer):
+    """beta * mean_x tr F(x), F the Fisher information of q(theta|x) w.r.t. x.  ``algorithm="ema"`` (the config's
+    choice) estimates the trace with ``ema_mc_samples`` scores per row, takes its weight gradient (double backward),
+    smooths it with an EMA and OVERWRITES ``p.grad`` with the bias-corrected average; the caller's ``loss.backward()``
+    then accumulates the NLL gradient on top."""
+
+    def __init__(self, model: Module, loss_fn: TrainLoss, beta: float = 1.0, algorithm: str = "jac_exact",
+                 mc_samples: int = 20, ema_mc_samples: int = 1, ema_decay: float = 0.99, clamp_val=None,
+                 grad_clamp_val=None, reduce: str = "mean"):
+        super().__init__(model, loss_fn, reduce=reduce)
+        self.beta = beta
+        self.algorithm = algorithm
+        self.mc_samples = mc_samples
+        self.ema = ExponentialMovingAverageEstimator(ema_decay)
+        self.ema_mc_samples = ema_mc_samples
+        self.clamp_val = clamp_val
+        self.grad_clamp_val = grad_clamp_val
+
+    def _set_algorithm(self, method, **kwargs) -> None:
+        self._algorithm = method
+        if method == "jac_exact":
+            self._regularizer = self._regularizer_exact
+        elif method == "ema":
+            self._regularizer = self._regularizer_ema
+
+    def _trace(self, input: Tensor, output: Distribution, mc_samples: int) -> Tensor:
+        reg = monte_carlo_fisher(self.model, input, output, mc_samples=mc_samples, create_graph=True,
+                                 retain_graph=True, typ="trace")
+        reg = reg[torch.isfinite(reg)]
+        if self.clamp_val is not None:
+            reg = reg.clamp(min=0, max=self.clamp_val)
+        return self.beta * self._reduce(reg)
+
+    def _regularizer_exact(self, input: Tensor, output: Distribution, target: Tensor) -> Tensor:
+        # for a flow the reference's fisher_information_matrix dispatches to the MC score estimator as well
+        return self._trace(input, output, self.mc_samples)
+
+    def _regularizer_ema(self, input: Tensor, output: Distribution, target: Tensor) -> Tensor:
+        reg = self._trace(input, output, self.ema_mc_samples)
+        grads = torch.autograd.grad(reg, list(self.model.parameters()), retain_graph=True)
+        self.ema(grads)
+        for params, grad in zip(self.model.parameters(), self.ema.value):
+            params.grad = torch.nan_to_num(grad.detach())
+        if self.grad_clamp_val is not None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clamp_val, norm_type=2.0)
+        return torch.zeros(1, device=input.device)
+
+
+class TradesAdversarialRegularizer(AdditiveRegularizer):
+    """beta * D(q(.|x) || q(.|x')) with x' = attack(x)   (clean distribution FIRST)."""
+
+    def __init__(self, model: Module, loss_fn: TrainLoss, attack: Attack, reg_loss_fn: Callable, beta: float = 1.0,
+                 reduce: str = "mean", **kwargs):
+        super().__init__(model, loss_fn, reduce)
+        self.attack = attack
+        self.reg_loss_fn = reg_loss_fn
+        self.beta = beta
+        self._regularizer = self._regularizer_attack
+
+    def _set_algorithm(self, method: str):
+        self._regularizer = self._regularizer_attack
+
+    def _regularizer_attack(self, input: Tensor, output: Tensor, target: Tensor):
+        if self.beta == 0.0:
+            return torch.zeros(1, device=input.device)
+        # NOTE: the reference's inner ``loss.backward()`` calls also accumulate the attack loss' weight gradient into
+        # ``p.grad`` (an unintended side effect of advertorch's loop).  The fused attack has no weight
+        # gradient, so that pollution is NOT reproduced; the regulariser value and its own gradient are identical.
+        x_pert = self.attack.perturb(input)
+        return self.beta * self.reg_loss_fn(self.model(input), self.model(x_pert))
+
+
+class L2PGDrKLTrades(TradesAdversarialRegularizer):
+    def __init__(self, model: Module, loss_fn: TrainLoss, attack_loss_fn: Optional[EvalLoss] = None,
+                 reg_loss_fn: Optional[EvalLoss] = None, eps: float = 0.5, beta: float = 1.0, reduce: str = "mean",
+                 **kwargs):
+        if attack_loss_fn is None:
+            attack_loss_fn = ReverseKLLoss(mc_samples=1)
+        if reg_loss_fn is None:
+            if hasattr(attack_loss_fn, "mc_samples"):
+                reg_loss_fn = attack_loss_fn.__class__(mc_samples=int(attack_loss_fn.mc_samples))
+            else:
+                reg_loss_fn = attack_loss_fn.__class__()
+        attack = L2PGDAttack(model, attack_loss_fn, eps=eps, **kwargs)
+        super().__init__(model, loss_fn, attack, reg_loss_fn, beta, reduce, **kwargs)

@@ -175,7 +175,7 @@ class MAFPosterior(Distribution):
             return False
         if any(t is not None and t.requires_grad for t in tensors) or self.ctx_in.requires_grad:
             return True
-        return self.model.training and any(p.requires_grad for p in self.model.parameters())
+        return any(p.requires_grad for p in self.model.parameters())
 
     def _flatten_value(self, value: Tensor):
         D = self.event_shape[0]

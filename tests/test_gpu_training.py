@@ -1,0 +1,112 @@
+"""GPU parity tests of the training-side rows against the reference fixtures: NLL and its weight
+gradient, Fisher trace and the double-backward weight gradient, two steps of FIMTraceRegularizer(algorithm="ema")
+through TrainLoss (EMA state + ``p.grad`` side effect), and L2PGDrKLTrades."""
+import pytest
+import torch
+
+from tests.util import RTOL, build_product, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TRAIN_CASES = ["tiny", "gaussian_linear", "lotka_volterra", "pyloric_small", "tiny_shuffle"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module", params=TRAIN_CASES)
+def case(request, dev):
+    g = load_golden(request.param)
+    model = build_product(g, dev, with_output_transform=False).train()  # run_train strips the output transform
+    return request.param, g, model
+
+
+def _grads(model):
+    return [p.grad.detach().cpu() if p.grad is not None else torch.zeros_like(p).cpu() for p in model.parameters()]
+
+
+def _check_grads(mine, ref, tol):
+    # gradients are compared on the scale of the largest gradient tensor of the model (masked / dead entries are 0)
+    scale = max(float(r.abs().max()) for r in ref)
+    for a, b in zip(mine, ref):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= tol * scale, (float((a - b).abs().max()), scale)
+
+
+def test_nll_and_weight_gradient(case, dev):
+    from rabi_b200.loss import NLLLoss
+
+    name, g, model = case
+    model.zero_grad()
+    loss_fn = NLLLoss(model).train()
+    loss = loss_fn(g["x"].to(dev), g["theta_train"].to(dev))
+    loss.backward()
+    assert abs(float(loss) - float(g["nll"])) < RTOL * abs(float(g["nll"]))
+    _check_grads(_grads(model), g["nll_grads"], RTOL)
+
+
+def test_fisher_trace_and_double_backward(case, dev):
+    from rabi_b200 import noise
+    from rabi_b200.fisher import monte_carlo_fisher
+
+    name, g, model = case
+    model.zero_grad()
+    x = g["x"].to(dev)
+    with noise.injected([g["z_fim"]]):
+        q = model(x)
+        tr = monte_carlo_fisher(model, x, q, mc_samples=5, create_graph=True, typ="trace")
+    assert rel_err(tr, g["fim_trace"]) < 3 * RTOL
+    grads = torch.autograd.grad(0.05 * tr.mean(), list(model.parameters()))
+    _check_grads([t.cpu() for t in grads], g["fim_grads"], 3 * RTOL)
+
+
+def test_fim_trace_regularizer_ema_two_steps(case, dev):
+    from rabi_b200 import noise
+    from rabi_b200.defenses import FIMTraceRegularizer
+    from rabi_b200.loss import NLLLoss
+
+    name, g, model = case
+    loss_fn = NLLLoss(model).train()
+    defense = FIMTraceRegularizer(model, loss_fn, beta=0.05, mc_samples=50, ema_mc_samples=5, algorithm="ema",
+                                  ema_decay=0.85, reduce="mean")
+    defense.activate()
+    x, th = g["x"].to(dev), g["theta_train"].to(dev)
+    try:
+        for step in g["fim_reg_steps"]:
+            model.zero_grad(set_to_none=True)
+            with noise.injected([step["z"]]):
+                loss = loss_fn(x, th)
+                loss.backward()
+            assert abs(float(loss) - float(step["loss"])) < RTOL * abs(float(step["loss"]))
+            _check_grads(_grads(model), step["grads"], 3 * RTOL)
+    finally:
+        defense.deactivate()
+
+
+def test_trades_rkl_regularizer(case, dev):
+    from rabi_b200 import noise
+    from rabi_b200.defenses import L2PGDrKLTrades
+    from rabi_b200.loss import NLLLoss
+
+    name, g, model = case
+    t = g["trades"]
+    loss_fn = NLLLoss(model).train()
+    trades = L2PGDrKLTrades(model, loss_fn, eps=t["eps"], eps_iter=t["eps_iter"], nb_iter=t["nb_iter"], beta=t["beta"])
+    # inject the reference's delta0 through the attack (the noise queue carries the base noise of the 3 PGD steps and
+    # of the final regulariser draw)
+    orig = trades.attack.perturb
+    trades.attack.perturb = lambda x, y=None, **kw: orig(x, y, delta_init=t["delta0"].to(dev), **kw)
+    trades.activate()
+    x, th = g["x"].to(dev), g["theta_train"].to(dev)
+    try:
+        model.zero_grad(set_to_none=True)
+        with noise.injected(list(t["z"])):
+            loss = loss_fn(x, th)
+            loss.backward()
+        assert abs(float(loss) - float(t["loss"])) < RTOL * abs(float(t["loss"]))
+        # function-level gradient (NLL + beta * KL); the reference's attack-backward pollution (Q3) is not reproduced
+        _check_grads(_grads(model), t["grads_clean"], 3 * RTOL)
+    finally:
+        trades.deactivate()
