@@ -187,7 +187,7 @@ def run_reference_arm(args, w, wname):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="rabi_b200", choices=["rabi_b200", "reference"])
     ap.add_argument("--workload", default="lotka_volterra_l2pgd_rkl", choices=list(WORKLOADS))
@@ -309,9 +309,16 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_fast_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
-        "bound": "fp32_fma", "kernel": "k_pairs<RKL_GRAD>", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s",
-        "frac": (achieved / fma_peak) if (achieved and fma_peak > 0) else None, "traffic": None,
+        "bound": "fp32_fma", "kernel": "k_fast<GRAD> (per-pair rKL forward + reverse, one launch per PGD iteration)",
+        "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s",
+        "frac": (achieved / fma_peak) if (achieved and fma_peak > 0) else None, "traffic": traffic,
+        "algorithmic_bytes_per_launch": int(4 * (w["rows"] * w["S_att"] * w["D"] + 3 * w["K"] * w["hidden"][0] * w["rows"])),
         "peak_source": "rabi_fma_peak_tflops (register-only FFMA microbenchmark run in this process; "
                        "MEASURED_PEAKS.json has no fp32 entry)",
         "flop_per_launch": pairs_launch * flops["pair_kernel_attack"],
