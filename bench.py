@@ -158,6 +158,21 @@ def run_reference_arm(args, w, wname):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if os.environ.get("OMP_NUM_THREADS") == "1" and not os.environ.get("RABI_REF_CHILD"):
+        # torchrun exports OMP_NUM_THREADS=1, which pins the CPU arm to one thread no matter what
+        # torch.set_num_threads says later: re-run it in a clean environment so it can use all host threads
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS") and not k.startswith(("TORCHELASTIC", "GROUP_", "ROLE_"))}
+        env["RABI_REF_CHILD"] = "1"
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE"):
+            env.pop(k, None)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", str(args.gpus),
+                              "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", wname],
+                             env=env, capture_output=True, text=True)
+        sys.stderr.write(out.stderr[-2000:])
+        print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else
+              json.dumps({"impl": "reference", "unavailable": "reference arm subprocess failed"}), flush=True)
+        return
     from rabi_b200.models import ZScoreLayer
 
     model = make_weights(w)
