@@ -91,14 +91,15 @@ struct ActBuf<true> {
 };
 
 // out[r][c] = sum_{i<e4} W[(min(c,cmax))*ld + i] * act_r[i]     (NR rows x RP pairs, e4 multiple of 4, e4 >= 4)
-template <int RP, int NR, bool TM>
-__device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld, int cmax, int e4,
+template <int RP, int NR, bool TM, int LDC>
+__device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld_rt, int cmax, int e4,
                                           const ActBuf<TM> (&ab)[RP], float (&out)[RP][NR]) {
     float2 acc[RP][NR];
 #pragma unroll
     for (int r = 0; r < RP; ++r)
 #pragma unroll
         for (int c = 0; c < NR; ++c) acc[r][c] = make_float2(0.f, 0.f);
+    const int ld = LDC ? LDC : ld_rt;  // compile-time leading dimension: row addresses become immediates
     const float* wr[NR];
 #pragma unroll
     for (int c = 0; c < NR; ++c) wr[c] = W + (size_t)min(c, cmax) * ld;
@@ -135,18 +136,20 @@ __device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld, i
 
 // out[r][c] = sum_{v in [va4, vb4)} W[v*ld + c] * g_r[v]     (NC columns x RP pairs; W offset to the first column;
 // va4 < vb4 multiples of 4; rows >= the layer's width are zero padding)
-template <int RP, int NC, bool TM>
-__device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld, int va4, int vb4,
+template <int RP, int NC, bool TM, int LDC>
+__device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld_rt, int va4, int vb4,
                                            const ActBuf<TM> (&ab)[RP], float (&out)[RP][NC]) {
     float2 acc[RP][NC / 2];
 #pragma unroll
     for (int r = 0; r < RP; ++r)
 #pragma unroll
         for (int c = 0; c < NC / 2; ++c) acc[r][c] = make_float2(0.f, 0.f);
+    const int ld = LDC ? LDC : ld_rt;
+    const float* wbase = W + (size_t)va4 * ld;
     float4 gn[RP];
 #pragma unroll
     for (int r = 0; r < RP; ++r) gn[r] = ab[r].ld4(va4);
-    for (int v = va4; v < vb4; v += 4) {
+    for (int v = va4; v < vb4; v += 4, wbase += 4 * ld) {
         float4 g4[RP];
 #pragma unroll
         for (int r = 0; r < RP; ++r) {
@@ -159,7 +162,7 @@ __device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld, 
         }
 #pragma unroll
         for (int dv = 0; dv < 4; ++dv) {
-            const float* wrow = W + (size_t)(v + dv) * ld;
+            const float* wrow = wbase + dv * ld;
 #pragma unroll
             for (int cc = 0; cc < NC / 4; ++cc) {
                 const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * cc);
@@ -190,7 +193,7 @@ struct FastRel {
     int perm, permy, deg0, pre1, grp0, grp1, first1; // ints, relative to t.perm
 };
 
-template <int MODE, int RP, int DP, bool TM>
+template <int MODE, int RP, int DP, bool TM, int LDC>
 __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g, const FastArgs a, const FastRel rel) {
     extern __shared__ __align__(16) float sm[];
     const int T = blockDim.x, tid = threadIdx.x;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
     const float* W1 = Ws + rel.W1;
     const float* WoT = Ws + rel.WoT;   // [H1][2*DP]: m-weights of positions 0..DP-1, then s-weights
     const float* bo = Ws + rel.bo;     // [2*DP]
-    const int ld1 = rel.ld1;
+    const int ld1 = LDC ? LDC : rel.ld1;
     const int* perm = Ms + rel.perm;
     const int* permy = Ms + rel.permy;
     const int* grp0 = Ms + rel.grp0;
@@ -338,7 +341,8 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
             if (kind < 2) {
                 // ===================== forward pass of transform k =====================
                 const float* Aptr[RP];
-                float zos[RP][DP], y[RP][DP], om[RP][DP], os[RP][DP];
+                float zos[RP][DP], y[RP][DP];
+                float2 oms[RP][DP];  // (mean, log-scale) accumulators of every position
                 uint32_t w0[RP], w1[RP];
                 const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
 #pragma unroll
@@ -349,8 +353,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                     for (int jj = 0; jj < DP; ++jj) {
                         zos[r][jj] = (seq && jj < D) ? vecp[r][oV + k * D + perm[jj]] : 0.f;
                         y[r][jj] = (!seq && jj < D) ? vecp[r][src + permy[jj]] : 0.f;
-                        om[r][jj] = jj < D ? bo[jj] : 0.f;
-                        os[r][jj] = jj < D ? bo[DP + jj] : 0.f;
+                        oms[r][jj] = jj < D ? make_float2(bo[2 * jj], bo[2 * jj + 1]) : make_float2(0.f, 0.f);
                     }
                 }
                 // ---- the context projection of this transform goes into the activation buffer first (16 loads in
@@ -431,29 +434,26 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                         auto block = [&](auto NRtag, int v0, int nv) {
                             constexpr int NR = decltype(NRtag)::value;
                             float h[RP][NR];
-                            dot_block<RP, NR, TM>(W1 + (size_t)v0 * ld1, ld1, nv - 1, e4, ab, h);
+                            dot_block<RP, NR, TM, LDC>(W1 + (size_t)v0 * ld1, ld1, nv - 1, e4, ab, h);
 #pragma unroll
                             for (int c = 0; c < NR; ++c) {
                                 if (c < nv) {
                                     const int v = v0 + c;
                                     const float bias = b1[v];
                                     const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
-                                    float wm[DP], ws[DP];
+                                    float4 wq[DP / 2];  // (m_0, s_0, m_1, s_1), ...
 #pragma unroll
-                                    for (int q4 = 0; q4 < DP / 4; ++q4) {
-                                        const float4 m4 = wo[q4], s4 = wo[DP / 4 + q4];
-                                        wm[4 * q4] = m4.x; wm[4 * q4 + 1] = m4.y; wm[4 * q4 + 2] = m4.z; wm[4 * q4 + 3] = m4.w;
-                                        ws[4 * q4] = s4.x; ws[4 * q4 + 1] = s4.y; ws[4 * q4 + 2] = s4.z; ws[4 * q4 + 3] = s4.w;
-                                    }
+                                    for (int q2 = 0; q2 < DP / 2; ++q2) wq[q2] = wo[q2];
 #pragma unroll
                                     for (int r = 0; r < RP; ++r) {
                                         const float val = h[r][c] + bias;
                                         const bool on = val > 0.f;
                                         const float hv = on ? val : 0.f;
+                                        const float2 hh = make_float2(hv, hv);
 #pragma unroll
-                                        for (int jj = 0; jj < DP; ++jj) {
-                                            om[r][jj] = fmaf(wm[jj], hv, om[r][jj]);
-                                            os[r][jj] = fmaf(ws[jj], hv, os[r][jj]);
+                                        for (int q2 = 0; q2 < DP / 2; ++q2) {
+                                            oms[r][2 * q2] = ffma2(make_float2(wq[q2].x, wq[q2].y), hh, oms[r][2 * q2]);
+                                            oms[r][2 * q2 + 1] = ffma2(make_float2(wq[q2].z, wq[q2].w), hh, oms[r][2 * q2 + 1]);
                                         }
                                         if (MODE == FAST_GRAD) {
                                             if (on) w1[r] |= 1u << (v & 31);
@@ -469,7 +469,9 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                         int v = va;
                         for (; v + 16 <= vb; v += 16) block(std::integral_constant<int, 16>{}, v, 16);
                         if (v + 8 <= vb) { block(std::integral_constant<int, 8>{}, v, 8); v += 8; }
-                        for (; v < vb; v += 4) block(std::integral_constant<int, 4>{}, v, min(4, vb - v));
+                        if (v + 4 <= vb) { block(std::integral_constant<int, 4>{}, v, 4); v += 4; }
+                        if (v + 2 <= vb) { block(std::integral_constant<int, 2>{}, v, 2); v += 2; }
+                        if (v < vb) block(std::integral_constant<int, 1>{}, v, 1);
                     }
                     if (seq) {  // position j is final: y_j = (z_j - m_j) exp(-clamp(s_j))
 #pragma unroll
@@ -477,8 +479,8 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                             float m = 0.f, s = 0.f, zj = 0.f;
 #pragma unroll
                             for (int jj = 0; jj < DP; ++jj) {
-                                m = jj == j ? om[r][jj] : m;
-                                s = jj == j ? os[r][jj] : s;
+                                m = jj == j ? oms[r][jj].x : m;
+                                s = jj == j ? oms[r][jj].y : s;
                                 zj = jj == j ? zos[r][jj] : zj;
                             }
                             const float sh = fminf(fmaxf(s, g.lo), g.hi);
@@ -497,10 +499,10 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
 #pragma unroll
                         for (int jj = 0; jj < DP; ++jj) {
                             if (jj < D) {
-                                const float sh = fminf(fmaxf(os[r][jj], g.lo), g.hi);
+                                const float sh = fminf(fmaxf(oms[r][jj].y, g.lo), g.hi);
                                 vecp[r][oSHQ + k * D + jj] = sh;
                                 logq[r] += sh;
-                                vecp[r][oU + k * D + perm[jj]] = fmaf(expf(sh), y[r][jj], om[r][jj]);
+                                vecp[r][oU + k * D + perm[jj]] = fmaf(expf(sh), y[r][jj], oms[r][jj].x);
                             }
                         }
                     }
@@ -574,20 +576,20 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                             for (int c = 0; c < 4; ++c) {
                                 const int v = min(v0 + c, vb - 1);
                                 const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
+                                float2 g2[RP];
 #pragma unroll
-                                for (int r = 0; r < RP; ++r) gs[r][c] = 0.f;
+                                for (int r = 0; r < RP; ++r) g2[r] = make_float2(0.f, 0.f);
 #pragma unroll
-                                for (int q4 = 0; q4 < DP / 4; ++q4) {
-                                    const float4 m4 = wo[q4], s4 = wo[DP / 4 + q4];
+                                for (int q2 = 0; q2 < DP / 2; ++q2) {
+                                    const float4 wq = wo[q2];  // (m_j, s_j, m_j+1, s_j+1)
 #pragma unroll
                                     for (int r = 0; r < RP; ++r) {
-                                        float t0 = fmaf(s4.x, sb[r][4 * q4], m4.x * mb[r][4 * q4]);
-                                        float t1 = fmaf(s4.y, sb[r][4 * q4 + 1], m4.y * mb[r][4 * q4 + 1]);
-                                        float t2 = fmaf(s4.z, sb[r][4 * q4 + 2], m4.z * mb[r][4 * q4 + 2]);
-                                        float t3 = fmaf(s4.w, sb[r][4 * q4 + 3], m4.w * mb[r][4 * q4 + 3]);
-                                        gs[r][c] += (t0 + t1) + (t2 + t3);
+                                        g2[r] = ffma2(make_float2(wq.x, wq.y), make_float2(mb[r][2 * q2], sb[r][2 * q2]), g2[r]);
+                                        g2[r] = ffma2(make_float2(wq.z, wq.w), make_float2(mb[r][2 * q2 + 1], sb[r][2 * q2 + 1]), g2[r]);
                                     }
                                 }
+#pragma unroll
+                                for (int r = 0; r < RP; ++r) gs[r][c] = g2[r].x + g2[r].y;
                             }
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                         auto cblock = [&](auto NCtag, int u0) {
                             constexpr int NC = decltype(NCtag)::value;
                             float g0[RP][NC];
-                            tdot_block<RP, NC, TM>(W1 + u0, ld1, va4, vb4, ab, g0);
+                            tdot_block<RP, NC, TM, LDC>(W1 + u0, ld1, va4, vb4, ab, g0);
                             uint32_t wb[RP];
 #pragma unroll
                             for (int r = 0; r < RP; ++r) wb[r] = bitp[r][bs * WL + (u0 >> 5)] >> (u0 & 31);

@@ -389,10 +389,10 @@ __global__ void k_pack_out(MafImg g, int k, const float* __restrict__ W, const f
     int src = half * D + g.m[t.perm + j];
     const float wv = (v < g.m[t.preo + j]) ? W[(size_t)src * HL + v] : 0.f;
     f[t.Wo + (size_t)r * t.ldo + v] = wv;
-    f[t.WoT + (size_t)v * 2 * t.ldt + half * t.ldt + j] = wv;
+    f[t.WoT + (size_t)v * 2 * t.ldt + 2 * j + half] = wv;   // (mean, log-scale) pairs per position
     if (v == 0) {
         f[t.bo + r] = b[src];
-        f[t.boF + half * t.ldt + j] = b[src];
+        f[t.boF + 2 * j + half] = b[src];
     }
 }
 
@@ -865,10 +865,10 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-template <int MODE, int RP, int DP, bool TM>
+template <int MODE, int RP, int DP, bool TM, int LDC>
 static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel, int grid, int T, size_t smem,
                             cudaStream_t st) {
-    CU_OK(h, cudaFuncSetAttribute(k_fast<MODE, RP, DP, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_OK(h, cudaFuncSetAttribute(k_fast<MODE, RP, DP, TM, LDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool prof = h->profiling && MODE == FAST_GRAD;
     if (prof) {
         if (h->prof_used == h->prof_events.size()) {
@@ -879,7 +879,7 @@ static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel,
         }
         CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].first, st));
     }
-    k_fast<MODE, RP, DP, TM><<<grid, T, smem, st>>>(h->img, fa, rel);
+    k_fast<MODE, RP, DP, TM, LDC><<<grid, T, smem, st>>>(h->img, fa, rel);
     LAUNCH_CHECK(h);
     if (prof) {
         CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].second, st));
@@ -973,14 +973,17 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
         int need = ((T / 32 + 3) / 4) * RP * AS;
         while (fa.tm_cols < need) fa.tm_cols *= 2;
     }
-#define RABI_FAST_CASE(RPv, DPv, TMv) \
-    if (RP == RPv && DP == DPv && TM == TMv) return launch_fast_inst<MODE, RPv, DPv, TMv>(h, fa, rel, grid, T, smem, st);
-    RABI_FAST_CASE(1, 4, true)
-    RABI_FAST_CASE(1, 8, true)
-    RABI_FAST_CASE(1, 12, true)
-    RABI_FAST_CASE(1, 4, false)
-    RABI_FAST_CASE(2, 4, false)
-    RABI_FAST_CASE(2, 4, true)
+#define RABI_FAST_CASE(RPv, DPv, TMv, LDv) \
+    if (RP == RPv && DP == DPv && TM == TMv && (LDv == 0 || rel.ld1 == LDv))  \
+        return launch_fast_inst<MODE, RPv, DPv, TMv, LDv>(h, fa, rel, grid, T, smem, st);
+    RABI_FAST_CASE(1, 4, true, 100)   // lotka_volterra: hidden [100, 100]
+    RABI_FAST_CASE(1, 12, true, 100)  // gaussian_linear
+    RABI_FAST_CASE(1, 4, true, 0)
+    RABI_FAST_CASE(1, 8, true, 0)
+    RABI_FAST_CASE(1, 12, true, 0)
+    RABI_FAST_CASE(1, 4, false, 0)
+    RABI_FAST_CASE(2, 4, false, 0)
+    RABI_FAST_CASE(2, 4, true, 0)
 #undef RABI_FAST_CASE
     return 2;
 }
