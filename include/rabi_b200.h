@@ -111,6 +111,18 @@ int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const 
                      float eps_iter, float clip_min, float clip_max, float inv_B, float norm_floor,
                      float* x_adv_dev, rabi_stream_t s);
 
+/* Forward-KL attack loss (ForwardKLLoss, rbi/rbi/loss/eval_loss.py:108-126 -- the default attack_loss_fn of
+ * config/eval_rob/attack/l2pgd.yaml): loss = inv_B * sum_b KL(target_b || q(.|x_b + delta_b)); samples are drawn from the
+ * fixed target (projection A_t_dev; NULL in the run = the clean x), the gradient flows through the density pass only.
+ * Same argument meaning as the rabi_rkl_* counterparts. */
+int rabi_fkl_input_grad(rabi_maf_t* h, const float* x_dev, const float* zs_mean_dev, const float* zs_std_dev,
+                        const float* A_t_dev, const float* z_dev, int S, int B, float inv_B, float* gx_dev,
+                        float* kl_dev, rabi_stream_t s);
+int rabi_fkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* zs_mean_dev,
+                     const float* zs_std_dev, const float* A_t_dev, const float* z_all_dev, int nb_iter, int S, int B,
+                     float eps, float eps_iter, float clip_min, float clip_max, float inv_B, float norm_floor,
+                     float* x_adv_dev, rabi_stream_t s);
+
 /* Measurement support (bench.py): CUDA-event timing of the dominant kernel (the per-pair rKL forward+backward
  * kernel) on the stream it is launched on.  rabi_profile_read synchronises the device, returns the summed duration
  * and the number of timed launches since the last read, and resets the counters. */

@@ -83,7 +83,7 @@ class L2PGDAttack(Attack):
         m = self.predict
         if not isinstance(m, InverseAffineAutoregressiveModel) or not isinstance(y, MAFPosterior) or y.model is not m:
             return False
-        if type(self.loss_fn) is not ReverseKLLoss or self.loss_fn.reduction != "mean":
+        if type(self.loss_fn) not in (ReverseKLLoss, ForwardKLLoss) or self.loss_fn.reduction != "mean":
             return False
         from .models import _split_embedding
         return _split_embedding(m.embedding_net)[1] is None
@@ -102,7 +102,7 @@ class L2PGDAttack(Attack):
         if not self._fused_ok(y):
             raise NotImplementedError(
                 "fused L2-PGD supports predict=InverseAffineAutoregressiveModel with an identity/z-score embedding "
-                f"and loss_fn=ReverseKLLoss(reduction='mean'); got loss_fn={type(self.loss_fn).__name__}")
+                f"and loss_fn=ReverseKLLoss / ForwardKLLoss (reduction='mean'); got loss_fn={type(self.loss_fn).__name__}")
         model: InverseAffineAutoregressiveModel = self.predict
         eng = model.engine()
         x = x.float().contiguous()
@@ -131,4 +131,4 @@ class L2PGDAttack(Attack):
 
     def _run(self, eng, x, delta, zs, y, z_all, inv_B):
         return eng.pgd_run(x, delta, zs[0], zs[1], y.A, z_all, self.eps, self.eps_iter, self.clip_min, self.clip_max,
-                           inv_B)
+                           inv_B, forward_kl=type(self.loss_fn) is ForwardKLLoss)

@@ -185,7 +185,10 @@ __device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld_r
         }
 }
 
-enum FastMode { FAST_FWD = 0, FAST_GRAD = 1 };
+// FAST_GRAD: reverse KL, gradient w.r.t. the projection of the sampled-from posterior (A_p).
+// FAST_FKL : forward-KL attack loss KL(target || q(.|x+delta)): samples come from the fixed target (A_p), the gradient
+//            flows only through the density pass (A_q): d/dA_q of -w*log q, emitted by the reverse density phases.
+enum FastMode { FAST_FWD = 0, FAST_GRAD = 1, FAST_FKL = 2 };
 
 // Relative offsets (floats / ints) of the sections inside one transform's staged block.
 struct FastRel {
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
     float* Ws = sm;
     int* Ms = reinterpret_cast<int*>(Ws + a.wfloats);
     float* gAt = reinterpret_cast<float*>(Ms + a.wints);                    // [H0][TBp]  (GRAD only)
-    float* act = gAt + (MODE == FAST_GRAD ? (((size_t)H0 * a.TBp + 3) & ~(size_t)3) : 0);  // [RP*T][AS], 16-B aligned
+    float* act = gAt + (MODE != FAST_FWD ? (((size_t)H0 * a.TBp + 3) & ~(size_t)3) : 0);  // [RP*T][AS], 16-B aligned
     float* vec = act + (TM ? 0 : (size_t)RP * T * a.AS);                    // [RP*T][VS]  (TM: no smem activations)
     uint32_t* bits = reinterpret_cast<uint32_t*>(vec + (size_t)RP * T * a.VS);  // [RP*T][BWS] (GRAD only)
 
@@ -287,14 +290,14 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
         const float* Ap[RP];
         const float* Aq[RP];
         int rows_here = 0, b0 = 0;
-        if (MODE == FAST_GRAD) {
+        if (MODE != FAST_FWD) {
             b0 = tile * a.TB;
             rows_here = min(a.TB, a.B - b0);
         }
 #pragma unroll
         for (int r = 0; r < RP; ++r) {
             const int q = tid + r * T;
-            if (MODE == FAST_GRAD) {
+            if (MODE != FAST_FWD) {
                 live[r] = q < rows_here * a.S;
                 const int s = live[r] ? q / rows_here : 0;
                 rrow[r] = live[r] ? q % rows_here : 0;
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
             Ap[r] = a.A_p + b;
             Aq[r] = a.A_q + b;
         }
-        if (MODE == FAST_GRAD) {
+        if (MODE != FAST_FWD) {
             __syncthreads();
             for (int i = tid; i < H0 * a.TBp; i += T) gAt[i] = 0.f;
         }
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
         // One loop over the 2K (forward) / 4K (forward + reverse) phases; every building block below is
         // instantiated exactly once.  kind: 0 = sampling pass under A_p (k ascending), 1 = density pass under A_q
         // (k descending), 2 = reverse of the density pass (k ascending), 3 = reverse of the sampling pass.
-        const int nphase = (MODE == FAST_GRAD ? 4 : 2) * K;
+        const int nphase = (MODE == FAST_GRAD ? 4 : MODE == FAST_FKL ? 3 : 2) * K;
         for (int ph = 0; ph < nphase; ++ph) {
             const int kind = ph / K;
             const int idx = ph - kind * K;
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                                     if (u >= ua && u < ub) {
                                         const bool on = pre[r][c] > 0.f;
                                         nv[c] = on ? pre[r][c] : 0.f;
-                                        if (MODE == FAST_GRAD) {
+                                        if (MODE != FAST_FWD) {
                                             if (on) w0[r] |= 1u << (u & 31);
                                             if ((u & 31) == 31 || u == H0 - 1) {
                                                 bitp[r][bs * WL + (u >> 5)] = w0[r];
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                                             oms[r][2 * q2] = ffma2(make_float2(wq[q2].x, wq[q2].y), hh, oms[r][2 * q2]);
                                             oms[r][2 * q2 + 1] = ffma2(make_float2(wq[q2].z, wq[q2].w), hh, oms[r][2 * q2 + 1]);
                                         }
-                                        if (MODE == FAST_GRAD) {
+                                        if (MODE != FAST_FWD) {
                                             if (on) w1[r] |= 1u << (v & 31);
                                             if ((v & 31) == 31 || v == H1 - 1) {
                                                 bitp[r][(bs + 1) * WL + (v >> 5)] = w1[r];
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                             for (int d = 0; d < D; ++d) {
                                 const float u = vecp[r][oU + d];
                                 ssq = fmaf(u, u, ssq);
-                                if (MODE == FAST_GRAD) vecp[r][oG + d] = a.w * u;  // d(-w log q)/d u_0
+                                if (MODE != FAST_FWD) vecp[r][oG + d] = a.w * u;  // d(-w log q)/d u_0
                             }
                             logq[r] += -0.5f * ssq - (float)D * HALF_LOG_2PI;
                             if (a.diff && live[r]) a.diff[pidx[r]] = logp[r] - logq[r];
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                                         const float gv = ((wb[r] >> c) & 1u) ? g0[r][c] : 0.f;
 #pragma unroll
                                         for (int jj = 0; jj < DP; ++jj) yb[r][jj] = fmaf(wrow[jj], gv, yb[r][jj]);
-                                        if (seq && live[r]) atomicAdd(gAt + (size_t)u * a.TBp + rrow[r], gv);
+                                        if ((seq || MODE == FAST_FKL) && live[r]) atomicAdd(gAt + (size_t)u * a.TBp + rrow[r], gv);
                                     }
                                 }
                             }
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                             if (seq) vecp[r][oG + perm[jj]] = zb[r][jj];
                             else vecp[r][oG + permy[jj]] = yb[r][jj];
                         }
-                if (seq) {  // flush the gA tile of this transform (rows of this tile are owned by this CTA alone)
+                if (seq || MODE == FAST_FKL) {  // flush the gA tile of this transform (rows of this tile are owned by this CTA alone)
                     __syncthreads();
                     for (int i = tid; i < H0 * rows_here; i += T) {
                         const int u = i / rows_here, rr = i % rows_here;

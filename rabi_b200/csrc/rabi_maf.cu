@@ -869,7 +869,7 @@ template <int MODE, int RP, int DP, bool TM, int LDC>
 static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel, int grid, int T, size_t smem,
                             cudaStream_t st) {
     CU_OK(h, cudaFuncSetAttribute(k_fast<MODE, RP, DP, TM, LDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const bool prof = h->profiling && MODE == FAST_GRAD;
+    const bool prof = h->profiling && MODE != FAST_FWD;
     if (prof) {
         if (h->prof_used == h->prof_events.size()) {
             cudaEvent_t e0, e1;
@@ -920,7 +920,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     fa.AS = AS;
     fa.VS = ((4 * K + 2) * D) | 1;
     const int WL = (g.Hmax + 31) / 32;
-    fa.BWS = MODE == FAST_GRAD ? ((2 * K * 2 * WL) | 1) : 0;
+    fa.BWS = MODE != FAST_FWD ? ((2 * K * 2 * WL) | 1) : 0;
     const size_t per_slot = (size_t)((TM ? 0 : fa.AS) + fa.VS + fa.BWS) * sizeof(float);
     const size_t fixed = (size_t)(fa.wfloats + fa.wints) * sizeof(float);
     const size_t budget = (size_t)h->max_smem_optin - 1024;
@@ -934,7 +934,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     size_t smem = 0;
     const long long npairs = (long long)fa.S * fa.B;
     auto gat_bytes = [&](int tbp) { return (((size_t)H0 * tbp + 3) & ~(size_t)3) * sizeof(float); };
-    if (MODE == FAST_GRAD) {
+    if (MODE != FAST_FWD) {
         // largest T whose slots (+ the gA tile for the rows they hold) fit
         for (;; T -= 32) {
             if (T < 32) return 2;
@@ -1021,7 +1021,7 @@ extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_
 // workspace layout for the PGD step: [A_p: K*H0*B][gA: K*H0*B][gx: B*C][diff: S*B]
 static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float* zm, const float* zs, const float* A_q,
                          const float* z, int S, int B, float eps, float eps_iter, float cmin, float cmax, float inv_B,
-                         float floor_, float* kl, cudaStream_t st) {
+                         float floor_, float* kl, cudaStream_t st, int forward_kl = 0) {
     const size_t nA = (size_t)h->K * h->H[0] * B;
     float* A_p = (float*)h->ws;
     float* gA = A_p + nA;
@@ -1037,7 +1037,15 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
     fa.S = S;
     fa.B = B;
     fa.w = inv_B / (float)S;
-    int rc = launch_fast<FAST_GRAD>(h, fa, st);
+    int rc;
+    if (forward_kl) {  // KL(target || q(.|x+delta)): sample from the target's projection, differentiate the density pass
+        fa.A_p = A_q;
+        fa.A_q = A_p;
+        rc = launch_fast<FAST_FKL>(h, fa, st);
+        if (rc == 2) return fail(h, "the forward-KL attack loss is only available on the fast path (two hidden layers, D <= 12)");
+    } else {
+        rc = launch_fast<FAST_GRAD>(h, fa, st);
+    }
     if (rc == 1) return 1;
     if (rc == 2) {  // generic per-pair kernel (accumulates gA with atomics)
         CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
@@ -1098,6 +1106,49 @@ extern "C" int rabi_rkl_input_grad(rabi_maf_t* h, const float* x_dev, const floa
         return 1;
     const float* gx = (const float*)h->ws + 2 * (size_t)h->K * h->H[0] * B;
     CU_OK(h, cudaMemcpyAsync(gx_dev, gx, (size_t)B * h->C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int rabi_fkl_input_grad(rabi_maf_t* h, const float* x_dev, const float* zs_mean_dev, const float* zs_std_dev,
+                                   const float* A_t_dev, const float* z_dev, int S, int B, float inv_B, float* gx_dev,
+                                   float* kl_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (S <= 0 || B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    if (ensure_ws(h, pgd_ws_bytes(h, S, B))) return 1;
+    if (pgd_step_impl(h, x_dev, nullptr, zs_mean_dev, zs_std_dev, A_t_dev, z_dev, S, B, -1.f, 0.f, 0.f, 0.f, inv_B, 0.f,
+                      kl_dev, st, 1))
+        return 1;
+    const float* gx = (const float*)h->ws + 2 * (size_t)h->K * h->H[0] * B;
+    CU_OK(h, cudaMemcpyAsync(gx_dev, gx, (size_t)B * h->C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int rabi_fkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* zs_mean_dev,
+                                const float* zs_std_dev, const float* A_t_dev, const float* z_all_dev, int nb_iter, int S,
+                                int B, float eps, float eps_iter, float clip_min, float clip_max, float inv_B,
+                                float norm_floor, float* x_adv_dev, rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (S <= 0 || B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    const size_t nA = (size_t)h->K * h->H[0] * B;
+    if (ensure_ws(h, pgd_ws_bytes(h, S, B) + nA * sizeof(float))) return 1;
+    const float* A_t = A_t_dev;
+    if (!A_t) {
+        float* own = (float*)((char*)h->ws + pgd_ws_bytes(h, S, B));
+        if (launch_ctx_project(h, x_dev, nullptr, zs_mean_dev, zs_std_dev, B, own, st)) return 1;
+        A_t = own;
+    }
+    const size_t zstride = (size_t)S * B * h->D;
+    for (int it = 0; it < nb_iter; ++it)
+        if (pgd_step_impl(h, x_dev, delta_dev, zs_mean_dev, zs_std_dev, A_t, z_all_dev + (size_t)it * zstride, S, B, eps,
+                          eps_iter, clip_min, clip_max, inv_B, norm_floor, nullptr, st, 1))
+            return 1;
+    if (x_adv_dev) {
+        size_t n = (size_t)B * h->C;
+        k_clamp_add<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_dev, delta_dev, n, clip_min, clip_max, x_adv_dev);
+        LAUNCH_CHECK(h);
+    }
     return 0;
 }
 

@@ -162,14 +162,15 @@ class MafEngine:
                 self._check(self.L.rabi_rkl_fwd(self.h, _ptr(A_p), _ptr(A_q), _ptr(z), S, B, _ptr(out), self._stream()))
         return out
 
-    def rkl_input_grad(self, x, zs_mean, zs_std, A_q, z, inv_B, want_kl=True):
-        """-> (d[inv_B * sum_b KL(q(.|x_b) || target_b)]/dx  [B, C], kl [B] | None)."""
+    def rkl_input_grad(self, x, zs_mean, zs_std, A_q, z, inv_B, want_kl=True, forward_kl=False):
+        """-> (d[inv_B * sum_b KL(q(.|x_b) || target_b)]/dx  [B, C], kl [B] | None); ``forward_kl``: KL(target || q(.|x))."""
         z = _f32c(z)
         S, B, _ = z.shape
         gx = torch.empty((B, self.C), device=self.device, dtype=torch.float32)
         kl = torch.empty((B,), device=self.device, dtype=torch.float32) if want_kl else None
         with torch.cuda.device(self.device):
-            self._check(self.L.rabi_rkl_input_grad(self.h, _ptr(_f32c(x)), _ptr(zs_mean), _ptr(zs_std), _ptr(A_q), _ptr(z),
+            fn = self.L.rabi_fkl_input_grad if forward_kl else self.L.rabi_rkl_input_grad
+            self._check(fn(self.h, _ptr(_f32c(x)), _ptr(zs_mean), _ptr(zs_std), _ptr(A_q), _ptr(z),
                                                    S, B, float(inv_B), _ptr(gx), _ptr(kl), self._stream()))
         return gx, kl
 
@@ -186,14 +187,15 @@ class MafEngine:
         return kl
 
     def pgd_run(self, x, delta, zs_mean, zs_std, A_q, z_all, eps, eps_iter, clip_min, clip_max, inv_B,
-                norm_floor=1e-6):
+                norm_floor=1e-6, forward_kl=False):
         """z_all [nb_iter, S, B, D]; updates delta in place and returns x_adv = clamp(x + delta).
         A_q None: untargeted (projection of the clean x is computed inside)."""
         z_all = _f32c(z_all)
         nb_iter, S, B, _ = z_all.shape
         x_adv = torch.empty_like(x)
         with torch.cuda.device(self.device):
-            self._check(self.L.rabi_rkl_pgd_run(self.h, _ptr(x), _ptr(delta), _ptr(zs_mean), _ptr(zs_std), _ptr(A_q),
+            fn = self.L.rabi_fkl_pgd_run if forward_kl else self.L.rabi_rkl_pgd_run
+            self._check(fn(self.h, _ptr(x), _ptr(delta), _ptr(zs_mean), _ptr(zs_std), _ptr(A_q),
                                                 _ptr(z_all), nb_iter, S, B, float(eps), float(eps_iter), float(clip_min),
                                                 float(clip_max), float(inv_B), float(norm_floor), _ptr(x_adv),
                                                 self._stream()))

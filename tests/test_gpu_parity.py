@@ -196,3 +196,41 @@ def test_size_independent_properties_at_config2_scale(dev):
         kl_rand = ReverseKLLoss(mc_samples=256, reduction=None)(
             model(x + eps * torch.nn.functional.normalize(torch.randn_like(x), dim=-1)), model(x))
     assert float(kl_adv.mean()) > float(kl_rand.mean())  # the attack beats a random direction of the same norm
+
+
+@pytest.mark.parametrize("shape", ["gaussian_linear", "lotka_volterra"])
+def test_forward_kl_attack_vs_oracle(shape, dev):
+    """ForwardKLLoss as the attack loss (the default of config/eval_rob/attack/l2pgd.yaml):
+    gradient of mean_B KL(q(.|x) || q(.|x~)) w.r.t. x~ and the L2-PGD trajectory, against the live oracle."""
+    from oracle import rbi_oracle as O
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ForwardKLLoss
+
+    ref, model, x = _fresh(SHAPES[shape], dev, seed=2)
+    B, D = x.shape[0], SHAPES[shape]["D"]
+    S, nb = 5, 8
+    eps = float(0.5 * x.std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+    g = torch.Generator().manual_seed(9)
+    zs = [torch.randn(S, B, D, generator=g) for _ in range(nb)]
+    xt = x + 0.2 * eps * torch.randn(B, x.shape[1], generator=g)
+    xt_ = xt.clone().requires_grad_()
+    with O.injected_base_noise([zs[0]]):
+        with torch.no_grad():
+            y = ref(x)
+        O.ForwardKLLoss(mc_samples=S)(ref(xt_), y).backward()
+    with torch.no_grad():
+        q = model(x.to(dev))
+        _, zsc, _ = model.condition_inputs(xt.to(dev))
+        gx, _ = model.engine().rkl_input_grad(xt.to(dev), zsc[0], zsc[1], q.A, zs[0].to(dev), 1.0 / B, forward_kl=True)
+    assert rel_err(gx, xt_.grad) < RTOL
+    d0 = O.adv.clamp_by_pnorm(torch.randn(B, x.shape[1], generator=g), 2, eps)
+    d0 = O.adv.clamp(x + d0, cmin, cmax) - x
+    with O.injected_base_noise(zs):
+        xa_ref = O.l2pgd_perturb(ref, x, O.ForwardKLLoss(mc_samples=S), eps, nb, eps / 10, cmin, cmax, delta0=d0)
+    atk = L2PGDAttack(model, loss_fn=ForwardKLLoss(mc_samples=S), eps=eps, nb_iter=nb, eps_iter=eps / 10,
+                      clip_min=cmin, clip_max=cmax)
+    with noise.injected(zs):
+        xa = atk.perturb(x.to(dev), delta_init=d0.to(dev))
+    assert_trajectories_match(xa.cpu() - x, xa_ref - x, 2 * RTOL)
