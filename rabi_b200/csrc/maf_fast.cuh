@@ -26,7 +26,8 @@ struct FastArgs {
     const float* A_p;
     const float* A_q;
     const float* z;     // [S,B,D]
-    float* diff;        // [S,B] log p - log q (optional in GRAD mode)
+    float* diff;        // [S,B] log p - log q (optional in GRAD mode); RSAMPLE: log q(own sample); LOGPROB: log q(theta)
+    float* theta_out;   // RSAMPLE: [S,B,D]
     float* gA;          // GRAD: [K,H0,B] d loss / d A_p (plain stores: every row belongs to exactly one tile)
     int S, B;
     float w;
@@ -188,7 +189,9 @@ __device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld_r
 // FAST_GRAD: reverse KL, gradient w.r.t. the projection of the sampled-from posterior (A_p).
 // FAST_FKL : forward-KL attack loss KL(target || q(.|x+delta)): samples come from the fixed target (A_p), the gradient
 //            flows only through the density pass (A_q): d/dA_q of -w*log q, emitted by the reverse density phases.
-enum FastMode { FAST_FWD = 0, FAST_GRAD = 1, FAST_FKL = 2 };
+// FAST_RSAMPLE: sampling passes only (theta and its log-density); FAST_LOGPROB: density passes only on given theta.
+enum FastMode { FAST_FWD = 0, FAST_GRAD = 1, FAST_FKL = 2, FAST_RSAMPLE = 3, FAST_LOGPROB = 4 };
+__host__ __device__ constexpr bool fast_is_grad(int mode) { return mode == FAST_GRAD || mode == FAST_FKL; }
 
 // Relative offsets (floats / ints) of the sections inside one transform's staged block.
 struct FastRel {
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
     float* Ws = sm;
     int* Ms = reinterpret_cast<int*>(Ws + a.wfloats);
     float* gAt = reinterpret_cast<float*>(Ms + a.wints);                    // [H0][TBp]  (GRAD only)
-    float* act = gAt + (MODE != FAST_FWD ? (((size_t)H0 * a.TBp + 3) & ~(size_t)3) : 0);  // [RP*T][AS], 16-B aligned
+    float* act = gAt + (fast_is_grad(MODE) ? (((size_t)H0 * a.TBp + 3) & ~(size_t)3) : 0);  // [RP*T][AS], 16-B aligned
     float* vec = act + (TM ? 0 : (size_t)RP * T * a.AS);                    // [RP*T][VS]  (TM: no smem activations)
     uint32_t* bits = reinterpret_cast<uint32_t*>(vec + (size_t)RP * T * a.VS);  // [RP*T][BWS] (GRAD only)
 
@@ -290,14 +293,14 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
         const float* Ap[RP];
         const float* Aq[RP];
         int rows_here = 0, b0 = 0;
-        if (MODE != FAST_FWD) {
+        if (fast_is_grad(MODE)) {
             b0 = tile * a.TB;
             rows_here = min(a.TB, a.B - b0);
         }
 #pragma unroll
         for (int r = 0; r < RP; ++r) {
             const int q = tid + r * T;
-            if (MODE != FAST_FWD) {
+            if (fast_is_grad(MODE)) {
                 live[r] = q < rows_here * a.S;
                 const int s = live[r] ? q / rows_here : 0;
                 rrow[r] = live[r] ? q % rows_here : 0;
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
             Ap[r] = a.A_p + b;
             Aq[r] = a.A_q + b;
         }
-        if (MODE != FAST_FWD) {
+        if (fast_is_grad(MODE)) {
             __syncthreads();
             for (int i = tid; i < H0 * a.TBp; i += T) gAt[i] = 0.f;
         }
@@ -322,18 +325,18 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
             float ssq = 0.f;
             for (int d = 0; d < D; ++d) {
                 const float zv = live[r] ? a.z[(size_t)pidx[r] * D + d] : 0.f;
-                vecp[r][oV + d] = zv;
+                vecp[r][oV + (MODE == FAST_LOGPROB ? K * D : 0) + d] = zv;  // LOGPROB: the input is theta = v_K
                 ssq = fmaf(zv, zv, ssq);
             }
-            logp[r] = -0.5f * ssq - (float)D * HALF_LOG_2PI;
+            logp[r] = MODE == FAST_LOGPROB ? 0.f : -0.5f * ssq - (float)D * HALF_LOG_2PI;
             logq[r] = 0.f;
         }
 
         // One loop over the 2K (forward) / 4K (forward + reverse) phases; every building block below is
         // instantiated exactly once.  kind: 0 = sampling pass under A_p (k ascending), 1 = density pass under A_q
         // (k descending), 2 = reverse of the density pass (k ascending), 3 = reverse of the sampling pass.
-        const int nphase = (MODE == FAST_GRAD ? 4 : MODE == FAST_FKL ? 3 : 2) * K;
-        for (int ph = 0; ph < nphase; ++ph) {
+        const int nphase = (MODE == FAST_GRAD ? 4 : MODE == FAST_FKL ? 3 : MODE == FAST_RSAMPLE ? 1 : 2) * K;
+        for (int ph = (MODE == FAST_LOGPROB ? K : 0); ph < nphase; ++ph) {
             const int kind = ph / K;
             const int idx = ph - kind * K;
             const int k = (kind == 0 || kind == 2) ? idx : K - 1 - idx;
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                                     if (u >= ua && u < ub) {
                                         const bool on = pre[r][c] > 0.f;
                                         nv[c] = on ? pre[r][c] : 0.f;
-                                        if (MODE != FAST_FWD) {
+                                        if (fast_is_grad(MODE)) {
                                             if (on) w0[r] |= 1u << (u & 31);
                                             if ((u & 31) == 31 || u == H0 - 1) {
                                                 bitp[r][bs * WL + (u >> 5)] = w0[r];
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                                             oms[r][2 * q2] = ffma2(make_float2(wq[q2].x, wq[q2].y), hh, oms[r][2 * q2]);
                                             oms[r][2 * q2 + 1] = ffma2(make_float2(wq[q2].z, wq[q2].w), hh, oms[r][2 * q2 + 1]);
                                         }
-                                        if (MODE != FAST_FWD) {
+                                        if (fast_is_grad(MODE)) {
                                             if (on) w1[r] |= 1u << (v & 31);
                                             if ((v & 31) == 31 || v == H1 - 1) {
                                                 bitp[r][(bs + 1) * WL + (v >> 5)] = w1[r];
@@ -516,10 +519,10 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                             for (int d = 0; d < D; ++d) {
                                 const float u = vecp[r][oU + d];
                                 ssq = fmaf(u, u, ssq);
-                                if (MODE != FAST_FWD) vecp[r][oG + d] = a.w * u;  // d(-w log q)/d u_0
+                                if (fast_is_grad(MODE)) vecp[r][oG + d] = a.w * u;  // d(-w log q)/d u_0
                             }
                             logq[r] += -0.5f * ssq - (float)D * HALF_LOG_2PI;
-                            if (a.diff && live[r]) a.diff[pidx[r]] = logp[r] - logq[r];
+                            if (a.diff && live[r]) a.diff[pidx[r]] = MODE == FAST_LOGPROB ? logq[r] : logp[r] - logq[r];
                         }
                     }
                 }
@@ -667,6 +670,14 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                     __syncthreads();
                 }
             }
+        }
+        if (MODE == FAST_RSAMPLE) {
+#pragma unroll
+            for (int r = 0; r < RP; ++r)
+                if (live[r]) {
+                    for (int d = 0; d < D; ++d) a.theta_out[(size_t)pidx[r] * D + d] = vecp[r][oV + K * D + d];
+                    if (a.diff) a.diff[pidx[r]] = logp[r];
+                }
         }
     }
     if (TM) {

@@ -832,6 +832,9 @@ extern "C" double rabi_fma_peak_tflops(int device, int repeats) {
     return cudaGetLastError() == cudaSuccess ? best : -1.0;
 }
 
+template <int MODE>
+static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st);  // defined below
+
 extern "C" int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const float* theta_dev, int S, int B,
                                      float* logp_dev, rabi_stream_t s) {
     REQUIRE_READY(h);
@@ -841,6 +844,17 @@ extern "C" int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const fl
     a.out_lp = logp_dev;
     a.S = S;
     a.B = B;
+    {
+        FastArgs fa = {};
+        fa.A_p = A_dev;
+        fa.A_q = A_dev;
+        fa.z = theta_dev;
+        fa.diff = logp_dev;
+        fa.S = S;
+        fa.B = B;
+        int rc = launch_fast<FAST_LOGPROB>(h, fa, (cudaStream_t)s);
+        if (rc != 2) return rc;
+    }
     return launch_pairs<MODE_LOGPROB>(h, a, (cudaStream_t)s);
 }
 
@@ -854,6 +868,18 @@ extern "C" int rabi_maf_rsample_fwd(rabi_maf_t* h, const float* A_dev, const flo
     a.out_lp = logq_dev;
     a.S = S;
     a.B = B;
+    {
+        FastArgs fa = {};
+        fa.A_p = A_dev;
+        fa.A_q = A_dev;
+        fa.z = z_dev;
+        fa.theta_out = theta_dev;
+        fa.diff = logq_dev;
+        fa.S = S;
+        fa.B = B;
+        int rc = launch_fast<FAST_RSAMPLE>(h, fa, (cudaStream_t)s);
+        if (rc != 2) return rc;
+    }
     return launch_pairs<MODE_RSAMPLE>(h, a, (cudaStream_t)s);
 }
 
@@ -869,7 +895,7 @@ template <int MODE, int RP, int DP, bool TM, int LDC>
 static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel, int grid, int T, size_t smem,
                             cudaStream_t st) {
     CU_OK(h, cudaFuncSetAttribute(k_fast<MODE, RP, DP, TM, LDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const bool prof = h->profiling && MODE != FAST_FWD;
+    const bool prof = h->profiling && fast_is_grad(MODE);
     if (prof) {
         if (h->prof_used == h->prof_events.size()) {
             cudaEvent_t e0, e1;
@@ -890,6 +916,7 @@ static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel,
 
 template <int MODE>
 static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
+    if ((long long)fa.S * fa.B <= 0) return 0;  // empty batch: nothing to launch
     if (env_int("RABI_DISABLE_FAST", 0)) return 2;
     if (h->L != 2 || h->D > 12) return 2;
     const MafImg& g = h->img;
@@ -920,7 +947,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     fa.AS = AS;
     fa.VS = ((4 * K + 2) * D) | 1;
     const int WL = (g.Hmax + 31) / 32;
-    fa.BWS = MODE != FAST_FWD ? ((2 * K * 2 * WL) | 1) : 0;
+    fa.BWS = fast_is_grad(MODE) ? ((2 * K * 2 * WL) | 1) : 0;
     const size_t per_slot = (size_t)((TM ? 0 : fa.AS) + fa.VS + fa.BWS) * sizeof(float);
     const size_t fixed = (size_t)(fa.wfloats + fa.wints) * sizeof(float);
     const size_t budget = (size_t)h->max_smem_optin - 1024;
@@ -934,7 +961,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     size_t smem = 0;
     const long long npairs = (long long)fa.S * fa.B;
     auto gat_bytes = [&](int tbp) { return (((size_t)H0 * tbp + 3) & ~(size_t)3) * sizeof(float); };
-    if (MODE != FAST_FWD) {
+    if (fast_is_grad(MODE)) {
         // largest T whose slots (+ the gA tile for the rows they hold) fit
         for (;; T -= 32) {
             if (T < 32) return 2;

@@ -182,7 +182,8 @@ class MAFPosterior(Distribution):
         nb = len(self.batch_shape)
         full = torch.broadcast_shapes(value.shape[:-1], self.batch_shape)
         sample_shape = full[: len(full) - nb]
-        v = value.expand(full + (D,)).reshape(-1, int(self.batch_shape.numel()), D)
+        # explicit sizes: reshape(-1, ...) is ambiguous for empty batches
+        v = value.expand(full + (D,)).reshape(int(sample_shape.numel()), int(self.batch_shape.numel()), D)
         return v, full, sample_shape
 
     # -- Distribution API

@@ -234,3 +234,78 @@ def test_forward_kl_attack_vs_oracle(shape, dev):
     with noise.injected(zs):
         xa = atk.perturb(x.to(dev), delta_init=d0.to(dev))
     assert_trajectories_match(xa.cpu() - x, xa_ref - x, 2 * RTOL)
+
+
+def test_edge_cases_empty_ragged_and_large_sample_counts(dev):
+    """Empty batches, S = 1, row counts that are not multiples of the tile / vector sizes, more samples per row than a
+    tile holds (falls back to the generic kernel), and equality of the fast and the generic kernels."""
+    import os
+
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+
+    ref, model, x = _fresh(dict(dx=10, D=4, hidden=[24, 24], B=37), dev, seed=4)
+    xd = x.to(dev)
+    with torch.no_grad():
+        q = model(xd)
+        # empty sample shape and empty batch
+        assert q.rsample((0,)).shape == (0, 37, 4)
+        assert model(xd[:0]).log_prob(torch.zeros(3, 0, 4, device=dev)).shape == (3, 0)
+        assert ReverseKLLoss(mc_samples=4, reduction=None)(model(xd[:0]), model(xd[:0])).shape == (0,)
+        # S = 1 and a ragged row count, fast vs generic kernel
+        g = torch.Generator().manual_seed(0)
+        for S in (1, 3, 700):
+            z = torch.randn(S, 37, 4, generator=g)
+            outs = []
+            for flag in ("0", "1"):
+                os.environ["RABI_DISABLE_FAST"] = flag
+                with noise.injected([z, z]):
+                    th = q.rsample((S,))
+                    lp = q.log_prob(th.clone())
+                    kl = ReverseKLLoss(mc_samples=S, reduction=None)(model(xd + 0.1), q)
+                outs.append((th, lp, kl))
+            os.environ["RABI_DISABLE_FAST"] = "0"
+            (th_f, lp_f, kl_f), (th_g, lp_g, kl_g) = outs
+            assert rel_err(th_f, th_g) < 1e-5 and rel_err(lp_f, lp_g) < 1e-5
+            # KL values are differences of O(10) log-densities: compare on that scale
+            assert float((kl_f - kl_g).abs().max()) < 1e-5 * float(lp_g.abs().max())
+            with O_injected([z]):
+                th_ref = ref(x).rsample((S,))
+            assert rel_err(outs[0][0], th_ref) < RTOL
+    # an attack whose S exceeds one tile's capacity still works (generic kernel) and respects the constraints
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=600), eps=0.3, nb_iter=2, eps_iter=0.1, clip_min=-2.0,
+                      clip_max=2.0)
+    xa = atk.perturb(xd[:3])
+    assert float((xa - xd[:3].clamp(-2, 2)).norm(dim=-1).max()) <= 0.3 * 1.001 + float((xd[:3] - xd[:3].clamp(-2, 2)).norm(dim=-1).max())
+
+
+def O_injected(noise_list):
+    from oracle import rbi_oracle as O
+
+    return O.injected_base_noise(noise_list)
+
+
+def test_sharded_equals_chunked_attack(dev):
+    """attacking all rows in one call with chunk_size=c gives every row the trajectory it gets when
+    the rows are attacked in independent chunks of c rows (the reference's batched walk)."""
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+
+    _, model, x = _fresh(SHAPES["lotka_volterra"], dev, seed=6)
+    xd = x.to(dev)[:64]
+    B, D, S, nb, c = 64, 4, 5, 6, 16
+    eps = float(0.5 * xd.std(1).mean())
+    g = torch.Generator().manual_seed(5)
+    zs = [torch.randn(S, B, D, generator=g) for _ in range(nb)]
+    d0 = (0.1 * eps * torch.randn(B, xd.shape[1], generator=g)).to(dev)
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=S), eps=eps, nb_iter=nb, eps_iter=eps / 10,
+                      clip_min=-4.0, clip_max=4.0)
+    with noise.injected(zs):
+        whole = atk.perturb(xd, delta_init=d0, chunk_size=c)
+    parts = []
+    for i in range(0, B, c):
+        with noise.injected([z[:, i:i + c].contiguous() for z in zs]):
+            parts.append(atk.perturb(xd[i:i + c], delta_init=d0[i:i + c]))
+    assert_trajectories_match(whole.cpu() - xd.cpu(), torch.cat(parts).cpu() - xd.cpu(), 1e-5)
