@@ -136,6 +136,11 @@ class _Struct:
                 starts[self.D] = int(deg.numel())
                 gl.append(starts)
             self.groups.append(gl)
+        dev = model.base_dist_mean.device
+        self.perm_prefix = [[torch.as_tensor(p[:j], dtype=torch.long, device=dev) for j in range(self.D)] for p in self.perm]
+        self.out_rows = [[torch.as_tensor([p[j], self.D + p[j]], dtype=torch.long, device=dev) for j in range(self.D)]
+                         for p in self.perm]
+        self.device = dev
         self.post = None
         if getattr(model, "shuffle", False):
             self.post = [getattr(model, "permute" + str(k)) for k in range(self.K)]
@@ -144,7 +149,7 @@ class _Struct:
 
 def _struct(model) -> _Struct:
     st = getattr(model, "_ag_struct", None)
-    if st is None:
+    if st is None or st.device != model.base_dist_mean.device:
         st = _Struct(model)
         object.__setattr__(model, "_ag_struct", st)
     return st
@@ -224,7 +229,7 @@ def rsample_differentiable(post, z: Tensor) -> Tuple[Tensor, Tensor]:
             a0, a1 = grp[0][j], grp[0][j + 1]
             pre = A[:, a0:a1]
             if j > 0 and a1 > a0:
-                Wt = W0[a0:a1, C:].index_select(1, torch.as_tensor(perm[:j], device=W0.device))
+                Wt = W0[a0:a1, C:].index_select(1, st.perm_prefix[k][j])
                 pre = pre + linear(torch.stack(ys, -1), Wt)
             hs[0].append(torch.relu(pre))
             for l in range(1, nl):
@@ -235,7 +240,7 @@ def rsample_differentiable(post, z: Tensor) -> Tuple[Tensor, Tensor]:
                 hs[l].append(torch.relu(linear(hin, W[v0:v1, :e], b[v0:v1])))
             e = grp[nl - 1][j + 1]
             hin = torch.cat(hs[nl - 1], -1)
-            rows = torch.as_tensor([d, D + d], device=Wo.device)
+            rows = st.out_rows[k][j]
             ms = linear(hin, Wo.index_select(0, rows)[:, :e], bo.index_select(0, rows))
             sh = clamp_preserve_gradients(ms[:, 1], lo, hi)
             yj = (x[:, d] - ms[:, 0]) * torch.exp(-sh)

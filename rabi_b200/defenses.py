@@ -87,8 +87,12 @@ class FIMTraceRegularizer(AdditiveRegularizer):
 
     def __init__(self, model: Module, loss_fn: TrainLoss, beta: float = 1.0, algorithm: str = "jac_exact",
                  mc_samples: int = 20, ema_mc_samples: int = 1, ema_decay: float = 0.99, clamp_val=None,
-                 grad_clamp_val=None, reduce: str = "mean"):
+                 grad_clamp_val=None, reduce: str = "mean", cuda_graph: bool = True):
         super().__init__(model, loss_fn, reduce=reduce)
+        # ``cuda_graph``: capture (trace estimate + double backward + EMA update) once per input shape and replay it
+        # every step -- the unfused path is ~1.7k tiny launches, i.e. launch-bound; replay runs them back to back.
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
         self.beta = beta
         self.algorithm = algorithm
         self.mc_samples = mc_samples
@@ -107,6 +111,13 @@ class FIMTraceRegularizer(AdditiveRegularizer):
     def _trace(self, input: Tensor, output: Distribution, mc_samples: int) -> Tensor:
         reg = monte_carlo_fisher(self.model, input, output, mc_samples=mc_samples, create_graph=True,
                                  retain_graph=True, typ="trace")
+        if self.reduce in ("mean", "sum"):
+            # mean over the finite entries without a data-dependent shape (== reg[isfinite(reg)].mean(); capturable)
+            mask = torch.isfinite(reg)
+            reg = torch.where(mask, reg, torch.zeros_like(reg))
+            if self.clamp_val is not None:
+                reg = reg.clamp(min=0, max=self.clamp_val)
+            return self.beta * (reg.sum() / mask.sum())
         reg = reg[torch.isfinite(reg)]
         if self.clamp_val is not None:
             reg = reg.clamp(min=0, max=self.clamp_val)
@@ -116,7 +127,56 @@ class FIMTraceRegularizer(AdditiveRegularizer):
         # for a flow the reference's fisher_information_matrix dispatches to the MC score estimator as well
         return self._trace(input, output, self.mc_samples)
 
+    # ---- CUDA-graph replay of the ema step ---------------------------------------------------------------------
+    def _graph_eligible(self, input: Tensor) -> bool:
+        from . import noise
+        return (self.cuda_graph and input.is_cuda and input.dim() == 2 and noise._queue is None
+                and self.reduce in ("mean", "sum") and self.ema.t >= 2)  # two eager steps warm everything up
+
+    def _ema_graphed(self, input: Tensor) -> Tensor:
+        from . import noise
+        params = list(self.model.parameters())
+        key = (tuple(input.shape), input.device, tuple(id(p) for p in params))
+        st = self._graphs.get(key)
+        D = self.model.output_dim
+        if st is None:
+            d = float(self.ema.decay)
+            st = {"x": input.detach().clone(),
+                  "z": torch.empty((self.ema_mc_samples, input.shape[0], D), device=input.device),
+                  "t": torch.full((), float(self.ema.t), device=input.device),
+                  "m": [m.detach().clone() for m in self.ema._x_old],
+                  "grads": [torch.zeros_like(p) for p in params]}
+            side = torch.cuda.Stream(device=input.device)
+            side.wait_stream(torch.cuda.current_stream(input.device))
+            graph = torch.cuda.CUDAGraph()
+            st["z"].normal_()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    with noise.injected([st["z"]]):
+                        reg = self._trace(st["x"], self.model(st["x"]), self.ema_mc_samples)
+                    grads = torch.autograd.grad(reg, params)
+                    st["t"].add_(1.0)
+                    corr = 1.0 - torch.pow(torch.full_like(st["t"], 1.0 - d), st["t"])
+                    for m, g_, out in zip(st["m"], grads, st["grads"]):
+                        m.mul_(1.0 - d).add_(torch.nan_to_num(g_), alpha=d)
+                        out.copy_(torch.nan_to_num(m / corr))
+            torch.cuda.current_stream(input.device).wait_stream(side)
+            st["graph"] = graph
+            self._graphs[key] = st
+        st["x"].copy_(input.detach())
+        st["z"].normal_()
+        st["graph"].replay()
+        self.ema.t += 1
+        self.ema._x_old = st["m"]
+        for p, g_ in zip(params, st["grads"]):
+            p.grad = g_
+        if self.grad_clamp_val is not None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clamp_val, norm_type=2.0)
+        return torch.zeros(1, device=input.device)
+
     def _regularizer_ema(self, input: Tensor, output: Distribution, target: Tensor) -> Tensor:
+        if self._graph_eligible(input):
+            return self._ema_graphed(input)
         reg = self._trace(input, output, self.ema_mc_samples)
         grads = torch.autograd.grad(reg, list(self.model.parameters()), retain_graph=True)
         self.ema(grads)

@@ -296,11 +296,13 @@ class InverseAffineAutoregressiveModel(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_engine"] = None  # device handles are rebuilt lazily; keeps deepcopy / torch.save(model) working
+        state.pop("_ag_struct", None)
         return state
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self._engine = None
+        self.__dict__.pop("_ag_struct", None)
         return out
 
     def load_state_dict(self, state_dict, *a, **k):

@@ -110,3 +110,48 @@ def test_trades_rkl_regularizer(case, dev):
         _check_grads(_grads(model), t["grads_clean"], 3 * RTOL)
     finally:
         trades.deactivate()
+
+
+def test_fim_regularizer_cuda_graph_replay_equals_eager(dev):
+    """The CUDA-graph replay of the ema step (trace + double backward + EMA) gives the same ``p.grad`` and EMA state
+    as the eager path when both see the same base noise."""
+    import copy
+
+    from rabi_b200 import noise
+    from rabi_b200.defenses import FIMTraceRegularizer
+    from rabi_b200.loss import NLLLoss
+
+    g = load_golden("lotka_volterra")
+    m1 = build_product(g, dev, with_output_transform=False).train()
+    m2 = copy.deepcopy(m1).to(dev).train()
+    x = torch.randn(64, g["cfg"]["dx"], device=dev) * g["zs_std"].to(dev) + g["zs_mean"].to(dev)
+    th = torch.randn(64, g["cfg"]["D"], device=dev)
+    regs = []
+    for m, graph in ((m1, True), (m2, False)):
+        lf = NLLLoss(m).train()
+        r = FIMTraceRegularizer(m, lf, beta=0.05, ema_mc_samples=5, algorithm="ema", ema_decay=0.85, cuda_graph=graph)
+        r.activate()
+        regs.append((m, lf, r))
+    torch.manual_seed(0)
+    for step in range(5):
+        z = torch.randn(5, 64, g["cfg"]["D"], device=dev)
+        grads = []
+        for m, lf, r in regs:
+            m.zero_grad(set_to_none=True)
+            if r.cuda_graph and r.ema.t >= 2:
+                # graph mode draws its own noise into a static buffer; overwrite it for the comparison
+                orig = torch.Tensor.normal_
+                try:
+                    torch.Tensor.normal_ = lambda self, *a, **k: self.copy_(z) if self.shape == z.shape else orig(self, *a, **k)
+                    loss = lf(x, th)
+                finally:
+                    torch.Tensor.normal_ = orig
+            else:
+                with noise.injected([z]):
+                    loss = lf(x, th)
+            loss.backward()
+            grads.append([p.grad.detach().clone() for p in m.parameters()])
+        scale = max(float(b.abs().max()) for b in grads[1])
+        for a, b in zip(*grads):
+            assert float((a - b).abs().max()) <= 2e-4 * scale, (step, float((a - b).abs().max()), scale)
+    assert regs[0][2]._graphs, "the graph path was not taken"
