@@ -1227,18 +1227,21 @@ __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float*
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    // split-K: blockIdx.z owns the k-range [kz0, kz1); partial tiles are combined with atomicAdd into a zeroed C
+    const int kper = ((K + gridDim.z - 1) / gridDim.z + BK - 1) / BK * BK;
+    const int kz0 = blockIdx.z * kper, kz1 = min(K, kz0 + kper);
+    for (int k0 = kz0; k0 < kz1; k0 += BK) {
         for (int i = threadIdx.x; i < BM * BK; i += 256) {
             int mm, kk;
             if (TA) { mm = i % BM; kk = i / BM; } else { kk = i % BK; mm = i / BK; }
             const int m = m0 + mm, k = k0 + kk;
-            As[kk][mm] = (m < M && k < K) ? (TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
+            As[kk][mm] = (m < M && k < kz1) ? (TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
         }
         for (int i = threadIdx.x; i < BN * BK; i += 256) {
             int nn, kk;
             if (TB) { kk = i % BK; nn = i / BK; } else { nn = i % BN; kk = i / BN; }
             const int n = n0 + nn, k = k0 + kk;
-            Bs[kk][nn] = (n < N && k < K) ? (TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n]) : 0.f;
+            Bs[kk][nn] = (n < N && k < kz1) ? (TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n]) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -1262,7 +1265,8 @@ __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float*
             const int n = n0 + 4 * tx + j;
             if (n < N) {
                 float* c = C + (size_t)m * ldc + n;
-                *c = beta != 0.f ? beta * *c + acc[i][j] : acc[i][j];
+                if (gridDim.z > 1) atomicAdd(c, acc[i][j]);
+                else *c = beta != 0.f ? beta * *c + acc[i][j] : acc[i][j];
             }
         }
     }
@@ -1277,6 +1281,16 @@ extern "C" int rabi_sgemm(int device, int transA, int transB, int M, int N, int 
     if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, "cudaSetDevice(%d) failed", device);
     cudaStream_t st = (cudaStream_t)s;
     dim3 grid((N + 63) / 64, (M + 63) / 64);
+    // few output tiles and a long reduction (weight gradients: the batch is the K dimension): split K over blocks
+    if (beta == 0.f && grid.x * grid.y <= 16 && K >= 512) {
+        grid.z = std::min(64, (K + 127) / 128);
+        for (int m = 0; m < M; ++m)
+            if (ldc == N) {
+                if (cudaMemsetAsync(C_dev, 0, (size_t)M * N * sizeof(float), st) != cudaSuccess) return fail(nullptr, "memset failed");
+                break;
+            } else if (cudaMemsetAsync(C_dev + (size_t)m * ldc, 0, (size_t)N * sizeof(float), st) != cudaSuccess)
+                return fail(nullptr, "memset failed");
+    }
     if (transA && transB) k_sgemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A_dev, lda, B_dev, ldb, C_dev, ldc, beta);
     else if (transA) k_sgemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A_dev, lda, B_dev, ldb, C_dev, ldc, beta);
     else if (transB) k_sgemm<false, true><<<grid, 256, 0, st>>>(M, N, K, A_dev, lda, B_dev, ldb, C_dev, ldc, beta);

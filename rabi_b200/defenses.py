@@ -152,9 +152,15 @@ class FIMTraceRegularizer(AdditiveRegularizer):
             st["z"].normal_()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(graph, stream=side):
-                    with noise.injected([st["z"]]):
-                        reg = self._trace(st["x"], self.model(st["x"]), self.ema_mc_samples)
-                    grads = torch.autograd.grad(reg, params)
+                    # Differentiate w.r.t. fresh leaves that alias the live parameters: the parameters' own
+                    # AccumulateGrad nodes belong to the (still alive) NLL graph on the default stream, and letting
+                    # the engine touch them would join the capturing stream with the legacy stream.
+                    from torch.nn.utils import stateless
+                    leaves = {n: p.detach().requires_grad_() for n, p in self.model.named_parameters()}
+                    with stateless._reparametrize_module(self.model, leaves):
+                        with noise.injected([st["z"]]):
+                            reg = self._trace(st["x"], self.model(st["x"]), self.ema_mc_samples)
+                        grads = torch.autograd.grad(reg, [leaves[n] for n, _ in self.model.named_parameters()])
                     st["t"].add_(1.0)
                     corr = 1.0 - torch.pow(torch.full_like(st["t"], 1.0 - d), st["t"])
                     for m, g_, out in zip(st["m"], grads, st["grads"]):
