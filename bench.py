@@ -34,6 +34,12 @@ WORKLOADS = {
     # BASELINE.json configs[1]
     "lotka_volterra_l2pgd_rkl": dict(dx=100, D=4, hidden=[100, 100], K=3, rows=10000, chunk=1000, nb_iter=200,
                                      S_att=5, S_eval=256),
+    # not bench lines of their own (parity-test shapes); selectable for the record with --workload
+    "gaussian_linear_l2pgd_rkl": dict(dx=10, D=10, hidden=[100, 100], K=3, rows=10000, chunk=1000, nb_iter=200,
+                                      S_att=5, S_eval=256),
+    # BASELINE configs[4], ctx-space variant: h ~ N(0, I_100) given, 12 500 rows per GPU
+    "pyloric_ctx_l2pgd_rkl": dict(dx=100, D=31, hidden=[200, 200, 200], K=3, rows=12500, chunk=500, nb_iter=200,
+                                  S_att=5, S_eval=256),
 }
 METRIC = "attacked (x, MC-sample) MAF posterior evals/sec"
 UNIT = "pairs/s"

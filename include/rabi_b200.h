@@ -111,6 +111,12 @@ int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const 
                      float eps_iter, float clip_min, float clip_max, float inv_B, float norm_floor,
                      float* x_adv_dev, rabi_stream_t s);
 
+/* The update half of one advertorch perturb_iterative(ord=2) iteration on its own, for attacks whose gradient has to be
+ * chained through a non-identity embedding net by the caller (x-space PGD, e.g. pyloric's CNN embedding):
+ *   g = grad / max(||grad||_2, norm_floor);  delta += eps_iter*g;  delta = clamp(x+delta) - x;  delta *= min(1, eps/||delta||_2) */
+int rabi_pgd_update(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* grad_dev, int B, int dx, float eps,
+                    float eps_iter, float clip_min, float clip_max, float norm_floor, rabi_stream_t s);
+
 /* Forward-KL attack loss (ForwardKLLoss, rbi/rbi/loss/eval_loss.py:108-126 -- the default attack_loss_fn of
  * config/eval_rob/attack/l2pgd.yaml): loss = inv_B * sum_b KL(target_b || q(.|x_b + delta_b)); samples are drawn from the
  * fixed target (projection A_t_dev; NULL in the run = the clean x), the gradient flows through the density pass only.

@@ -83,10 +83,7 @@ class L2PGDAttack(Attack):
         m = self.predict
         if not isinstance(m, InverseAffineAutoregressiveModel) or not isinstance(y, MAFPosterior) or y.model is not m:
             return False
-        if type(self.loss_fn) not in (ReverseKLLoss, ForwardKLLoss) or self.loss_fn.reduction != "mean":
-            return False
-        from .models import _split_embedding
-        return _split_embedding(m.embedding_net)[1] is None
+        return type(self.loss_fn) in (ReverseKLLoss, ForwardKLLoss) and self.loss_fn.reduction == "mean"
 
     def perturb(self, x: Tensor, y: Optional[Any] = None, delta_init: Optional[Tensor] = None,
                 chunk_size: Optional[int] = None) -> Tensor:
@@ -101,8 +98,8 @@ class L2PGDAttack(Attack):
             raise ValueError("perturb expects x of shape [B, dx]")
         if not self._fused_ok(y):
             raise NotImplementedError(
-                "fused L2-PGD supports predict=InverseAffineAutoregressiveModel with an identity/z-score embedding "
-                f"and loss_fn=ReverseKLLoss / ForwardKLLoss (reduction='mean'); got loss_fn={type(self.loss_fn).__name__}")
+                "L2PGDAttack supports predict=InverseAffineAutoregressiveModel (any embedding net) with "
+                f"loss_fn=ReverseKLLoss / ForwardKLLoss (reduction='mean'); got loss_fn={type(self.loss_fn).__name__}")
         model: InverseAffineAutoregressiveModel = self.predict
         eng = model.engine()
         x = x.float().contiguous()
@@ -123,11 +120,30 @@ class L2PGDAttack(Attack):
         inv_B = 1.0 / float(min(B, chunk_size) if chunk_size else B)
         if self.targeted:
             inv_B = -inv_B  # perturb_iterative(minimize=True): descend on the loss
+        from .models import _split_embedding
+        if _split_embedding(model.embedding_net)[1] is not None:
+            return self._run_embedded(model, eng, x, delta, y, z_all, inv_B).detach()
         _, zs, _ = model.condition_inputs(x)
         zs = zs if zs is not None else (None, None)
         # A_q: the target's projection (== projection of the clean x when untargeted)
         x_adv = self._run(eng, x, delta, zs, y, z_all, inv_B)
         return x_adv.detach()
+
+    def _run_embedded(self, model, eng, x, delta, y, z_all, inv_B):
+        """x-space PGD through a non-identity embedding net (e.g. pyloric's CNN): every iteration the embedding runs in
+        torch, the flow part (divergence and its gradient w.r.t. the embedded context h) runs on the fused kernels, the
+        gradient is chained back through the embedding by autograd and the step / projection runs on the update
+        kernel.  Same arithmetic as perturb_iterative(ord=2) on ``loss_fn(predict(x + delta), y)``."""
+        fkl = type(self.loss_fn) is ForwardKLLoss
+        for it in range(z_all.shape[0]):
+            xd = (x + delta).requires_grad_()
+            with torch.enable_grad():
+                h = model.embedding_net(xd)
+            gh, _ = eng.rkl_input_grad(h.detach().float().contiguous(), None, None, y.A, z_all[it], inv_B,
+                                       want_kl=False, forward_kl=fkl)
+            (gx,) = torch.autograd.grad(h, xd, gh)
+            eng.pgd_update(x, delta, gx.contiguous(), self.eps, self.eps_iter, self.clip_min, self.clip_max)
+        return torch.clamp(x + delta, self.clip_min, self.clip_max)
 
     def _run(self, eng, x, delta, zs, y, z_all, inv_B):
         return eng.pgd_run(x, delta, zs[0], zs[1], y.A, z_all, self.eps, self.eps_iter, self.clip_min, self.clip_max,

@@ -1121,6 +1121,18 @@ extern "C" int rabi_rkl_pgd_step(rabi_maf_t* h, const float* x_dev, float* delta
                          clip_max, inv_B, norm_floor, kl_dev, (cudaStream_t)s);
 }
 
+extern "C" int rabi_pgd_update(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* grad_dev, int B, int dx,
+                               float eps, float eps_iter, float clip_min, float clip_max, float norm_floor,
+                               rabi_stream_t s) {
+    REQUIRE_READY(h);
+    if (B <= 0 || dx <= 0) return 0;
+    int threads = 128, rows_per_block = threads / 32;
+    k_pgd_update<<<(B + rows_per_block - 1) / rows_per_block, threads, 0, (cudaStream_t)s>>>(
+        x_dev, delta_dev, grad_dev, B, dx, eps, eps_iter, clip_min, clip_max, norm_floor);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
 extern "C" int rabi_rkl_input_grad(rabi_maf_t* h, const float* x_dev, const float* zs_mean_dev, const float* zs_std_dev,
                                    const float* A_q_dev, const float* z_dev, int S, int B, float inv_B, float* gx_dev,
                                    float* kl_dev, rabi_stream_t s) {

@@ -174,6 +174,14 @@ class MafEngine:
                                                    S, B, float(inv_B), _ptr(gx), _ptr(kl), self._stream()))
         return gx, kl
 
+    def pgd_update(self, x, delta, grad, eps, eps_iter, clip_min, clip_max, norm_floor=1e-6):
+        """In-place L2 step / box clamp / projection of ``delta`` given d loss / d delta."""
+        B, dx = x.shape
+        with torch.cuda.device(self.device):
+            self._check(self.L.rabi_pgd_update(self.h, _ptr(x), _ptr(delta), _ptr(_f32c(grad)), B, dx, float(eps),
+                                               float(eps_iter), float(clip_min), float(clip_max), float(norm_floor),
+                                               self._stream()))
+
     def pgd_step(self, x, delta, zs_mean, zs_std, A_q, z, eps, eps_iter, clip_min, clip_max, inv_B,
                  norm_floor=1e-6, want_kl=False):
         z = _f32c(z)

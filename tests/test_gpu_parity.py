@@ -309,3 +309,53 @@ def test_sharded_equals_chunked_attack(dev):
         with noise.injected([z[:, i:i + c].contiguous() for z in zs]):
             parts.append(atk.perturb(xd[i:i + c], delta_init=d0[i:i + c]))
     assert_trajectories_match(whole.cpu() - xd.cpu(), torch.cat(parts).cpu() - xd.cpu(), 1e-5)
+
+
+def test_l2pgd_through_a_nonidentity_embedding_vs_oracle(dev):
+    """x-space PGD with a learned embedding net in front of the flow (pyloric-style: z-score -> network -> context):
+    the gradient is chained through the torch embedding, everything else runs on the kernels."""
+    from oracle import rbi_oracle as O
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+    from rabi_b200.models import InverseAffineAutoregressiveModel, ZScoreLayer
+
+    torch.manual_seed(8)
+    dx, C, D, B, S, nb = 40, 12, 5, 24, 5, 6
+    kw = dict(log_scale_min_clip=-7, log_scale_max_clip=5, stable=False)
+    mean, std = 0.2 * torch.randn(dx), 0.5 + torch.rand(dx)
+
+    def emb(zcls):
+        torch.manual_seed(3)
+        return torch.nn.Sequential(zcls(mean.clone(), std.clone()), torch.nn.Linear(dx, 32), torch.nn.Tanh(),
+                                   torch.nn.Linear(32, C))
+
+    ref = O.OracleMAF(dx, D, hidden_dims=[32, 32], num_transforms=3, shuffle=False, embedding_net=emb(O.ZScoreLayer), **kw)
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if n.startswith("t"):
+                p.add_(0.3 * torch.randn_like(p) * (p.abs().mean() + 0.05))
+    model = InverseAffineAutoregressiveModel(dx, D, hidden_dims=[32, 32], num_transforms=3, shuffle=False,
+                                             embedding_net=emb(ZScoreLayer), **kw)
+    model.load_state_dict(ref.state_dict())
+    ref, model = ref.eval(), model.to(dev).eval()
+    assert model.context_dim == C
+    x = torch.randn(B, dx) * std + mean
+    eps = float(0.5 * x.std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+    g = torch.Generator().manual_seed(1)
+    zs = [torch.randn(S, B, D, generator=g) for _ in range(nb)]
+    d0 = O.adv.clamp_by_pnorm(torch.randn(B, dx, generator=g), 2, eps)
+    d0 = O.adv.clamp(x + d0, cmin, cmax) - x
+    with O.injected_base_noise(zs):
+        xa_ref = O.l2pgd_perturb(ref, x, O.ReverseKLLoss(mc_samples=S), eps, nb, eps / 10, cmin, cmax, delta0=d0)
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=S), eps=eps, nb_iter=nb, eps_iter=eps / 10,
+                      clip_min=cmin, clip_max=cmax)
+    with noise.injected(zs):
+        xa = atk.perturb(x.to(dev), delta_init=d0.to(dev))
+    assert_trajectories_match(xa.cpu() - x, xa_ref - x, 2 * RTOL)
+    with torch.no_grad(), O.injected_base_noise([zs[0]]):
+        kl_ref = O.ReverseKLLoss(mc_samples=S, reduction=None)(ref(xa_ref), ref(x))
+    with torch.no_grad(), noise.injected([zs[0]]):
+        kl = ReverseKLLoss(mc_samples=S, reduction=None)(model(xa_ref.to(dev)), model(x.to(dev)))
+    assert float((kl.cpu() - kl_ref).abs().max()) < 1e-3
