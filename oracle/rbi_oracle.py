@@ -48,11 +48,25 @@ def injected_base_noise(noise: Sequence[Tensor]):
         assert tuple(z.shape) == tuple(shape), (z.shape, shape)
         return z.to(dtype=dtype, device=device)
 
+    orig_sample = Normal.sample
+
+    def fake_sample(self, sample_shape=torch.Size()):
+        # ``q.sample`` (no rsample) draws with torch.normal(loc, scale); the flow's base is N(0, 1), so the draw IS z
+        if len(torch.Size(sample_shape)) == 0:  # the throw-away draw of every model(x) (utils/distributions.py:457)
+            return orig_sample(self, sample_shape)
+        shape = self._extended_shape(sample_shape)
+        z = queue.pop(0)
+        assert tuple(z.shape) == tuple(shape), (z.shape, shape)
+        with torch.no_grad():
+            return self.loc.expand(shape) + self.scale.expand(shape) * z.to(self.loc)
+
     tn._standard_normal = fake
+    Normal.sample = fake_sample
     try:
         yield queue
     finally:
         tn._standard_normal = orig
+        Normal.sample = orig_sample
 
 
 @contextlib.contextmanager
@@ -67,11 +81,23 @@ def recorded_base_noise(record: List[Tensor]):
         record.append(z.detach().clone())
         return z
 
+    orig_sample = Normal.sample
+
+    def rec_sample(self, sample_shape=torch.Size()):
+        out = orig_sample(self, sample_shape)
+        if len(torch.Size(sample_shape)) == 0:
+            return out
+        assert bool((self.loc == 0).all()) and bool((self.scale == 1).all()), "only a standard-normal base is recorded"
+        record.append(out.detach().clone())
+        return out
+
     tn._standard_normal = rec
+    Normal.sample = rec_sample
     try:
         yield record
     finally:
         tn._standard_normal = orig
+        Normal.sample = orig_sample
 
 
 # ----------------------------------------------------------------------------- model
@@ -333,3 +359,96 @@ def trades_rkl_regularizer(model, x, beta, eps, eps_iter, nb_iter, mc_samples=1,
     x_pert = l2pgd_perturb(model, x, ReverseKLLoss(mc_samples=mc_samples), eps, nb_iter, eps_iter,
                            clip_min, clip_max, delta0=delta0)
     return beta * ReverseKLLoss(mc_samples=mc_samples)(model(x), model(x_pert)), x_pert
+
+
+# ============================================================================= SURVEY 8f "next" rows
+def rob_metric_eval(model, x, loss_fn, perturb_fn, attack_attemps=5, descending=True, targeted=False):
+    """rbibm/rbibm/metric/base.py:225-300 (``RobustnessMetric._eval``) for the untargeted KL metrics of
+    robustness_metric.py:54-155: per attempt x~ = perturb_fn(i); loss = loss_fn(q(.|x~), q(.|x)) (reduction None);
+    overflow guard; keep per row the best attempt.  ``loss_fn`` is a Reverse/ForwardKLLoss with reduction None."""
+    losses = xs_tilde = None
+    for i in range(attack_attemps):
+        x_tilde = perturb_fn(i)
+        with torch.no_grad():
+            q_tilde = model(x_tilde)
+            q = model(x)
+            loss = loss_fn(q_tilde, q)
+            mask_neg = loss < -10000
+            loss[mask_neg] = loss[~mask_neg].median()
+        if i == 0:
+            xs_tilde, losses = x_tilde.detach(), loss.detach()
+        else:
+            if descending:
+                better = loss > losses if not targeted else loss < losses
+            else:
+                better = loss < losses if not targeted else loss > losses
+            xs_tilde[better] = x_tilde[better].detach()
+            losses[better] = loss[better].detach()
+    return losses, xs_tilde
+
+
+def nll_metric(model, x, theta):
+    """rbibm/rbibm/metric/approximation_metric.py:205-232: -log q(theta|x) per row under no_grad."""
+    with torch.no_grad():
+        return nll(model, x, theta)
+
+
+def expected_coverage(model, x, theta, mc_samples, alphas):
+    """rbibm/rbibm/metric/approximation_metric.py:300-324: one [alphas] vector for one batch."""
+    q = model(x)
+    logq_theta = q.log_prob(theta)
+    samples = q.sample((mc_samples,))
+    logq_samples = q.log_prob(samples)
+    out = []
+    for a in alphas:
+        if float(a) == 0:
+            out.append(torch.zeros(1).mean())
+        elif float(a) == 1:
+            out.append(torch.ones(1).mean())
+        else:
+            cut_off = int(mc_samples * (1 - a))
+            srt, _ = torch.sort(logq_samples, dim=0)
+            out.append((srt[cut_off:].min(0).values < logq_theta).float().mean())
+    return torch.stack(out)
+
+
+def coverage_abs_auc(cov, alphas):
+    """approximation_metric.py:281-291 (the branch every reduction takes): area of |coverage - alpha|."""
+    while cov.ndim > 1:
+        cov = cov.mean(0)
+    return torch.trapz(torch.abs(cov - alphas), alphas)
+
+
+def sample_l2_uniformly(N, d, eps):
+    """rbi/rbi/utils/distributions.py:22-40 with p = 2 (draw order: Gamma, sign uniforms, radius uniforms)."""
+    c = 2.0 * torch.ones(d)  # a tensor exponent on purpose: pow(t, tensor) and pow(t, 0.5) (= sqrt) differ by an ulp
+    xi = torch.distributions.Gamma(1 / 2.0 * torch.ones(d), 1.0).sample((N,)) ** (1 / c)
+    signs = (torch.rand((N, d)) - 0.5).sign()
+    v = xi * signs
+    z = torch.rand(N, 1) ** (1 / d)
+    return eps * z * (v / torch.linalg.norm(v, keepdim=True, ord=2.0, dim=-1))
+
+
+def l2_uniform_noise_perturb(x, eps, clip_min=-1000.0, clip_max=1000.0, noise=None):
+    """rbi/rbi/attacks/noise_attacks.py:30-35."""
+    if noise is None:
+        noise = sample_l2_uniformly(x.shape[0], x.shape[-1], eps)
+    return torch.clip(x + noise, min=clip_min, max=clip_max)
+
+
+def train_loss_with_pre_regularizer(model, x, theta, transform):
+    """rbi/rbi/loss/base.py:156-163 with ONE pre-loss regulariser (defenses/adversarial_training.py:34-50): the NLL is
+    evaluated at (x', theta') = transform(x, theta)."""
+    x2, theta2 = transform(x, theta)
+    q = model(x2)
+    loss = -q.log_prob(theta2.reshape(*(q.batch_shape + q.event_shape)))
+    post = torch.zeros(1)
+    return torch.mean(loss) + (post - post.detach()), x2
+
+
+def trades_regularizer(model, x, beta, eps, eps_iter, nb_iter, loss_cls, mc_samples=1, delta0=None,
+                       clip_min=-1000.0, clip_max=1000.0):
+    """rbi/rbi/defenses/trades_regularizers.py:58-99 for a KL loss class (ForwardKLLoss: ``L2PGDTrades``)."""
+    x_pert = l2pgd_perturb(model, x, loss_cls(mc_samples=mc_samples), eps, nb_iter, eps_iter, clip_min, clip_max,
+                           delta0=delta0)
+    return beta * loss_cls(mc_samples=mc_samples)(model(x), model(x_pert)), x_pert

@@ -136,3 +136,22 @@ def install(reference_src: str = REFERENCE_SRC):
     if reference_src not in sys.path:
         sys.path.insert(0, reference_src)
     install._done = True
+
+
+REFERENCE_RBIBM_SRC = "/root/reference/src/rbibm"
+
+
+def install_rbibm(reference_src: str = REFERENCE_RBIBM_SRC):
+    """Additionally make the reference's ``rbibm.metric`` modules importable (metric base classes, robustness and
+    approximation metrics).  ``rbibm.tasks`` (simulators; pulls in MCMC code that imports ``turtle``/tkinter by accident)
+    and ``rbibm.utils`` helpers outside batched processing are not needed by the metrics and become placeholders."""
+    install()
+    if getattr(install_rbibm, "_done", False):
+        return
+    _module("turtle")
+    if reference_src not in sys.path:
+        sys.path.insert(0, reference_src)
+    import rbibm  # the real (empty-ish) package __init__
+    _module("rbibm.tasks")
+    _module("rbibm.tasks.base")
+    install_rbibm._done = True

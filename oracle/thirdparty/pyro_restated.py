@@ -366,6 +366,11 @@ class Permute(Transform):
     def _inverse(self, y):
         return y.index_select(self.dim, self.inv_permutation)
 
+    def clear_cache(self):
+        # pyro/distributions/torch_patch.py patches ``Transform.clear_cache`` onto every torch transform
+        if self._cache_size == 1:
+            self._cached_x_y = None, None
+
     def log_abs_det_jacobian(self, x, y):
         return torch.zeros(x.size()[: -(-self.dim)], dtype=x.dtype, layout=x.layout, device=x.device)
 

@@ -1,5 +1,6 @@
 """L2-PGD attack on the amortized posterior, mirroring ``rbi.attacks.L2PGDAttack``
-(hydra: ``attack_module: rabi_b200.attacks``, ``attack_class: L2PGDAttack``).
+(hydra: ``attack_module: rabi_b200.attacks``, ``attack_class: L2PGDAttack``), plus the random-noise "attacks"
+(rbi/rbi/attacks/noise_attacks.py:12-69) that the noise-augmentation defenses and the l2noise baseline use.
 
 Reference behaviour reproduced (rbi/rbi/attacks/base.py:9-84, attacks/advertorch_attack.py:23-42 and advertorch's
 ``PGDAttack.perturb`` / ``perturb_iterative(ord=2)`` / ``rand_init_delta``):
@@ -148,3 +149,59 @@ class L2PGDAttack(Attack):
     def _run(self, eng, x, delta, zs, y, z_all, inv_B):
         return eng.pgd_run(x, delta, zs[0], zs[1], y.A, z_all, self.eps, self.eps_iter, self.clip_min, self.clip_max,
                            inv_B, forward_kl=type(self.loss_fn) is ForwardKLLoss)
+
+
+# ---- random perturbations (no model evaluation; elementwise host-side torch) --------------------------------------------
+def sample_lp_uniformly(N: int, d: int, p=2.0, eps=0.5, device="cuda") -> Tensor:
+    """N points uniform in the d-dimensional l_p ball of radius eps (rbi/rbi/utils/distributions.py:22-43): direction
+    from i.i.d. generalised-Gamma(1/p, p) magnitudes with random signs, normalised in l_p; radius eps * U^(1/d)."""
+    if p in ("inf", float("inf")):
+        return torch.rand(N, d, device=device) * eps * 2 - eps
+    if not isinstance(p, (int, float)):
+        raise ValueError("Unknown order...")
+    conc = torch.full((d,), 1.0 / p, device=device)
+    mag = torch.distributions.Gamma(conc, 1.0).sample((N,)) ** (1.0 / p)
+    direction = mag * (torch.rand((N, d), device=device) - 0.5).sign()
+    radius = torch.rand(N, 1, device=device) ** (1.0 / d)
+    return eps * radius * (direction / torch.linalg.norm(direction, keepdim=True, ord=p, dim=-1))
+
+
+class UniformNoiseAttack(Attack):
+    """x + noise, noise uniform in the l_p eps-ball, clipped to the box."""
+
+    def __init__(self, predict: Callable, eps: float = 0.5, ord=2.0, **kwargs) -> None:
+        super().__init__(predict, **kwargs)
+        self.eps = eps
+        self.ord = ord
+
+    def perturb(self, x: Tensor, *args, **kwargs) -> Tensor:
+        with torch.no_grad():
+            noise_ = sample_lp_uniformly(x.shape[0], x.shape[-1], p=self.ord, eps=self.eps, device=x.device)
+            return torch.clip(x + noise_, min=self.clip_min, max=self.clip_max)
+
+
+class L2UniformNoiseAttack(UniformNoiseAttack):
+    def __init__(self, predict, eps=0.5, **kwargs) -> None:
+        super().__init__(predict, eps, ord=2.0, **kwargs)
+
+
+class L1UniformNoiseAttack(UniformNoiseAttack):
+    def __init__(self, predict, eps=0.5, **kwargs) -> None:
+        super().__init__(predict, eps, ord=1.0, **kwargs)
+
+
+class LinfUniformNoiseAttack(UniformNoiseAttack):
+    def __init__(self, predict, eps=0.5, **kwargs) -> None:
+        super().__init__(predict, eps, ord="inf", **kwargs)
+
+
+class GaussianNoiseAttack(Attack):
+    def __init__(self, predict, eps=0.5, **kwargs) -> None:
+        super().__init__(predict, **kwargs)
+        self.eps = eps
+        if self.targeted:
+            raise ValueError("This attack cannot be targeted")
+
+    def perturb(self, x, **kwargs):
+        with torch.no_grad():
+            return torch.clip(x + torch.randn_like(x) * self.eps, min=self.clip_min, max=self.clip_max)

@@ -2,8 +2,11 @@
 
 * ``AdditiveRegularizer``            rbi/rbi/defenses/base.py:38-128   (post-loss regulariser registry on TrainLoss)
 * ``FIMTraceRegularizer``            rbi/rbi/defenses/fisher_regularization.py:15-95   (config/defense/fisher_trace.yaml)
-* ``TradesAdversarialRegularizer`` / ``L2PGDrKLTrades``   rbi/rbi/defenses/trades_regularizers.py:26-64,101-133
-                                                          (config/defense/l2pgdTrades_rKL.yaml)
+* ``TradesAdversarialRegularizer`` / ``L2PGDrKLTrades`` / ``L2PGDTrades`` (fKL)
+                                     rbi/rbi/defenses/trades_regularizers.py:26-133   (config/defense/l2pgdTrades_rKL.yaml)
+* ``DataAugmentationRegularizer``    rbi/rbi/defenses/base.py:131-176   (pre-loss seam of TrainLoss)
+* ``AdversarialTraining`` / ``L2PGDAdversarialTraining`` / ``L2UniformNoiseTraining``
+                                     rbi/rbi/defenses/adversarial_training.py:21-135   (config/defense/l2pgdAdvTraining.yaml)
 The inner L2-PGD of TRADES runs on the fused attack kernels; the regulariser values and their (first/second order)
 weight gradients run through rabi_b200/autograd.py.
 """
@@ -16,9 +19,9 @@ from torch import Tensor
 from torch.distributions import Distribution
 from torch.nn import Module
 
-from .attacks import Attack, L2PGDAttack
+from .attacks import Attack, L2PGDAttack, L2UniformNoiseAttack
 from .fisher import ExponentialMovingAverageEstimator, monte_carlo_fisher
-from .loss import EvalLoss, ReverseKLLoss, TrainLoss
+from .loss import EvalLoss, ForwardKLLoss, ReverseKLLoss, TrainLoss
 
 
 class Defense:
@@ -224,9 +227,72 @@ class L2PGDrKLTrades(TradesAdversarialRegularizer):
         if attack_loss_fn is None:
             attack_loss_fn = ReverseKLLoss(mc_samples=1)
         if reg_loss_fn is None:
-            if hasattr(attack_loss_fn, "mc_samples"):
-                reg_loss_fn = attack_loss_fn.__class__(mc_samples=int(attack_loss_fn.mc_samples))
-            else:
-                reg_loss_fn = attack_loss_fn.__class__()
+            reg_loss_fn = _default_reg_loss(attack_loss_fn)
         attack = L2PGDAttack(model, attack_loss_fn, eps=eps, **kwargs)
         super().__init__(model, loss_fn, attack, reg_loss_fn, beta, reduce, **kwargs)
+
+
+def _default_reg_loss(attack_loss_fn):
+    if hasattr(attack_loss_fn, "mc_samples"):
+        return attack_loss_fn.__class__(mc_samples=int(attack_loss_fn.mc_samples))
+    return attack_loss_fn.__class__()
+
+
+class L2PGDTrades(TradesAdversarialRegularizer):
+    """TRADES with the forward KL (samples from the clean posterior) as attack and regulariser loss."""
+
+    def __init__(self, model: Module, loss_fn: TrainLoss, attack_loss_fn: Optional[EvalLoss] = None,
+                 reg_loss_fn: Optional[EvalLoss] = None, eps: float = 0.5, beta: float = 1.0, reduce: str = "mean",
+                 **kwargs):
+        if attack_loss_fn is None:
+            attack_loss_fn = ForwardKLLoss(mc_samples=1)
+        if reg_loss_fn is None:
+            reg_loss_fn = _default_reg_loss(attack_loss_fn)
+        attack = L2PGDAttack(model, attack_loss_fn, eps=eps, **kwargs)
+        super().__init__(model, loss_fn, attack, reg_loss_fn, beta, reduce, **kwargs)
+
+
+# ---- defenses that change the data BEFORE the loss ------------------------------------------------------------------------
+class DataAugmentationRegularizer(Defense):
+    """(x, theta) -> (x', theta') through ``TrainLoss.register_pre_loss_regularizer``."""
+
+    @property
+    def regularizer(self) -> Callable:
+        return self._transform
+
+    def _transform(self, input: Tensor, target):
+        raise NotImplementedError("Transfrom not implemented")
+
+    def activate(self):
+        self.loss_fn.register_pre_loss_regularizer(self.__class__.__name__, self.regularizer)
+
+    def deactivate(self):
+        self.loss_fn.remove_pre_loss_regularizer(self.__class__.__name__)
+
+
+class AdversarialTraining(DataAugmentationRegularizer):
+    """The training loss is evaluated on attack(x) instead of x."""
+
+    def __init__(self, model: Module, loss_fn: TrainLoss, attack: Attack, **kwargs):
+        super().__init__(model, loss_fn, **kwargs)
+        self.attack = attack
+
+    def _transform(self, input: Tensor, target):
+        if not self.attack.targeted:
+            x_tilde = self.attack.perturb(input)
+        else:
+            x_tilde = self.attack.perturb(input, target)
+        return x_tilde.detach(), target
+
+
+class L2PGDAdversarialTraining(AdversarialTraining):
+    def __init__(self, model: Module, loss_fn: TrainLoss, attack_loss_fn: Optional[Callable] = None,
+                 eps: float = 0.5, **kwargs):
+        if attack_loss_fn is None:
+            attack_loss_fn = ForwardKLLoss(mc_samples=1)
+        super().__init__(model, loss_fn, L2PGDAttack(model, attack_loss_fn, eps=eps, **kwargs))
+
+
+class L2UniformNoiseTraining(AdversarialTraining):
+    def __init__(self, model: Module, loss_fn: TrainLoss, eps: float = 0.5, **kwargs):
+        super().__init__(model, loss_fn, L2UniformNoiseAttack(model, eps=eps, **kwargs))

@@ -1,9 +1,13 @@
-"""Robustness metric of the hot path, mirroring ``rbibm.metric.robustness_metric.ReverseKLRobMetric``
-(rbibm/rbibm/metric/base.py:84-170,225-346 and metric/robustness_metric.py:54-99).
+"""Metrics of the hot path, mirroring ``rbibm.metric`` (hydra: ``metric_module: rabi_b200.metric``).
 
-For every observation row: x~ = attack.perturb(x); loss = KL(q(.|x~) || q(.|x)) with ``mc_samples`` MC samples
-(``eval_mc_budget``, 256 in config/eval_rob/metric/rKL.yaml); losses below -1e4 are replaced by the median; the best
-of ``attack_attemps`` is kept; the summary is mean + quantiles over the finite values.
+* ``Metric`` / ``summary_reduce``                 rbibm/rbibm/metric/base.py:27-170
+* ``RobustnessMetric``                            rbibm/rbibm/metric/base.py:173-355
+* ``ReverseKLRobMetric`` / ``ForwardKLRobMetric`` rbibm/rbibm/metric/robustness_metric.py:54-155
+* ``NegativeLogLikelihoodMetric`` / ``ExpectedCoverageMetric``   rbibm/rbibm/metric/approximation_metric.py:205-324
+
+Robustness metrics, for every observation row: x~ = attack.perturb(x); loss = D(q(.|x~), q(.|x)) with ``mc_samples`` MC
+samples (``eval_mc_budget``, 256 in config/eval_rob/metric/rKL.yaml); losses below -1e4 are replaced by the median; the
+best of ``attack_attemps`` is kept; the summary is mean + quantiles over the finite values.
 
 B200-first difference in *scheduling only*: the reference walks the data in ``batch_size`` chunks to bound memory
 (rbibm/utils/batched_processing.py:5-15).  Rows are independent except for the 1/batch factor in the attack
@@ -12,13 +16,13 @@ gradient, so here all rows of a shard go through ONE call with that 
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Optional, Tuple, Union
+from typing import Any, Callable, Optional, Tuple
 
 import torch
 from torch import Tensor
 
 from .attacks import Attack, L2PGDAttack
-from .loss import ReverseKLLoss
+from .loss import EvalLoss, ForwardKLLoss, NegativeLogLikelihoodLoss, ReverseKLLoss
 
 
 def summary_reduce(m: Tensor, reduction: Optional[str]):
@@ -53,40 +57,85 @@ def summary_reduce(m: Tensor, reduction: Optional[str]):
     return out if supp is None else (out, supp)
 
 
-class ReverseKLRobMetric:
-    def __init__(self, model, attack: Attack, targeted: bool = False, target_wrapper: Callable = lambda x: x,
-                 attack_attemps: int = 5, device: str = "cuda", mask: Optional[Tensor] = None,
-                 reduction: Optional[str] = "mean_quantile95", batch_size: Optional[int] = None,
-                 descending: bool = True, **kwargs):
-        if mask is not None:
-            raise NotImplementedError("masked-feature attacks are outside the maf_pyro / l2pgd / rKL path")
+class Metric:
+    """Common surface of every metric: ``eval(x, other)`` -> reduced value (metric/base.py:27-170)."""
+
+    def __init__(self, model, reduction: Optional[str] = None, batch_size: Optional[int] = None,
+                 descending: bool = False, device: str = "cuda") -> None:
         self.model = model
-        self.attack = attack
-        self.loss_fn = ReverseKLLoss(**kwargs)  # kwargs carries mc_samples (run_rob_eval.py:178-189)
-        self.targeted = targeted
-        self.target_wrapper = target_wrapper
-        self.attack_attemps = attack_attemps
-        self.device = device
-        self.reduction = reduction
         self.batch_size = batch_size
         self.descending = descending
+        self.device = device
+        self._reduction = reduction  # not validated at construction (metric/base.py:47), only by the setter
+
+    @property
+    def reduction(self):
+        return self._reduction
+
+    @reduction.setter
+    def reduction(self, x: Optional[str]) -> None:
+        self._set_reduction(x)
+
+    def _set_reduction(self, x: Optional[str]) -> None:
+        if x is None:
+            self._reduction = None
+            return
+        if not isinstance(x, str):
+            raise ValueError("Unknown reduction type")
+        parts = x.split("_")
+        main_ok = parts[0] in ("mean", "median", "sum", "max", "min")
+        supp_ok = parts[1] in ("std", "q95", "summary") if len(parts) > 1 else True
+        if not (main_ok and supp_ok):
+            raise ValueError("Unknown reduction type")
+        self._reduction = x
+
+    def _reduce(self, m: Tensor):
+        return summary_reduce(m, self.reduction)
+
+    def _eval(self, x, other=None) -> Tensor:
+        raise NotImplementedError
+
+    def eval(self, x: Tensor, other: Any = None):
+        if x.ndim == 1:
+            x = x.unsqueeze(0)
+        x = x.to(self.device)
+        if other is not None and hasattr(other, "to"):
+            other = other.to(self.device)
+        return self._reduce(self._eval(x, other))
+
+
+class RobustnessMetric(Metric):
+    """max_d D(q(x + d), q(x))  (or min_d D(q(x + d), t) for a target t)."""
+
+    def __init__(self, model, loss_fn: EvalLoss, attack: Attack, attack_attemps: int = 5, targeted: bool = False,
+                 target_wrapper: Callable = lambda x: x, mask: Optional[Tensor] = None, descending: bool = True,
+                 batch_size: Optional[int] = None, reduction: Optional[str] = None, device: str = "cuda"):
+        if mask is not None:
+            raise NotImplementedError("masked-feature attacks are outside the maf_pyro / l2pgd / KL path")
+        super().__init__(model, reduction=reduction, batch_size=batch_size, descending=descending, device=device)
+        self.loss_fn = loss_fn
+        self.loss_fn.reduction = None
+        self.attack_attemps = attack_attemps
+        self.targeted = targeted
+        self.target_wrapper = target_wrapper
+        self.attack = attack
+        self.mask = mask
         self._cached_x = None
         self._cached_xs_tilde = None
         self._cached_losses = None
 
-    # robustness_metric.py:93-99
+    def _get_goal(self, x, target):
+        raise NotImplementedError
+
     @staticmethod
     def _ensure_loss_constraint(loss: Tensor) -> Tensor:
-        mask_neg = loss < -10000
-        if mask_neg.any():
-            loss[mask_neg] = loss[~mask_neg].median()
         return loss
 
     def _eval(self, x: Tensor, target: Optional[Any] = None) -> Tensor:
         target = self.target_wrapper(target)
         losses = None
         xs_tilde = None
-        # chunk_size: the reference attacks `batch_size` rows at a time; ReverseKLLoss(reduction="mean") then puts a
+        # chunk_size: the reference attacks `batch_size` rows at a time; a loss with reduction="mean" then puts a
         # 1/batch_size factor in front of every row's gradient before advertorch's 1e-6 norm floor.
         chunk = self.batch_size if (self.batch_size is not None and self.batch_size < x.shape[0]) else None
         for i in range(self.attack_attemps):
@@ -97,8 +146,8 @@ class ReverseKLRobMetric:
                 x_tilde = self.attack.perturb(x, target, **kw)
             with torch.no_grad():
                 q_tilde = self.model(x_tilde)
-                q = target if self.targeted else self.model(x)
-                loss = ReverseKLLoss(mc_samples=self.loss_fn.mc_samples, reduction=None)(q_tilde, q)
+                q = self._get_goal(x, target)
+                loss = self.loss_fn(q_tilde, q)
                 loss = self._ensure_loss_constraint(loss)
             if i == 0:
                 xs_tilde, losses = x_tilde.detach(), loss.detach()
@@ -111,15 +160,6 @@ class ReverseKLRobMetric:
         self._cached_losses = losses if self._cached_losses is None else torch.cat([self._cached_losses, losses])
         return losses
 
-    def eval(self, x: Tensor, other: Any = None):
-        if x.ndim == 1:
-            x = x.unsqueeze(0)
-        x = x.to(self.device)
-        if other is not None and hasattr(other, "to"):
-            other = other.to(self.device)
-        out = self._eval(x, other)
-        return summary_reduce(out, self.reduction)
-
     def generate_adversarial_examples(self, x: Tensor, target: Optional[Any] = None,
                                       num_examples: int = 100) -> Tuple[Tensor, Tensor]:
         if self._cached_x is None or self._cached_x.shape != x.shape or \
@@ -130,3 +170,153 @@ class ReverseKLRobMetric:
         _, idx = torch.sort(self._cached_losses.flatten(), descending=order_val)
         idx = idx[torch.isfinite(self._cached_losses.flatten()[idx])]
         return idx[:num_examples], self._cached_xs_tilde[idx][:num_examples]
+
+
+def _median_for_overflow(loss: Tensor) -> Tensor:
+    # robustness_metric.py:93-99 / 148-153: overflowed (very negative) MC estimates are replaced by the median
+    mask_neg = loss < -10000
+    if mask_neg.any():
+        loss[mask_neg] = loss[~mask_neg].median()
+    return loss
+
+
+class ReverseKLRobMetric(RobustnessMetric):
+    """D_KL(q(.|x~) || q(.|x)), samples from the perturbed posterior (config/eval_rob/metric/rKL.yaml)."""
+
+    def __init__(self, model, attack: Attack, targeted: bool = False, target_wrapper: Callable = lambda x: x,
+                 attack_attemps: int = 5, device: str = "cuda", mask: Optional[Tensor] = None,
+                 reduction: Optional[str] = "mean_quantile95", batch_size: Optional[int] = None,
+                 descending: bool = True, **kwargs):
+        super().__init__(model, loss_fn=ReverseKLLoss(**kwargs), attack=attack, attack_attemps=attack_attemps,
+                         targeted=targeted, target_wrapper=target_wrapper, device=device, mask=mask,
+                         batch_size=batch_size, reduction=reduction, descending=descending)
+
+    def _get_goal(self, x, target):
+        if self.targeted:
+            return target
+        with torch.no_grad():
+            return self.model(x)
+
+    _ensure_loss_constraint = staticmethod(_median_for_overflow)
+
+
+class ForwardKLRobMetric(RobustnessMetric):
+    """D_KL(q(.|x) || q(.|x~)), samples from the clean posterior (config/eval_rob/metric/fKL.yaml)."""
+
+    def __init__(self, model, attack: Attack, targeted: bool = False, target_wrapper: Callable = lambda x: x,
+                 attack_attemps: int = 5, device: str = "cuda", mask: Optional[Tensor] = None,
+                 reduction: Optional[str] = "mean_quantile95", batch_size: Optional[int] = None,
+                 descending: bool = True, empirical_approx: bool = False, empirical_mc_samples=20, **kwargs):
+        if empirical_approx:
+            raise NotImplementedError("empirical_approx (EmpiricalDistribution targets) is outside the maf_pyro path")
+        self.empirical_approx = empirical_approx
+        self.empirical_mc_samples = empirical_mc_samples
+        super().__init__(model, loss_fn=ForwardKLLoss(**kwargs), attack=attack, attack_attemps=attack_attemps,
+                         targeted=targeted, target_wrapper=target_wrapper, device=device, mask=mask,
+                         batch_size=batch_size, reduction=reduction, descending=descending)
+
+    def _get_goal(self, x, target):
+        if self.targeted or self.attack.targeted:
+            return target
+        with torch.no_grad():
+            return self.model(x)
+
+    _ensure_loss_constraint = staticmethod(_median_for_overflow)
+
+
+# ---- approximation metrics on clean / adversarial x (rbibm_script.py:232-257) -----------------------------------------
+class ApproximationMetric(Metric):
+    requires_posterior = False
+    requires_thetas = False
+    requires_potential = False
+    can_eval_single = True
+    can_eval_x_xtilde = False
+
+    def __init__(self, model, prior=None, simulator=None, ground_truth=None, potential_fn=None,
+                 reduction: Optional[str] = "mean", batch_size: Optional[int] = None, descending: bool = False,
+                 device: str = "cuda") -> None:
+        super().__init__(model, reduction=reduction, batch_size=batch_size, descending=descending, device=device)
+        self.prior = prior
+        self.simulator = simulator
+        self.ground_truth = ground_truth
+        self.potential_fn = potential_fn
+
+
+class NegativeLogLikelihoodMetric(ApproximationMetric):
+    """-log q(theta | x) per row.  All rows go through one log-prob launch; the reference's ``batch_size`` walk only
+    bounds memory and does not change any row's value."""
+    requires_thetas = True
+
+    def __init__(self, model, reduction: Optional[str] = "mean", batch_size: Optional[int] = None,
+                 device: str = "cuda", **kwargs) -> None:
+        self.loss_fn = NegativeLogLikelihoodLoss(reduction=None)
+        super().__init__(model, reduction=reduction, batch_size=batch_size, device=device)
+
+    def _eval(self, xs: Tensor, target: Optional[Tensor]) -> Tensor:
+        with torch.no_grad():
+            return self.loss_fn(self.model(xs), target)
+
+
+class ExpectedCoverageMetric(ApproximationMetric):
+    """Expected coverage of the highest-density regions: for every level alpha the fraction of rows whose true theta has
+    a higher log q than the (1-alpha)-quantile of ``mc_samples`` posterior samples' log q.  Per ``batch_size`` chunk one
+    [alphas] vector (the chunk mean), then the mean over chunks -- the reference's ``vstack`` + ``mean(0)``
+    (approximation_metric.py:275-324, batched_processing.py:5-15).  Sampling and log q of the samples are one fused
+    launch (the "free" log-prob of a fresh sample)."""
+    requires_thetas = True
+    can_eval_single = False
+
+    def __init__(self, model, mc_samples: int = 100, alphas: Tensor = None, device: str = "cuda",
+                 batch_size: int = 1000, reduction: Optional[str] = "absAUC", **kwargs):
+        super().__init__(model=model, device=device, batch_size=batch_size, reduction=reduction)
+        self.mc_samples = mc_samples
+        self.alphas = (torch.linspace(0, 1, 100) if alphas is None else alphas).to(device)
+
+    def _set_reduction(self, x):
+        if x not in ("AUC", "absAUC", "AUC_full", "absAUC_full", None):
+            raise ValueError("Unknown reduction type")
+        self._reduction = x
+
+    def _reduce(self, m: Tensor):
+        # The reference's branch test (`== "absAUC" or "absAUC_full"`) is always true: every reduction, None included,
+        # takes the |coverage - alpha| area branch (approximation_metric.py:281-291).  Reproduced.
+        while m.ndim > 1:
+            m = m.mean(0)
+        val = torch.trapz(torch.abs(m - self.alphas), self.alphas)
+        if self._reduction == "absAUC":
+            return val
+        return val, {"alphas": self.alphas.cpu(), "quantiles": m.cpu()}
+
+    def eval(self, x: Tensor, other: Any = None):
+        x = x.to(self.device)
+        other = other.to(self.device)
+        if self.batch_size is not None and self.batch_size < x.shape[0]:
+            out = torch.vstack([self._eval(xb, tb) for xb, tb in
+                                zip(torch.split(x, self.batch_size), torch.split(other, self.batch_size))])
+        else:
+            out = self._eval(x, other)
+        return self._reduce(out)
+
+    def coverage_curve(self, logq_theta: Tensor, logq_samples: Tensor) -> Tensor:
+        """All levels at once: sorted sample log-densities [S, B]; the level-alpha threshold is row ``int(S*(1-alpha))``
+        of the sort (== ``sorted[cut:].min(0)``); alpha = 0 / 1 are defined as 0 / 1."""
+        S = logq_samples.shape[0]
+        srt, _ = torch.sort(logq_samples, dim=0)
+        out = []
+        for a in self.alphas.cpu():
+            if float(a) == 0:
+                out.append(torch.zeros((), device=logq_theta.device))
+            elif float(a) == 1:
+                out.append(torch.ones((), device=logq_theta.device))
+            else:
+                cut = int(self.mc_samples * (1 - a))  # fp32 tensor arithmetic, as in the reference (0.95*40 -> 38)
+                out.append((srt[min(cut, S - 1)] < logq_theta).float().mean())
+        return torch.stack(out)
+
+    def _eval(self, xs: Tensor, thetas: Tensor) -> Tensor:
+        with torch.no_grad():
+            q = self.model(xs)
+            logq_theta = q.log_prob(thetas)
+            samples = q.sample((self.mc_samples,))
+            logq_samples = q.log_prob(samples)
+            return self.coverage_curve(logq_theta, logq_samples)

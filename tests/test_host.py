@@ -179,3 +179,64 @@ def test_l2pgd_attack_defaults_follow_the_reference_overrides():
     d = rand_init_delta_l2(x, 0.3, -1.0, 1.5)
     assert float(d.norm(dim=1).max()) <= 0.3 * (1 + 1e-5) + float((x - x.clamp(-1.0, 1.5)).norm(dim=1).max())
     assert float((x + d).min()) >= -1.0 - 1e-6 and float((x + d).max()) <= 1.5 + 1e-6
+
+
+def test_coverage_curve_equals_the_reference_level_loop():
+    """``ExpectedCoverageMetric.coverage_curve`` (all levels from one sort) against the per-level restatement."""
+    from rabi_b200.metric import ExpectedCoverageMetric
+
+    torch.manual_seed(0)
+    S, B = 40, 17
+    alphas = torch.linspace(0, 1, 21)
+    met = ExpectedCoverageMetric(model=None, mc_samples=S, alphas=alphas, device="cpu")
+    logq_samples, logq_theta = torch.randn(S, B), torch.randn(B)
+    mine = met.coverage_curve(logq_theta, logq_samples)
+    srt, _ = torch.sort(logq_samples, dim=0)
+    for i, a in enumerate(alphas):
+        if float(a) in (0.0, 1.0):
+            assert float(mine[i]) == float(a)
+        else:
+            cut = int(S * (1 - a))
+            assert float(mine[i]) == float((srt[cut:].min(0).values < logq_theta).float().mean())
+    # a calibrated posterior has coverage(alpha) = alpha: here theta and the samples are exchangeable draws
+    cov = ExpectedCoverageMetric(None, mc_samples=200, alphas=alphas, device="cpu").coverage_curve(
+        torch.randn(4000), torch.randn(200, 4000))
+    assert float((cov - alphas).abs().max()) < 0.04
+    val, full = ExpectedCoverageMetric(None, mc_samples=S, alphas=alphas, device="cpu",
+                                       reduction="absAUC_full")._reduce(torch.stack([mine, mine]))
+    assert torch.isclose(val, torch.trapz((mine - alphas).abs(), alphas)) and set(full) == {"alphas", "quantiles"}
+    with pytest.raises(ValueError):
+        ExpectedCoverageMetric(None, device="cpu").reduction = "mean"
+
+
+def test_metric_reduction_setter_validates_like_the_reference():
+    from rabi_b200.metric import Metric
+
+    m = Metric(None, reduction="mean_quantile95", device="cpu")  # not validated at construction (rKL.yaml default)
+    assert m._reduce(torch.tensor([1.0, 3.0])) == 2.0
+    m.reduction = "median_summary"
+    with pytest.raises(ValueError):
+        m.reduction = "mean_foo"
+    with pytest.raises(ValueError):
+        m.reduction = "mode"
+
+
+def test_pre_and_post_loss_defenses_register_on_the_train_loss():
+    from rabi_b200.defenses import L2PGDAdversarialTraining, L2PGDTrades, L2UniformNoiseTraining
+    from rabi_b200.loss import ForwardKLLoss, NLLLoss
+
+    m = _model()
+    lf = NLLLoss(m)
+    adv = L2PGDAdversarialTraining(m, lf, eps=0.3, eps_iter=0.05, nb_iter=4)
+    assert type(adv.attack.loss_fn) is ForwardKLLoss and adv.attack.loss_fn.mc_samples == 1 and adv.attack.nb_iter == 4
+    noise_def = L2UniformNoiseTraining(m, lf, eps=0.2)
+    trades = L2PGDTrades(m, lf, eps=0.3, beta=0.1, nb_iter=2)
+    assert type(trades.reg_loss_fn) is ForwardKLLoss and trades.reg_loss_fn is not trades.attack.loss_fn
+    adv.activate(); noise_def.activate(); trades.activate()
+    assert set(lf.pre_loss_regularizers) == {"L2PGDAdversarialTraining", "L2UniformNoiseTraining"}
+    assert set(lf.post_loss_regularizers) == {"L2PGDTrades"}
+    adv.deactivate(); noise_def.deactivate(); trades.deactivate()
+    assert not lf.pre_loss_regularizers and not lf.post_loss_regularizers
+    x = torch.randn(64, 6)
+    xn = noise_def.attack.perturb(x)  # pure elementwise torch: runs anywhere
+    assert float((xn - x).norm(dim=-1).max()) <= 0.2 * (1 + 1e-5)

@@ -137,3 +137,75 @@ def test_ema_estimator_matches_reference_semantics():
     assert torch.allclose(e.value[0], 0.85 * a / (1 - 0.15))
     e([b])
     assert torch.allclose(e.value[0], (0.85 * b + 0.15 * 0.85 * a) / (1 - 0.15 ** 2))
+
+
+# ---- SURVEY 8f "next" rows: fixtures of oracle/gen_golden_next.py ------------------------------------------------------
+NEXT_CASES = ["tiny", "lotka_volterra", "tiny_shuffle"]
+
+
+@pytest.mark.parametrize("name", NEXT_CASES)
+def test_restatement_reproduces_next_row_fixtures(name):
+    g = load_golden(f"next_{name}")
+    m = build_oracle(g, with_output_transform=False)
+    x, p = g["x"], g["pgd"]
+    # f1: forward-KL attack and both robustness metrics (3 attempts, best-of)
+    with O.injected_base_noise(list(p["z_fkl_5"])):
+        xa = O.l2pgd_perturb(m, x, O.ForwardKLLoss(mc_samples=5), p["eps"], 5, p["eps_iter"], p["clip_min"],
+                             p["clip_max"], delta0=p["delta0"])
+    close(xa - x, p["x_adv_fkl_5"] - x, 1e-5)
+    for kind, loss_cls in (("fkl", O.ForwardKLLoss), ("rkl", O.ReverseKLLoss)):
+        r = g[f"rob_{kind}"]
+        noise = [z for i in range(r["attempts"]) for z in (list(r["z_attack"][i]) + [r["z_eval"][i]])]
+        with O.injected_base_noise(noise):
+            losses, xs = O.rob_metric_eval(
+                m, x, loss_cls(mc_samples=r["S_eval"], reduction=None),
+                lambda i: O.l2pgd_perturb(m, x, loss_cls(mc_samples=5), p["eps"], r["nb_iter"], p["eps_iter"],
+                                          p["clip_min"], p["clip_max"], delta0=r["delta0"][i]),
+                attack_attemps=r["attempts"])
+        close(losses, r["losses"], 1e-5)
+        close(xs - x, r["xs_tilde"] - x, 1e-5)
+    # f2: approximation metrics
+    close(O.nll_metric(m, x, g["theta"]), g["nll_metric"])
+    c = g["coverage"]
+    with torch.no_grad(), O.injected_base_noise(list(c["z"])):
+        curves = torch.vstack([O.expected_coverage(m, xb, tb, c["mc_samples"], c["alphas"]) for xb, tb in
+                               zip(torch.split(x, c["batch_size"]), torch.split(g["theta"], c["batch_size"]))])
+    close(curves.mean(0), c["curve"])
+    close(O.coverage_abs_auc(curves, c["alphas"]), c["abs_auc"])
+    # f3: pre-loss defenses and forward-KL TRADES
+    th = g["theta_train"]
+    a = g["adv_training"]
+    m.zero_grad()  # the attacks above left their weight-gradient pollution behind
+    with O.injected_base_noise(list(a["z"])):
+        loss, x_pert = O.train_loss_with_pre_regularizer(
+            m, x, th, lambda xi, ti: (O.l2pgd_perturb(m, xi, O.ForwardKLLoss(mc_samples=1), a["eps"], a["nb_iter"],
+                                                      a["eps_iter"], delta0=a["delta0"]).detach(), ti))
+        loss.backward()
+    close(loss.detach().reshape(()), a["loss"].reshape(()))
+    for prm, ref in zip(m.parameters(), a["grads_polluted"]):
+        close(prm.grad, ref, 1e-5)
+    m.zero_grad()
+    n = g["noise_training"]
+    assert float(n["noise"].norm(dim=-1).max()) <= n["eps"] * (1 + 1e-5)
+    loss, x_noisy = O.train_loss_with_pre_regularizer(
+        m, x, th, lambda xi, ti: (O.l2_uniform_noise_perturb(xi, n["eps"], n["clip_min"], n["clip_max"], n["noise"]), ti))
+    close(loss.detach().reshape(()), n["loss"].reshape(()))
+    close(x_noisy, n["x_noisy"])
+    t = g["trades_fkl"]
+    with O.injected_base_noise(list(t["z"])):
+        reg, xp = O.trades_regularizer(m, x, t["beta"], t["eps"], t["eps_iter"], t["nb_iter"], O.ForwardKLLoss, 1,
+                                       delta0=t["delta0"])
+    close(xp - x, t["x_pert"] - x, 1e-5)
+    close(reg.detach().reshape(()), t["reg_value"].reshape(()), 1e-5)
+
+
+def test_l2_ball_noise_is_uniform_in_the_ball():
+    """Known answer: for a uniform draw in the d-ball of radius eps, P(||n|| <= r) = (r/eps)^d."""
+    torch.manual_seed(0)
+    d, eps = 3, 0.7
+    n = O.sample_l2_uniformly(20000, d, eps).norm(dim=-1)
+    assert float(n.max()) <= eps * (1 + 1e-6)
+    for r in (0.3, 0.5, 0.6):
+        assert abs(float((n <= r).float().mean()) - (r / eps) ** d) < 0.015
+    v = O.sample_l2_uniformly(20000, d, eps)
+    assert float(v.mean(0).abs().max()) < 0.01
