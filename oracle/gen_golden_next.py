@@ -266,9 +266,42 @@ def build_case(name, cfg):
     return out
 
 
+def build_checkpoint_fixture():
+    """f4: a whole pickled reference model, exactly as ``save_model_by_id`` writes it (utils_data.py:688-705:
+    ``torch.save(model.to("cpu"), path)``), with every feature a converter has to carry over: Permute layers, the
+    z-score embedding of run_train.py:104-111 and a box output transform."""
+    import rbi.models as RM
+    from rbi.models.module import ZScoreLayer as RefZ
+    from torch.distributions import biject_to, constraints
+
+    dx, D, hidden = 8, 5, [24, 24]
+    g = torch.Generator().manual_seed(5)
+    low, high = -torch.ones(D) * 2.0, torch.ones(D) * 3.0
+    out_tf = biject_to(constraints.independent(constraints.interval(low, high), 1))
+    torch.manual_seed(77)
+    ref = RM.InverseAffineAutoregressiveModel(dx, D, hidden_dims=hidden, num_transforms=K, shuffle=True,
+                                              output_transform=out_tf, **KW)
+    _perturb_weights(ref, 3)
+    mean, std = 0.3 * torch.randn(dx, generator=g), 0.05 + 1.95 * torch.rand(dx, generator=g)
+    ref.embedding_net = torch.nn.Sequential(RefZ(mean=mean, std=std), ref.embedding_net)
+    ref.eval()
+    x = torch.randn(6, dx, generator=g) * std + mean
+    theta = low + (high - low) * torch.rand(3, 6, D, generator=g)
+    with torch.no_grad():
+        lp = ref(x).log_prob(theta)
+    path = os.path.join(ROOT, "tests", "golden", "ref_checkpoint.pkl")
+    torch.save(ref.to("cpu"), path)
+    state = {k: (v.bool() if k.endswith(".mask") else v.clone()) for k, v in ref.state_dict().items()}
+    torch.save(dict(x=x, theta=theta, log_prob=lp, state_dict=state, box_low=low, box_high=high,
+                    cfg=dict(dx=dx, D=D, hidden=hidden, K=K, shuffle=True, **KW)),
+               os.path.join(ROOT, "tests", "golden", "ref_checkpoint_expected.pt"))
+    print(f"ref_checkpoint: ok -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def main():
     install_stubs.install_rbibm()
     torch.set_num_threads(1)
+    build_checkpoint_fixture()
     for name in NEXT_CASES:
         out = build_case(name, CASES[name])
         path = os.path.join(ROOT, "tests", "golden", f"next_{name}.pt")

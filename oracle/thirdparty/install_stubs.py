@@ -66,6 +66,17 @@ def install(reference_src: str = REFERENCE_SRC):
     def move_all_tensor_to_device(obj, device):  # sbi helper: no-op on CPU
         return None
 
+    # pyro/distributions/torch_patch.py gives every torch Transform a ``clear_cache`` (PyroFlowModel.to calls it on the
+    # output transform as well)
+    if not hasattr(tt.Transform, "clear_cache"):
+        def _transform_clear_cache(self):
+            if getattr(self, "_cache_size", 0) == 1:
+                self._cached_x_y = None, None
+            for part in getattr(self, "parts", []) or ([self.base_transform] if hasattr(self, "base_transform") else []):
+                part.clear_cache()
+
+        tt.Transform.clear_cache = _transform_clear_cache
+
     # ---- pyro
     _module("pyro")
     _module(
