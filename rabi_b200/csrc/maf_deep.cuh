@@ -1,0 +1,693 @@
+// Deep / wide conditioners (3+ hidden layers or D > 12: config 5, pyloric: D = 31, hidden [200, 200, 200]) whose weights
+// and per-pair state do not fit on chip together.  Same arithmetic as maf_pairs.cuh (one thread owns one (row, sample)
+// pair; sampling costs one pass-equivalent; reverse mode for the input gradient only), different placement:
+//
+//  * per-pair state (activations / cotangents of every layer, chain vectors, ReLU bits) lives in a GLOBAL-memory
+//    scratch laid out [quad][pair][4] / [entry][pair], so that a warp touches consecutive addresses: the state is
+//    L2-resident (126 MB) instead of limiting occupancy through shared memory (the generic kernel keeps 5 kB per pair
+//    in shared memory => one warp per SM);
+//  * the weights a CTA needs next are staged in shared memory once per CTA and read as warp-broadcast 128-bit loads:
+//    a whole layer for the full (density) passes, the rows / column strips of one MADE degree group per step of the
+//    sequential (sampling) passes;
+//  * products are register-blocked over 16 (8) units x 4 inputs with packed fma.rn.f32x2 (dot_block / tdot_block of
+//    maf_fast.cuh on an ActBuf that points into the scratch);
+//  * every (transform, pass) is its own launch: 4K launches per attack iteration, state carried by the scratch.
+//
+// Reference arithmetic replaced: as maf_pairs.cuh (ConditionalAutoRegressiveNN._forward, AffineAutoregressive._call /
+// _inverse, TransformedDistribution.rsample / log_prob, general_kl_divergence and the autograd input gradient).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "maf_fast.cuh"
+#include "maf_image.h"
+#include "maf_pairs.cuh"
+
+namespace rabi {
+
+template <>
+struct ActBuf<2> {
+    float* p;   // &buf[0][pair][0]
+    size_t q;   // floats between consecutive quads of one pair (= 4 * padded pair count)
+    __device__ __forceinline__ float4 ld4(int i) const { return *reinterpret_cast<const float4*>(p + (size_t)(i >> 2) * q); }
+    __device__ __forceinline__ void st4(int i, float4 v) const { *reinterpret_cast<float4*>(p + (size_t)(i >> 2) * q) = v; }
+    __device__ __forceinline__ void st1(int i, float v) const { p[(size_t)(i >> 2) * q + (i & 3)] = v; }
+    __device__ __forceinline__ float ld1(int i) const { return p[(size_t)(i >> 2) * q + (i & 3)]; }
+    __device__ __forceinline__ static void wait_ld(float4&) {}
+    __device__ __forceinline__ static void wait_st() {}
+};
+
+
+// Register-blocked products on a scratch-resident vector.  Same arithmetic as dot_block / tdot_block (maf_fast.cuh), but
+// the activation quads are fetched in batches of PD with the next batch in flight while the current one is consumed:
+// the scratch is L2-resident, and one quad of look-ahead leaves the pass bound by L2 latency.
+//   out[c] = sum_{i<e4} W[min(c,cmax)*ld + i] * x[i]
+template <int NR>
+__device__ __forceinline__ void gdot_block(const float* __restrict__ W, int ld, int cmax, int e4, const ActBuf<2>& x,
+                                           float (&out)[NR]) {
+    constexpr int PD = 4;
+    float2 acc[NR];
+    const float* wr[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
+        acc[c] = make_float2(0.f, 0.f);
+        wr[c] = W + (size_t)min(c, cmax) * ld;
+    }
+    float4 cur[PD], nxt[PD];
+#pragma unroll
+    for (int q = 0; q < PD; ++q) {
+        cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        nxt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * q < e4) cur[q] = x.ld4(4 * q);
+    }
+    for (int i = 0; i < e4; i += 4 * PD) {
+#pragma unroll
+        for (int q = 0; q < PD; ++q)
+            if (i + 4 * (PD + q) < e4) nxt[q] = x.ld4(i + 4 * (PD + q));
+#pragma unroll
+        for (int q = 0; q < PD; ++q)
+            if (i + 4 * q < e4) {
+                const float4 h = cur[q];
+#pragma unroll
+                for (int c = 0; c < NR; ++c) {
+                    const float4 w = *reinterpret_cast<const float4*>(wr[c] + i + 4 * q);
+                    acc[c] = ffma2(make_float2(w.x, w.y), make_float2(h.x, h.y), acc[c]);
+                    acc[c] = ffma2(make_float2(w.z, w.w), make_float2(h.z, h.w), acc[c]);
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < PD; ++q) cur[q] = nxt[q];
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) out[c] = acc[c].x + acc[c].y;
+}
+//   out[c] = sum_{v in [va4, vb4)} W[v*ld + c] * x[v]      (NC columns, multiple of 4; W offset to the first column)
+template <int NC>
+__device__ __forceinline__ void gtdot_block(const float* __restrict__ W, int ld, int va4, int vb4, const ActBuf<2>& x,
+                                            float (&out)[NC]) {
+    constexpr int PD = 4;
+    float2 acc[NC / 2];
+#pragma unroll
+    for (int c = 0; c < NC / 2; ++c) acc[c] = make_float2(0.f, 0.f);
+    float4 cur[PD], nxt[PD];
+#pragma unroll
+    for (int q = 0; q < PD; ++q) {
+        cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        nxt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (va4 + 4 * q < vb4) cur[q] = x.ld4(va4 + 4 * q);
+    }
+    for (int v = va4; v < vb4; v += 4 * PD) {
+#pragma unroll
+        for (int q = 0; q < PD; ++q)
+            if (v + 4 * (PD + q) < vb4) nxt[q] = x.ld4(v + 4 * (PD + q));
+#pragma unroll
+        for (int q = 0; q < PD; ++q)
+            if (v + 4 * q < vb4) {
+                const float4 g4 = cur[q];
+                const float* wbase = W + (size_t)(v + 4 * q) * ld;
+#pragma unroll
+                for (int dv = 0; dv < 4; ++dv) {
+                    const float gv = dv == 0 ? g4.x : dv == 1 ? g4.y : dv == 2 ? g4.z : g4.w;
+                    const float2 gg = make_float2(gv, gv);
+#pragma unroll
+                    for (int cc = 0; cc < NC / 4; ++cc) {
+                        const float4 w = *reinterpret_cast<const float4*>(wbase + dv * ld + 4 * cc);
+                        acc[2 * cc] = ffma2(make_float2(w.x, w.y), gg, acc[2 * cc]);
+                        acc[2 * cc + 1] = ffma2(make_float2(w.z, w.w), gg, acc[2 * cc + 1]);
+                    }
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < PD; ++q) cur[q] = nxt[q];
+    }
+#pragma unroll
+    for (int c = 0; c < NC / 2; ++c) {
+        out[2 * c] = acc[c].x;
+        out[2 * c + 1] = acc[c].y;
+    }
+}
+
+enum DeepMode { DEEP_FWD = 0, DEEP_GRAD = 1 };
+
+struct DeepArgs {
+    const float* A_p;   // [K,H0,B]
+    const float* A_q;
+    const float* z;     // [S*B][D]
+    float* diff;        // [S*B] log p - log q (optional)
+    float* gA;          // [K,H0,B] += d loss / d A_p (atomics; caller zeroes)
+    int S, B;
+    long long p0;       // first pair of this batch
+    int n;              // pairs in this batch
+    int Np;             // padded pair count of the scratch (>= gridDim.x * blockDim.x)
+    float w;
+    float* act;         // [L][Hq][Np][4]
+    float* obuf;        // [Oq][Np][4]   (mbar_0.., sbar_0..) of the reverse passes
+    float* vec;         // [NV*D][Np]
+    uint32_t* bits;     // [2*K*L*WL][Np]
+    float* lp;          // [2][Np]  log p, log q
+    int Hq, Oq;
+    int record;         // store ReLU masks (GRAD)
+};
+
+__host__ __device__ inline int deep_nvec(int K) { return 4 * K + 4; }
+
+struct DeepThread {
+    int col;
+    bool live;
+    long long p;
+    int b;
+};
+
+__device__ __forceinline__ DeepThread deep_thread(const DeepArgs& a) {
+    DeepThread t;
+    t.col = blockIdx.x * blockDim.x + threadIdx.x;
+    t.live = t.col < a.n;
+    t.p = a.p0 + (t.live ? t.col : 0);
+    t.b = (int)(t.p % a.B);
+    return t;
+}
+
+#define DV(slot, j) a.vec[((size_t)(slot) * D + (j)) * a.Np + th.col]
+
+__device__ __forceinline__ ActBuf<2> deep_act(const DeepArgs& a, int l, int col) {
+    ActBuf<2> h;
+    h.p = a.act + ((size_t)l * a.Hq * a.Np + col) * 4;
+    h.q = (size_t)4 * a.Np;
+    return h;
+}
+__device__ __forceinline__ ActBuf<2> deep_obuf(const DeepArgs& a, int col) {
+    ActBuf<2> h;
+    h.p = a.obuf + (size_t)col * 4;
+    h.q = (size_t)4 * a.Np;
+    return h;
+}
+
+// contiguous global -> shared copy of n4 float4 (all threads of the CTA; callers bracket it with __syncthreads)
+__device__ __forceinline__ void deep_stage(float* dst, const float* __restrict__ src, int n4) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+    float4* d = reinterpret_cast<float4*>(dst);
+    const int T = blockDim.x;
+    for (int base = threadIdx.x; base < n4; base += 4 * T) {
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (base + q * T < n4) v[q] = __ldg(s + base + q * T);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (base + q * T < n4) d[base + q * T] = v[q];
+    }
+}
+// column strip: dst[r][0..gw) = src[(r0 + r) * ld + c0 .. c0 + gw)  for r < nr   (c0, gw multiples of 4)
+__device__ __forceinline__ void deep_stage_strip(float* dst, const float* __restrict__ src, int ld, int r0, int nr, int c0,
+                                                 int gw) {
+    const int q = gw >> 2;
+    for (int i = threadIdx.x; i < nr * q; i += blockDim.x) {
+        const int r = i / q, c4 = i - r * q;
+        reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * ld + c0) + c4);
+    }
+}
+
+struct BitAcc {  // ReLU masks of one layer, units arrive in increasing order
+    uint32_t w;
+    uint32_t* base;  // &bits[slot*WL][col]
+    size_t stride;   // Np
+    int H;
+    bool on;
+    __device__ __forceinline__ void put(int unit, bool relu_on) {
+        if (!on) return;
+        if (relu_on) w |= 1u << (unit & 31);
+        if ((unit & 31) == 31 || unit == H - 1) {
+            base[(size_t)(unit >> 5) * stride] = w;
+            w = 0u;
+        }
+    }
+};
+__device__ __forceinline__ uint32_t* deep_bits(const DeepArgs& a, const MafImg& g, int pass, int k, int l, int col) {
+    const int WL = (g.Hmax + 31) >> 5;
+    return a.bits + ((size_t)((pass * g.K + k) * g.L + l) * WL) * a.Np + col;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sampling pass of transform k under A_p: D steps; step j evaluates the units of MADE degree j of every layer.
+template <int DP>
+__global__ void __launch_bounds__(512, 1) kd_seq_fwd(const MafImg g, const DeepArgs a, const int k) {
+    extern __shared__ __align__(16) float sm[];
+    const DeepThread th = deep_thread(a);
+    const TImg& t = g.t[k];
+    const float* F = g.f;
+    const int* M = g.m;
+    const int K = g.K, D = g.D, L = g.L, H0 = g.H[0];
+    const int SV = 0, SHP = 2 * K + 1;
+    const float HALF_LOG_2PI = 0.91893853320467274178f;
+    float logp;
+    if (k == 0) {
+        float ssq = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float zv = th.live ? a.z[(size_t)th.p * D + d] : 0.f;
+            DV(SV, d) = zv;
+            ssq = fmaf(zv, zv, ssq);
+        }
+        logp = -0.5f * ssq - (float)D * HALF_LOG_2PI;
+    } else {
+        logp = a.lp[th.col];
+    }
+    float zos[DP], y[DP];
+#pragma unroll
+    for (int jj = 0; jj < DP; ++jj) {
+        zos[jj] = jj < D ? DV(SV + k, M[t.perm + jj]) : 0.f;
+        y[jj] = 0.f;
+    }
+    const float* Ap = a.A_p + (size_t)k * H0 * a.B + th.b;
+    ActBuf<2> h[RABI_MAXL];
+    BitAcc bacc[RABI_MAXL];
+    for (int l = 0; l < L; ++l) {
+        h[l] = deep_act(a, l, th.col);
+        bacc[l].w = 0u;
+        bacc[l].base = deep_bits(a, g, 0, k, l, th.col);
+        bacc[l].stride = (size_t)a.Np;
+        bacc[l].H = g.H[l];
+        bacc[l].on = a.record != 0;
+    }
+    for (int j = 0; j < D; ++j) {
+        // ---- stage the rows of degree j: [W0t | W[1] | ... | W[L-1] | Wo rows j, D+j]
+        int off[RABI_MAXL + 1];
+        {
+            int o = 0;
+            for (int l = 0; l < L; ++l) {
+                off[l] = o;
+                const int n = M[t.grp[l] + j + 1] - M[t.grp[l] + j];
+                o += n * (l == 0 ? t.ldt : t.ld[l]);
+            }
+            off[L] = o;
+        }
+        __syncthreads();
+        for (int l = 0; l < L; ++l) {
+            const int r0 = M[t.grp[l] + j], n = M[t.grp[l] + j + 1] - r0;
+            const int ld = l == 0 ? t.ldt : t.ld[l];
+            deep_stage(sm + off[l], F + (l == 0 ? t.W0t : t.W[l]) + (size_t)r0 * ld, (n * ld) >> 2);
+        }
+        deep_stage(sm + off[L], F + t.Wo + (size_t)j * t.ldo, t.ldo >> 2);
+        deep_stage(sm + off[L] + t.ldo, F + t.Wo + (size_t)(D + j) * t.ldo, t.ldo >> 2);
+        __syncthreads();
+        // ---- layer 0
+        {
+            const int ua = M[t.grp[0] + j], ub = M[t.grp[0] + j + 1];
+            for (int u = ua; u < ub; ++u) {
+                float pre = th.live ? __ldg(Ap + (size_t)u * a.B) : 0.f;
+                const float* w = sm + off[0] + (size_t)(u - ua) * t.ldt;
+#pragma unroll
+                for (int q4 = 0; q4 < DP / 4; ++q4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w + 4 * q4);
+                    pre = fmaf(w4.x, y[4 * q4], pre);
+                    pre = fmaf(w4.y, y[4 * q4 + 1], pre);
+                    pre = fmaf(w4.z, y[4 * q4 + 2], pre);
+                    pre = fmaf(w4.w, y[4 * q4 + 3], pre);
+                }
+                const bool on = pre > 0.f;
+                bacc[0].put(u, on);
+                h[0].st1(u, on ? pre : 0.f);
+            }
+        }
+        // ---- hidden layers 1..L-1
+        for (int l = 1; l < L; ++l) {
+            const int va = M[t.grp[l] + j], vb = M[t.grp[l] + j + 1];
+            const int e4 = (M[t.grp[l - 1] + j + 1] + 3) & ~3;
+            const int ld = t.ld[l];
+            for (int v0 = va; v0 < vb; v0 += 8) {
+                const int nv = min(8, vb - v0);
+                float o[8];
+                gdot_block<8>(sm + off[l] + (size_t)(v0 - va) * ld, ld, nv - 1, e4, h[l - 1], o);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < nv) {
+                        const float val = o[c] + __ldg(F + t.b[l] + v0 + c);
+                        const bool on = val > 0.f;
+                        bacc[l].put(v0 + c, on);
+                        h[l].st1(v0 + c, on ? val : 0.f);
+                    }
+            }
+        }
+        // ---- output position j, then y_j = (z_j - m_j) exp(-clamp(s_j))
+        {
+            const int e4 = (M[t.grp[L - 1] + j + 1] + 3) & ~3;
+            float o[2];
+            gdot_block<2>(sm + off[L], t.ldo, 1, e4, h[L - 1], o);
+            const float m = o[0] + __ldg(F + t.bo + j), s = o[1] + __ldg(F + t.bo + D + j);
+            float zj = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < DP; ++jj) zj = jj == j ? zos[jj] : zj;
+            const float sh = fminf(fmaxf(s, g.lo), g.hi);
+            const float yj = (zj - m) * expf(-sh);
+#pragma unroll
+            for (int jj = 0; jj < DP; ++jj) y[jj] = jj == j ? yj : y[jj];
+            logp += sh;
+            DV(SHP + k, j) = sh;
+            DV(SV + k + 1, M[t.permy + j]) = yj;
+        }
+    }
+    a.lp[th.col] = logp;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Density pass of transform k under A_q (one full MADE pass) + the chain update u_k = exp(clamp(s)) u_{k+1} + m.
+template <int DP>
+__global__ void __launch_bounds__(512, 1) kd_full_fwd(const MafImg g, const DeepArgs a, const int k, const int mode) {
+    extern __shared__ __align__(16) float sm[];
+    const DeepThread th = deep_thread(a);
+    const TImg& t = g.t[k];
+    const float* F = g.f;
+    const int* M = g.m;
+    const int K = g.K, D = g.D, L = g.L, H0 = g.H[0];
+    const int SV = 0, SU = K + 1, SHQ = 3 * K + 1, TB = 4 * K + 2, TC = 4 * K + 3;
+    const float HALF_LOG_2PI = 0.91893853320467274178f;
+    const int src = (k == K - 1) ? SV + K : SU + k + 1;
+    float y[DP];
+#pragma unroll
+    for (int jj = 0; jj < DP; ++jj) y[jj] = jj < D ? DV(src, M[t.permy + jj]) : 0.f;
+    const float* Aq = a.A_q + (size_t)k * H0 * a.B + th.b;
+    // ---- layer 0
+    {
+        const int H0p = (H0 + 3) & ~3;
+        __syncthreads();
+        deep_stage(sm, F + t.W0t, (H0p * t.ldt) >> 2);
+        __syncthreads();
+        ActBuf<2> h0 = deep_act(a, 0, th.col);
+        BitAcc bacc = {0u, deep_bits(a, g, 1, k, 0, th.col), (size_t)a.Np, H0, a.record != 0};
+        for (int u0 = 0; u0 < H0p; u0 += 4) {
+            float val[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int u = u0 + c;
+                float pre = (th.live && u < H0) ? __ldg(Aq + (size_t)u * a.B) : 0.f;
+                const float* w = sm + (size_t)u * t.ldt;
+#pragma unroll
+                for (int q4 = 0; q4 < DP / 4; ++q4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w + 4 * q4);
+                    pre = fmaf(w4.x, y[4 * q4], pre);
+                    pre = fmaf(w4.y, y[4 * q4 + 1], pre);
+                    pre = fmaf(w4.z, y[4 * q4 + 2], pre);
+                    pre = fmaf(w4.w, y[4 * q4 + 3], pre);
+                }
+                const bool on = u < H0 && pre > 0.f;
+                if (u < H0) bacc.put(u, on);
+                val[c] = on ? pre : 0.f;
+            }
+            h0.st4(u0, make_float4(val[0], val[1], val[2], val[3]));
+        }
+    }
+    // ---- hidden layers
+    for (int l = 1; l < L; ++l) {
+        const int Hl = g.H[l], Hlp = (Hl + 3) & ~3, ld = t.ld[l];
+        __syncthreads();
+        deep_stage(sm, F + t.W[l], (Hlp * ld) >> 2);
+        __syncthreads();
+        const ActBuf<2> in = deep_act(a, l - 1, th.col);
+        ActBuf<2> out = deep_act(a, l, th.col);
+        BitAcc bacc = {0u, deep_bits(a, g, 1, k, l, th.col), (size_t)a.Np, Hl, a.record != 0};
+        for (int v0 = 0; v0 < Hlp; v0 += 16) {
+            const int nv = min(16, Hlp - v0);  // padded rows are zero rows of the image
+            const int e4 = (M[t.pre[l] + min(v0 + nv, Hl) - 1] + 3) & ~3;
+            float o[16];
+            gdot_block<16>(sm + (size_t)v0 * ld, ld, nv - 1, e4, in, o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * q < nv) {
+                    float val[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int v = v0 + 4 * q + c;
+                        const float x = o[4 * q + c] + __ldg(F + t.b[l] + min(v, Hl - 1));
+                        const bool on = v < Hl && x > 0.f;
+                        if (v < Hl) bacc.put(v, on);
+                        val[c] = on ? x : 0.f;
+                    }
+                    out.st4(v0 + 4 * q, make_float4(val[0], val[1], val[2], val[3]));
+                }
+        }
+    }
+    // ---- output layer: rows 0..D-1 means, D..2D-1 log-scales
+    {
+        const int R = 2 * D, HL = g.H[L - 1], e4 = (HL + 3) & ~3;
+        const int Rp = (R + 3) & ~3;
+        __syncthreads();
+        deep_stage(sm, F + t.Wo, (Rp * t.ldo) >> 2);
+        __syncthreads();
+        const ActBuf<2> in = deep_act(a, L - 1, th.col);
+        for (int r0 = 0; r0 < R; r0 += 16) {
+            const int nr = min(16, R - r0);
+            float o[16];
+            gdot_block<16>(sm + (size_t)r0 * t.ldo, t.ldo, nr - 1, e4, in, o);
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < nr) {
+                    const int r = r0 + c;
+                    const float val = o[c] + __ldg(F + t.bo + r);
+                    if (r < D) DV(TB, r) = val;
+                    else DV(TC, r - D) = val;
+                }
+        }
+    }
+    float logq = (k == K - 1) ? 0.f : a.lp[(size_t)a.Np + th.col];
+#pragma unroll
+    for (int jj = 0; jj < DP; ++jj)
+        if (jj < D) {
+            const float sh = fminf(fmaxf(DV(TC, jj), g.lo), g.hi);
+            DV(SHQ + k, jj) = sh;
+            logq += sh;
+            DV(SU + k, M[t.perm + jj]) = fmaf(expf(sh), y[jj], DV(TB, jj));
+        }
+    if (k == 0) {
+        float ssq = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float u = DV(SU, d);
+            ssq = fmaf(u, u, ssq);
+            if (mode == DEEP_GRAD) DV(SU, d) = a.w * u;  // seed of the reverse pass: d(-w log q)/d u_0
+        }
+        logq += -0.5f * ssq - (float)D * HALF_LOG_2PI;
+        if (a.diff && th.live) a.diff[th.p] = a.lp[th.col] - logq;
+    }
+    a.lp[(size_t)a.Np + th.col] = logq;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Reverse of the density pass of transform k (input gradient only).  The running cotangent lives in vec slot SU.
+template <int DP>
+__global__ void __launch_bounds__(512, 1) kd_full_bwd(const MafImg g, const DeepArgs a, const int k) {
+    extern __shared__ __align__(16) float sm[];
+    const DeepThread th = deep_thread(a);
+    const TImg& t = g.t[k];
+    const float* F = g.f;
+    const int* M = g.m;
+    const int K = g.K, D = g.D, L = g.L, H0 = g.H[0];
+    const int WL = (g.Hmax + 31) >> 5;
+    const int SV = 0, SU = K + 1, SHQ = 3 * K + 1;
+    const int src = (k == K - 1) ? SV + K : SU + k + 1;
+    const float w = a.w;
+    float yb[DP];
+    ActBuf<2> ob = deep_obuf(a, th.col);
+    const int R = 2 * D, Rp = (R + 3) & ~3;
+    for (int i = R; i < Rp; ++i) ob.st1(i, 0.f);
+#pragma unroll
+    for (int jj = 0; jj < DP; ++jj) {
+        if (jj < D) {
+            const float ub = DV(SU, M[t.perm + jj]);
+            const float es = expf(DV(SHQ + k, jj));
+            const float yin = DV(src, M[t.permy + jj]);
+            ob.st1(jj, ub);
+            ob.st1(D + jj, fmaf(ub * es, yin, -w));
+            yb[jj] = ub * es;
+        } else {
+            yb[jj] = 0.f;
+        }
+    }
+    // ---- last hidden layer from the output layer
+    {
+        const int HL = g.H[L - 1], HLp = (HL + 3) & ~3;
+        __syncthreads();
+        deep_stage(sm, F + t.Wo, (Rp * t.ldo) >> 2);
+        __syncthreads();
+        ActBuf<2> out = deep_act(a, L - 1, th.col);
+        const uint32_t* bw = deep_bits(a, g, 1, k, L - 1, th.col);
+        for (int v0 = 0; v0 < HLp; v0 += 16) {
+            float o[16];
+            gtdot_block<16>(sm + v0, t.ldo, 0, Rp, ob, o);  // columns >= ldo are never stored
+            const uint32_t word = bw[(size_t)(v0 >> 5) * a.Np] >> (v0 & 31);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (v0 + 4 * q < HLp) {
+                    float val[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) val[c] = ((word >> (4 * q + c)) & 1u) ? o[4 * q + c] : 0.f;
+                    out.st4(v0 + 4 * q, make_float4(val[0], val[1], val[2], val[3]));
+                }
+        }
+    }
+    // ---- down the hidden layers
+    for (int l = L - 1; l >= 1; --l) {
+        const int Hin = g.H[l - 1], Hinp = (Hin + 3) & ~3, Hl = g.H[l], Hlp = (Hl + 3) & ~3, ld = t.ld[l];
+        __syncthreads();
+        deep_stage(sm, F + t.W[l], (Hlp * ld) >> 2);
+        __syncthreads();
+        const ActBuf<2> in = deep_act(a, l, th.col);
+        ActBuf<2> out = deep_act(a, l - 1, th.col);
+        const uint32_t* bw = deep_bits(a, g, 1, k, l - 1, th.col);
+        for (int u0 = 0; u0 < Hinp; u0 += 16) {
+            const int va4 = min(M[t.first[l] + u0], Hlp - 4) & ~3;
+            float o[16];
+            gtdot_block<16>(sm + u0, ld, va4, Hlp, in, o);
+            const uint32_t word = bw[(size_t)(u0 >> 5) * a.Np] >> (u0 & 31);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (u0 + 4 * q < Hinp) {
+                    float val[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) val[c] = ((word >> (4 * q + c)) & 1u) ? o[4 * q + c] : 0.f;
+                    out.st4(u0 + 4 * q, make_float4(val[0], val[1], val[2], val[3]));
+                }
+        }
+    }
+    // ---- theta positions from layer 0
+    {
+        const int H0p = (H0 + 3) & ~3;
+        __syncthreads();
+        deep_stage(sm, F + t.W0t, (H0p * t.ldt) >> 2);
+        __syncthreads();
+        float o[DP];
+        gtdot_block<DP>(sm, t.ldt, 0, H0p, deep_act(a, 0, th.col), o);
+#pragma unroll
+        for (int jj = 0; jj < DP; ++jj) yb[jj] += o[jj];
+    }
+#pragma unroll
+    for (int jj = 0; jj < DP; ++jj)
+        if (jj < D) DV(SU, M[t.permy + jj]) = yb[jj];
+    (void)WL;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Reverse of the sampling pass of transform k: D steps in descending order, pull style (every cotangent is produced
+// once, when all its consumers are final); emits d loss / d A_p.
+template <int DP>
+__global__ void __launch_bounds__(512, 1) kd_seq_bwd(const MafImg g, const DeepArgs a, const int k) {
+    extern __shared__ __align__(16) float sm[];
+    const DeepThread th = deep_thread(a);
+    const TImg& t = g.t[k];
+    const float* F = g.f;
+    const int* M = g.m;
+    const int K = g.K, D = g.D, L = g.L, H0 = g.H[0];
+    const int SV = 0, SU = K + 1, SHP = 2 * K + 1, TC = 4 * K + 3;
+    const float w = a.w;
+    float yb[DP];
+#pragma unroll
+    for (int jj = 0; jj < DP; ++jj) yb[jj] = jj < D ? DV(SU, M[t.permy + jj]) : 0.f;
+    ActBuf<2> ob = deep_obuf(a, th.col);
+    const int R = 2 * D, Rp = (R + 3) & ~3;
+    for (int i = 0; i < Rp; ++i) ob.st1(i, 0.f);
+    ActBuf<2> h[RABI_MAXL];
+    for (int l = 0; l < L; ++l) h[l] = deep_act(a, l, th.col);
+    float* gAk = a.gA + (size_t)k * H0 * a.B + th.b;
+    for (int j = D - 1; j >= 0; --j) {
+        {
+            float ybj = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < DP; ++jj) ybj = jj == j ? yb[jj] : ybj;
+            const float shj = DV(SHP + k, j);
+            const float yj = DV(SV + k + 1, M[t.permy + j]);
+            const float zbj = ybj * expf(-shj);
+            ob.st1(j, -zbj);
+            ob.st1(D + j, fmaf(-ybj, yj, w));
+            DV(TC, j) = zbj;
+        }
+        // ---- stage: column strips of the degree-j units of every layer (+ the layer-0 rows for the theta push)
+        int off[RABI_MAXL + 1], c0[RABI_MAXL], gw[RABI_MAXL], r0[RABI_MAXL + 1];
+        {
+            int o = 0;
+            for (int l = L - 1; l >= 0; --l) {
+                const int ua = M[t.grp[l] + j], ub = M[t.grp[l] + j + 1];
+                c0[l] = ua & ~3;
+                gw[l] = ub > ua ? ((ub + 3) & ~3) - c0[l] : 0;
+                // consumer rows: output rows 0..Rp for l = L-1, rows >= grp[l+1][j] of W[l+1] otherwise
+                r0[l + 1] = l == L - 1 ? 0 : (M[t.grp[l + 1] + j] & ~3);
+                const int nr = l == L - 1 ? Rp : ((g.H[l + 1] + 3) & ~3) - r0[l + 1];
+                off[l + 1] = o;
+                o += nr * gw[l];
+            }
+            off[0] = o;  // layer-0 rows of the group: [n0][ldt]
+        }
+        __syncthreads();
+        for (int l = L - 1; l >= 0; --l) {
+            if (gw[l] == 0) continue;
+            if (l == L - 1) deep_stage_strip(sm + off[L], F + t.Wo, t.ldo, 0, Rp, c0[l], gw[l]);
+            else deep_stage_strip(sm + off[l + 1], F + t.W[l + 1], t.ld[l + 1], r0[l + 1], ((g.H[l + 1] + 3) & ~3) - r0[l + 1], c0[l], gw[l]);
+        }
+        {
+            const int ua = M[t.grp[0] + j], n = M[t.grp[0] + j + 1] - ua;
+            deep_stage(sm + off[0], F + t.W0t + (size_t)ua * t.ldt, (n * t.ldt) >> 2);
+        }
+        __syncthreads();
+        for (int l = L - 1; l >= 0; --l) {
+            const int ua = M[t.grp[l] + j], ub = M[t.grp[l] + j + 1];
+            if (ub <= ua) continue;
+            const uint32_t* bw = deep_bits(a, g, 0, k, l, th.col);
+            const ActBuf<2> in = l == L - 1 ? ob : h[l + 1];
+            const int va4 = r0[l + 1], vb4 = l == L - 1 ? Rp : ((g.H[l + 1] + 3) & ~3);
+            // strip row r holds consumer row r0 + r: shift the base so that the absolute row index works
+            const float* S = sm + off[l + 1] - (size_t)va4 * gw[l];
+            auto emit = [&](int cc, int c, float val) {
+                const int u = c0[l] + cc + c;
+                if (u >= ua && u < ub) {
+                    const bool on = (bw[(size_t)(u >> 5) * a.Np] >> (u & 31)) & 1u;
+                    const float gv = on ? val : 0.f;
+                    if (l > 0) {
+                        h[l].st1(u, gv);
+                    } else {
+                        if (th.live) atomicAdd(gAk + (size_t)u * a.B, gv);
+                        const float* wr = sm + off[0] + (size_t)(u - ua) * t.ldt;
+#pragma unroll
+                        for (int q4 = 0; q4 < DP / 4; ++q4) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * q4);
+                            yb[4 * q4] = fmaf(w4.x, gv, yb[4 * q4]);
+                            yb[4 * q4 + 1] = fmaf(w4.y, gv, yb[4 * q4 + 1]);
+                            yb[4 * q4 + 2] = fmaf(w4.z, gv, yb[4 * q4 + 2]);
+                            yb[4 * q4 + 3] = fmaf(w4.w, gv, yb[4 * q4 + 3]);
+                        }
+                    }
+                }
+            };
+            for (int cc = 0; cc < gw[l];) {  // the whole strip in as few passes over the consumer vector as possible
+                const int left = gw[l] - cc;
+                if (left >= 16) {
+                    float o[16];
+                    gtdot_block<16>(S + cc, gw[l], va4, vb4, in, o);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) emit(cc, c, o[c]);
+                    cc += 16;
+                } else if (left == 12) {
+                    float o[12];
+                    gtdot_block<12>(S + cc, gw[l], va4, vb4, in, o);
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) emit(cc, c, o[c]);
+                    cc += 12;
+                } else if (left >= 8) {
+                    float o[8];
+                    gtdot_block<8>(S + cc, gw[l], va4, vb4, in, o);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) emit(cc, c, o[c]);
+                    cc += 8;
+                } else {
+                    float o[4];
+                    gtdot_block<4>(S + cc, gw[l], va4, vb4, in, o);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) emit(cc, c, o[c]);
+                    cc += 4;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < DP; ++jj)
+        if (jj < D) DV(SU, M[t.perm + jj]) = DV(TC, jj);
+}
+
+#undef DV
+
+}  // namespace rabi

@@ -54,10 +54,11 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 // TMEM (tensor memory, 512 columns x 128 lanes x 32 bit per SM) is idle in this FMA-bound kernel; .32x32b accesses
 // give every thread of a warp its own lane, so a column range is a thread-private array with 128-bit vector access.
 // Keeping the activations there frees ~45% of the per-pair shared memory => twice the resident warps.
-template <bool TM>
+// kind: 0 = shared memory, 1 = tensor memory, 2 = global-memory scratch (maf_deep.cuh)
+template <int AK>
 struct ActBuf;
 template <>
-struct ActBuf<false> {
+struct ActBuf<0> {
     float* p;
     __device__ __forceinline__ float4 ld4(int i) const { return *reinterpret_cast<const float4*>(p + i); }
     __device__ __forceinline__ void st4(int i, float4 v) const { *reinterpret_cast<float4*>(p + i) = v; }
@@ -66,7 +67,7 @@ struct ActBuf<false> {
     __device__ __forceinline__ static void wait_st() {}
 };
 template <>
-struct ActBuf<true> {
+struct ActBuf<1> {
     uint32_t t;  // TMEM address of column 0 of this thread's row: (lane quadrant base << 16) | first column
     __device__ __forceinline__ float4 ld4(int i) const {
         float4 v;
@@ -92,7 +93,7 @@ struct ActBuf<true> {
 };
 
 // out[r][c] = sum_{i<e4} W[(min(c,cmax))*ld + i] * act_r[i]     (NR rows x RP pairs, e4 multiple of 4, e4 >= 4)
-template <int RP, int NR, bool TM, int LDC>
+template <int RP, int NR, int TM, int LDC>
 __device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld_rt, int cmax, int e4,
                                           const ActBuf<TM> (&ab)[RP], float (&out)[RP][NR]) {
     float2 acc[RP][NR];
@@ -137,7 +138,7 @@ __device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld_rt
 
 // out[r][c] = sum_{v in [va4, vb4)} W[v*ld + c] * g_r[v]     (NC columns x RP pairs; W offset to the first column;
 // va4 < vb4 multiples of 4; rows >= the layer's width are zero padding)
-template <int RP, int NC, bool TM, int LDC>
+template <int RP, int NC, int TM, int LDC>
 __device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld_rt, int va4, int vb4,
                                            const ActBuf<TM> (&ab)[RP], float (&out)[RP][NC]) {
     float2 acc[RP][NC / 2];

@@ -13,6 +13,7 @@
 #include "maf_image.h"
 #include "maf_pairs.cuh"
 #include "maf_fast.cuh"
+#include "maf_deep.cuh"
 
 using namespace rabi;
 
@@ -34,6 +35,8 @@ struct rabi_maf {
     size_t n_float = 0, n_int = 0;
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    void* deep_ws = nullptr;   // per-pair scratch of the deep path (maf_deep.cuh), zero-initialised on allocation
+    size_t deep_ws_bytes = 0;
     unsigned long long launches = 0;
     // optional CUDA-event timing of the dominant kernel (k_pairs<RKL_GRAD>) on its launch stream
     bool profiling = false;
@@ -111,6 +114,7 @@ extern "C" int rabi_maf_destroy(rabi_maf_t* h) {
     if (h->f_dev) cudaFree(h->f_dev);
     if (h->m_dev) cudaFree(h->m_dev);
     if (h->ws) cudaFree(h->ws);
+    if (h->deep_ws) cudaFree(h->deep_ws);
     for (auto& e : h->prof_events) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -1015,6 +1019,130 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     return 2;
 }
 
+// ---- deep / wide conditioners: per-(transform, pass) launches over a global-memory scratch (maf_deep.cuh) ----------
+template <int DP>
+static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaStream_t st) {
+    const int K = h->K, D = h->D, L = h->L;
+    const MafImg& g = h->img;
+    const std::vector<int>& M = h->meta_host;
+    auto r4 = [](int x) { return (x + 3) & ~3; };
+    // shared-memory needs (floats)
+    size_t full = (size_t)r4(h->H[0]) * g.t[0].ldt;
+    for (int l = 1; l < L; ++l) full = std::max(full, (size_t)r4(h->H[l]) * g.t[0].ld[l]);
+    full = std::max(full, (size_t)r4(2 * D) * g.t[0].ldo) + 64;
+    size_t seqf = 0, seqb = 0;
+    for (int k = 0; k < K; ++k) {
+        const TImg& t = g.t[k];
+        for (int j = 0; j < D; ++j) {
+            size_t f = 2 * (size_t)t.ldo, b = 0;
+            for (int l = 0; l < L; ++l) {
+                const int ua = M[t.grp[l] + j], ub = M[t.grp[l] + j + 1];
+                f += (size_t)(ub - ua) * (l == 0 ? t.ldt : t.ld[l]);
+                const int gw = ub > ua ? r4(ub) - (ua & ~3) : 0;
+                const int nr = l == L - 1 ? r4(2 * D) : r4(h->H[l + 1]) - (M[t.grp[l + 1] + j] & ~3);
+                b += (size_t)nr * gw;
+                if (l == 0) b += (size_t)(ub - ua) * t.ldt;
+            }
+            seqf = std::max(seqf, f);
+            seqb = std::max(seqb, b);
+        }
+    }
+    seqf += 64;
+    seqb += 64;
+    const size_t budget = (size_t)h->max_smem_optin - 1024;
+    if (full * 4 > budget || seqf * 4 > budget || seqb * 4 > budget) return 2;
+    CU_OK(h, cudaFuncSetAttribute(kd_seq_fwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(seqf * 4)));
+    CU_OK(h, cudaFuncSetAttribute(kd_full_fwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(full * 4)));
+    CU_OK(h, cudaFuncSetAttribute(kd_full_bwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(full * 4)));
+    CU_OK(h, cudaFuncSetAttribute(kd_seq_bwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(seqb * 4)));
+    // batches: at most one CTA of <= Tmax threads per SM, every SM gets the same number of pairs
+    const int Tmax = std::max(64, std::min(512, env_int("RABI_DEEP_T", 512) & ~31));
+    const long long cap = (long long)h->sm_count * Tmax;
+    const long long nbatch = (N + cap - 1) / cap;
+    const int nmax = (int)((N + nbatch - 1) / nbatch);
+    int T = (int)((((nmax + h->sm_count - 1) / h->sm_count) + 31) & ~31);
+    T = std::max(64, std::min(Tmax, T));
+    const int grid_max = (nmax + T - 1) / T;
+    const int Np = grid_max * T;
+    const int WL = (g.Hmax + 31) / 32;
+    const int Hq = (r4(g.Hmax) + 4) / 4, Oq = (r4(2 * D) + 4) / 4;
+    const size_t n_act = (size_t)L * Hq * Np * 4, n_ob = (size_t)Oq * Np * 4, n_vec = (size_t)deep_nvec(K) * D * Np;
+    const size_t n_bits = (size_t)2 * K * L * WL * Np, n_lp = (size_t)2 * Np;
+    const size_t bytes = (n_act + n_ob + n_vec + n_bits + n_lp) * sizeof(float);
+    if (bytes > h->deep_ws_bytes) {
+        if (h->deep_ws) {
+            CU_OK(h, cudaDeviceSynchronize());
+            CU_OK(h, cudaFree(h->deep_ws));
+            h->deep_ws = nullptr;
+            h->deep_ws_bytes = 0;
+        }
+        CU_OK(h, cudaMalloc(&h->deep_ws, bytes));
+        h->deep_ws_bytes = bytes;
+        CU_OK(h, cudaMemsetAsync(h->deep_ws, 0, bytes, st));
+    }
+    // stale activations are only ever multiplied by exact-zero (masked / padded) weights, so they must be finite:
+    // clear them per call (a diverged earlier call may have left NaN behind)
+    CU_OK(h, cudaMemsetAsync(h->deep_ws, 0, (n_act + n_ob) * sizeof(float), st));
+    a.act = (float*)h->deep_ws;
+    a.obuf = a.act + n_act;
+    a.vec = a.obuf + n_ob;
+    a.bits = (uint32_t*)(a.vec + n_vec);
+    a.lp = (float*)(a.bits + n_bits);
+    a.Np = Np;
+    a.Hq = Hq;
+    a.Oq = Oq;
+    a.record = mode == DEEP_GRAD;
+    const bool prof = h->profiling && mode == DEEP_GRAD;
+    if (prof) {
+        if (h->prof_used == h->prof_events.size()) {
+            cudaEvent_t e0, e1;
+            CU_OK(h, cudaEventCreate(&e0));
+            CU_OK(h, cudaEventCreate(&e1));
+            h->prof_events.push_back({e0, e1});
+        }
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].first, st));
+    }
+    for (long long p0 = 0; p0 < N; p0 += nmax) {
+        a.p0 = p0;
+        a.n = (int)std::min<long long>(nmax, N - p0);
+        const int grid = (a.n + T - 1) / T;
+        for (int k = 0; k < K; ++k) {
+            kd_seq_fwd<DP><<<grid, T, seqf * 4, st>>>(g, a, k);
+            LAUNCH_CHECK(h);
+        }
+        for (int k = K - 1; k >= 0; --k) {
+            kd_full_fwd<DP><<<grid, T, full * 4, st>>>(g, a, k, mode);
+            LAUNCH_CHECK(h);
+        }
+        if (mode == DEEP_GRAD) {
+            for (int k = 0; k < K; ++k) {
+                kd_full_bwd<DP><<<grid, T, full * 4, st>>>(g, a, k);
+                LAUNCH_CHECK(h);
+            }
+            for (int k = K - 1; k >= 0; --k) {
+                kd_seq_bwd<DP><<<grid, T, seqb * 4, st>>>(g, a, k);
+                LAUNCH_CHECK(h);
+            }
+        }
+    }
+    if (prof) {
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].second, st));
+        h->prof_used++;
+    }
+    return 0;
+}
+
+// returns 0 = launched, 1 = error, 2 = not applicable (caller falls back to the generic per-pair kernel)
+static int launch_deep(rabi_maf* h, const DeepArgs& a, int mode, cudaStream_t st) {
+    const long long N = (long long)a.S * a.B;
+    if (N <= 0) return 0;
+    if (env_int("RABI_DISABLE_DEEP", 0)) return 2;
+    if (h->L < 2 || h->D > 32) return 2;
+    if (h->D <= 4) return launch_deep_dp<4>(h, a, mode, N, st);
+    if (h->D <= 12) return launch_deep_dp<12>(h, a, mode, N, st);
+    return launch_deep_dp<32>(h, a, mode, N, st);
+}
+
 extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_q_dev, const float* z_dev, int S, int B,
                             float* kl_dev, rabi_stream_t s) {
     REQUIRE_READY(h);
@@ -1036,8 +1164,19 @@ extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_
         fa.diff = (float*)h->ws;
         fa.S = S;
         fa.B = B;
-        int rc = launch_fast<FAST_FWD>(h, fa, st);
+        int rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_FWD>(h, fa, st);
         if (rc == 1) return 1;
+        if (rc == 2) {
+            DeepArgs da = {};
+            da.A_p = A_p_dev;
+            da.A_q = A_q_dev;
+            da.z = z_dev;
+            da.diff = (float*)h->ws;
+            da.S = S;
+            da.B = B;
+            rc = launch_deep(h, da, DEEP_FWD, st);
+            if (rc == 1) return 1;
+        }
         if (rc == 2 && launch_pairs<MODE_RKL_FWD>(h, a, st)) return 1;
     }
     k_mean_over_s<<<(B + 127) / 128, 128, 0, st>>>((const float*)h->ws, S, B, kl_dev);
@@ -1071,9 +1210,24 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
         rc = launch_fast<FAST_FKL>(h, fa, st);
         if (rc == 2) return fail(h, "the forward-KL attack loss is only available on the fast path (two hidden layers, D <= 12)");
     } else {
-        rc = launch_fast<FAST_GRAD>(h, fa, st);
+        rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_GRAD>(h, fa, st);
     }
     if (rc == 1) return 1;
+    if (rc == 2) {  // deep path (global-memory scratch), gA accumulated with atomics
+        CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
+        DeepArgs da = {};
+        da.A_p = A_p;
+        da.A_q = A_q;
+        da.z = z;
+        da.diff = kl ? diff : nullptr;
+        da.gA = gA;
+        da.S = S;
+        da.B = B;
+        da.w = inv_B / (float)S;
+        rc = launch_deep(h, da, DEEP_GRAD, st);
+        if (rc == 1) return 1;
+        if (rc == 0) rc = 3;  // done
+    }
     if (rc == 2) {  // generic per-pair kernel (accumulates gA with atomics)
         CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
         PairArgs a = {};

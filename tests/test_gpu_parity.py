@@ -359,3 +359,75 @@ def test_l2pgd_through_a_nonidentity_embedding_vs_oracle(dev):
     with torch.no_grad(), noise.injected([zs[0]]):
         kl = ReverseKLLoss(mc_samples=S, reduction=None)(model(xa_ref.to(dev)), model(x.to(dev)))
     assert float((kl.cpu() - kl_ref).abs().max()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------
+# deep path (maf_deep.cuh: per-pair state in a global-memory scratch, one launch per (transform, pass)); it serves the
+# models the fast path cannot hold on chip (pyloric_small above already runs on it) and can be forced for any model
+@pytest.fixture()
+def force_deep():
+    import os
+
+    os.environ["RABI_FORCE_DEEP"] = "1"
+    yield
+    os.environ.pop("RABI_FORCE_DEEP", None)
+
+
+def test_deep_path_matches_reference_fixtures(case, dev, force_deep):
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+
+    name, g, model = case
+    x, xt = g["x"].to(dev), g["x_tilde"].to(dev)
+    launches0 = model.engine().launches
+    with torch.no_grad(), noise.injected([g["z_rkl64"]]):
+        kl = ReverseKLLoss(mc_samples=64, reduction=None)(model(xt), model(x))
+    scale = max(float(g["rsample_log_prob"].abs().max()), float(g["rkl64"].abs().max()))
+    assert float((kl.cpu() - g["rkl64"]).abs().max()) < RTOL * scale
+    eng = model.engine()
+    with torch.no_grad():
+        q = model(x)
+        _, zs, _ = model.condition_inputs(xt)
+        zs = zs or (None, None)
+        gx, klm = eng.rkl_input_grad(xt, zs[0], zs[1], q.A, g["z_rkl_grad"].to(dev), 1.0 / x.shape[0])
+    assert rel_err(gx, g["rkl_grad_x"]) < RTOL
+    assert abs(float(klm.mean()) - float(g["rkl_mean"])) < RTOL * float(g["rsample_log_prob"].abs().max())
+    p = g["pgd"]
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=p["S"]), eps=p["eps"], nb_iter=5, eps_iter=p["eps_iter"],
+                      clip_min=p["clip_min"], clip_max=p["clip_max"])
+    with noise.injected(list(p["z_5"])):
+        xa = atk.perturb(x, delta_init=p["delta0"].to(dev))
+    assert_trajectories_match(xa.cpu() - g["x"], p["x_adv_5"] - g["x"], RTOL)
+    assert model.engine().launches > launches0
+
+
+def test_deep_path_equals_generic_kernel_across_batches(dev):
+    """3 hidden layers, D = 9, more pairs than one batch of the deep path holds (RABI_DEEP_T=64 => 148 x 64 pairs per
+    batch), ragged sizes: deep == generic per-pair kernel for the metric and for the attack gradient."""
+    import os
+
+    ref, model, x = _fresh(dict(dx=12, D=9, hidden=[40, 36, 44], B=1201), dev, seed=7)
+    xd = x.to(dev)
+    eng = model.engine()
+    g = torch.Generator().manual_seed(1)
+    S = 9
+    z = torch.randn(S, xd.shape[0], 9, generator=g).to(dev)
+    with torch.no_grad():
+        q = model(xd)
+        _, zs, _ = model.condition_inputs(xd)
+        outs = []
+        for env in ({"RABI_DEEP_T": "64"}, {"RABI_DISABLE_DEEP": "1"}):
+            os.environ.update(env)
+            try:
+                Ap = model(xd + 0.05).A
+                kl = eng.rkl(Ap, q.A, z)
+                gx, klm = eng.rkl_input_grad(xd + 0.05, zs[0], zs[1], q.A, z, 1.0 / xd.shape[0])
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+            outs.append((kl, gx, klm))
+    (kl_d, gx_d, klm_d), (kl_g, gx_g, klm_g) = outs
+    assert float((kl_d - kl_g).abs().max()) < 1e-5 * max(1.0, float(kl_g.abs().max()) * 10)
+    assert float((klm_d - klm_g).abs().max()) < 1e-5 * max(1.0, float(klm_g.abs().max()) * 10)
+    assert_trajectories_match(gx_d, gx_g, 1e-4)
