@@ -54,16 +54,20 @@ __device__ __forceinline__ void gdot_block(const float* __restrict__ W, int ld, 
         wr[c] = W + (size_t)min(c, cmax) * ld;
     }
     float4 cur[PD], nxt[PD];
+    const float* xp = x.p;  // next quad to fetch (pointer stepping instead of 64-bit index arithmetic per load)
 #pragma unroll
     for (int q = 0; q < PD; ++q) {
         cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         nxt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (4 * q < e4) cur[q] = x.ld4(4 * q);
+        if (4 * q < e4) cur[q] = *reinterpret_cast<const float4*>(xp);
+        xp += x.q;
     }
     for (int i = 0; i < e4; i += 4 * PD) {
 #pragma unroll
-        for (int q = 0; q < PD; ++q)
-            if (i + 4 * (PD + q) < e4) nxt[q] = x.ld4(i + 4 * (PD + q));
+        for (int q = 0; q < PD; ++q) {
+            if (i + 4 * (PD + q) < e4) nxt[q] = *reinterpret_cast<const float4*>(xp);
+            xp += x.q;
+        }
 #pragma unroll
         for (int q = 0; q < PD; ++q)
             if (i + 4 * q < e4) {
@@ -90,16 +94,20 @@ __device__ __forceinline__ void gtdot_block(const float* __restrict__ W, int ld,
 #pragma unroll
     for (int c = 0; c < NC / 2; ++c) acc[c] = make_float2(0.f, 0.f);
     float4 cur[PD], nxt[PD];
+    const float* xp = x.p + (size_t)(va4 >> 2) * x.q;
 #pragma unroll
     for (int q = 0; q < PD; ++q) {
         cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         nxt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (va4 + 4 * q < vb4) cur[q] = x.ld4(va4 + 4 * q);
+        if (va4 + 4 * q < vb4) cur[q] = *reinterpret_cast<const float4*>(xp);
+        xp += x.q;
     }
     for (int v = va4; v < vb4; v += 4 * PD) {
 #pragma unroll
-        for (int q = 0; q < PD; ++q)
-            if (v + 4 * (PD + q) < vb4) nxt[q] = x.ld4(v + 4 * (PD + q));
+        for (int q = 0; q < PD; ++q) {
+            if (v + 4 * (PD + q) < vb4) nxt[q] = *reinterpret_cast<const float4*>(xp);
+            xp += x.q;
+        }
 #pragma unroll
         for (int q = 0; q < PD; ++q)
             if (v + 4 * q < vb4) {
@@ -127,14 +135,17 @@ __device__ __forceinline__ void gtdot_block(const float* __restrict__ W, int ld,
     }
 }
 
-enum DeepMode { DEEP_FWD = 0, DEEP_GRAD = 1 };
+// DEEP_FKL: forward-KL attack loss KL(target || q(.|x+delta)): samples from the fixed target (A_p), gradient through the
+// density pass only (d/dA_q, emitted by kd_full_bwd).  DEEP_LOGPROB / DEEP_RSAMPLE: one chain only.
+enum DeepMode { DEEP_FWD = 0, DEEP_GRAD = 1, DEEP_FKL = 2, DEEP_LOGPROB = 3, DEEP_RSAMPLE = 4 };
 
 struct DeepArgs {
     const float* A_p;   // [K,H0,B]
     const float* A_q;
     const float* z;     // [S*B][D]
     float* diff;        // [S*B] log p - log q (optional)
-    float* gA;          // [K,H0,B] += d loss / d A_p (atomics; caller zeroes)
+    float* gA;          // [K,H0,B] += d loss / d A_p (GRAD) or d A_q (FKL)  (atomics; caller zeroes)
+    float* theta_out;   // RSAMPLE: [S*B][D]
     int S, B;
     long long p0;       // first pair of this batch
     int n;              // pairs in this batch
@@ -230,7 +241,7 @@ __device__ __forceinline__ uint32_t* deep_bits(const DeepArgs& a, const MafImg& 
 // ---------------------------------------------------------------------------------------------------------------------
 // Sampling pass of transform k under A_p: D steps; step j evaluates the units of MADE degree j of every layer.
 template <int DP>
-__global__ void __launch_bounds__(512, 1) kd_seq_fwd(const MafImg g, const DeepArgs a, const int k) {
+__global__ void __launch_bounds__(384, 1) kd_seq_fwd(const MafImg g, const DeepArgs a, const int k) {
     extern __shared__ __align__(16) float sm[];
     const DeepThread th = deep_thread(a);
     const TImg& t = g.t[k];
@@ -251,16 +262,15 @@ __global__ void __launch_bounds__(512, 1) kd_seq_fwd(const MafImg g, const DeepA
     } else {
         logp = a.lp[th.col];
     }
-    float zos[DP], y[DP];
+    float y[DP];
 #pragma unroll
-    for (int jj = 0; jj < DP; ++jj) {
-        zos[jj] = jj < D ? DV(SV + k, M[t.perm + jj]) : 0.f;
-        y[jj] = 0.f;
-    }
+    for (int jj = 0; jj < DP; ++jj) y[jj] = 0.f;
     const float* Ap = a.A_p + (size_t)k * H0 * a.B + th.b;
     ActBuf<2> h[RABI_MAXL];
     BitAcc bacc[RABI_MAXL];
-    for (int l = 0; l < L; ++l) {
+#pragma unroll
+    for (int l = 0; l < RABI_MAXL; ++l) {
+        if (l >= L) continue;
         h[l] = deep_act(a, l, th.col);
         bacc[l].w = 0u;
         bacc[l].base = deep_bits(a, g, 0, k, l, th.col);
@@ -273,21 +283,26 @@ __global__ void __launch_bounds__(512, 1) kd_seq_fwd(const MafImg g, const DeepA
         int off[RABI_MAXL + 1];
         {
             int o = 0;
-            for (int l = 0; l < L; ++l) {
+#pragma unroll
+            for (int l = 0; l < RABI_MAXL; ++l) {
                 off[l] = o;
-                const int n = M[t.grp[l] + j + 1] - M[t.grp[l] + j];
-                o += n * (l == 0 ? t.ldt : t.ld[l]);
+                if (l < L) {
+                    const int n = M[t.grp[l] + j + 1] - M[t.grp[l] + j];
+                    o += n * (l == 0 ? t.ldt : t.ld[l]);
+                }
             }
-            off[L] = o;
+            off[RABI_MAXL] = o;  // output rows follow the last layer's rows
         }
         __syncthreads();
-        for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int l = 0; l < RABI_MAXL; ++l) {
+            if (l >= L) continue;
             const int r0 = M[t.grp[l] + j], n = M[t.grp[l] + j + 1] - r0;
             const int ld = l == 0 ? t.ldt : t.ld[l];
             deep_stage(sm + off[l], F + (l == 0 ? t.W0t : t.W[l]) + (size_t)r0 * ld, (n * ld) >> 2);
         }
-        deep_stage(sm + off[L], F + t.Wo + (size_t)j * t.ldo, t.ldo >> 2);
-        deep_stage(sm + off[L] + t.ldo, F + t.Wo + (size_t)(D + j) * t.ldo, t.ldo >> 2);
+        deep_stage(sm + off[RABI_MAXL], F + t.Wo + (size_t)j * t.ldo, t.ldo >> 2);
+        deep_stage(sm + off[RABI_MAXL] + t.ldo, F + t.Wo + (size_t)(D + j) * t.ldo, t.ldo >> 2);
         __syncthreads();
         // ---- layer 0
         {
@@ -309,7 +324,9 @@ __global__ void __launch_bounds__(512, 1) kd_seq_fwd(const MafImg g, const DeepA
             }
         }
         // ---- hidden layers 1..L-1
-        for (int l = 1; l < L; ++l) {
+#pragma unroll
+        for (int l = 1; l < RABI_MAXL; ++l) {
+            if (l >= L) continue;
             const int va = M[t.grp[l] + j], vb = M[t.grp[l] + j + 1];
             const int e4 = (M[t.grp[l - 1] + j + 1] + 3) & ~3;
             const int ld = t.ld[l];
@@ -331,11 +348,9 @@ __global__ void __launch_bounds__(512, 1) kd_seq_fwd(const MafImg g, const DeepA
         {
             const int e4 = (M[t.grp[L - 1] + j + 1] + 3) & ~3;
             float o[2];
-            gdot_block<2>(sm + off[L], t.ldo, 1, e4, h[L - 1], o);
+            gdot_block<2>(sm + off[RABI_MAXL], t.ldo, 1, e4, deep_act(a, L - 1, th.col), o);
             const float m = o[0] + __ldg(F + t.bo + j), s = o[1] + __ldg(F + t.bo + D + j);
-            float zj = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < DP; ++jj) zj = jj == j ? zos[jj] : zj;
+            const float zj = DV(SV + k, M[t.perm + j]);
             const float sh = fminf(fmaxf(s, g.lo), g.hi);
             const float yj = (zj - m) * expf(-sh);
 #pragma unroll
@@ -351,7 +366,7 @@ __global__ void __launch_bounds__(512, 1) kd_seq_fwd(const MafImg g, const DeepA
 // ---------------------------------------------------------------------------------------------------------------------
 // Density pass of transform k under A_q (one full MADE pass) + the chain update u_k = exp(clamp(s)) u_{k+1} + m.
 template <int DP>
-__global__ void __launch_bounds__(512, 1) kd_full_fwd(const MafImg g, const DeepArgs a, const int k, const int mode) {
+__global__ void __launch_bounds__(384, 1) kd_full_fwd(const MafImg g, const DeepArgs a, const int k, const int mode) {
     extern __shared__ __align__(16) float sm[];
     const DeepThread th = deep_thread(a);
     const TImg& t = g.t[k];
@@ -461,10 +476,10 @@ __global__ void __launch_bounds__(512, 1) kd_full_fwd(const MafImg g, const Deep
         for (int d = 0; d < D; ++d) {
             const float u = DV(SU, d);
             ssq = fmaf(u, u, ssq);
-            if (mode == DEEP_GRAD) DV(SU, d) = a.w * u;  // seed of the reverse pass: d(-w log q)/d u_0
+            if (mode == DEEP_GRAD || mode == DEEP_FKL) DV(SU, d) = a.w * u;  // reverse-pass seed: d(-w log q)/d u_0
         }
         logq += -0.5f * ssq - (float)D * HALF_LOG_2PI;
-        if (a.diff && th.live) a.diff[th.p] = a.lp[th.col] - logq;
+        if (a.diff && th.live) a.diff[th.p] = mode == DEEP_LOGPROB ? logq : a.lp[th.col] - logq;
     }
     a.lp[(size_t)a.Np + th.col] = logq;
 }
@@ -472,7 +487,7 @@ __global__ void __launch_bounds__(512, 1) kd_full_fwd(const MafImg g, const Deep
 // ---------------------------------------------------------------------------------------------------------------------
 // Reverse of the density pass of transform k (input gradient only).  The running cotangent lives in vec slot SU.
 template <int DP>
-__global__ void __launch_bounds__(512, 1) kd_full_bwd(const MafImg g, const DeepArgs a, const int k) {
+__global__ void __launch_bounds__(384, 1) kd_full_bwd(const MafImg g, const DeepArgs a, const int k, const int emit_gA) {
     extern __shared__ __align__(16) float sm[];
     const DeepThread th = deep_thread(a);
     const TImg& t = g.t[k];
@@ -552,6 +567,17 @@ __global__ void __launch_bounds__(512, 1) kd_full_bwd(const MafImg g, const Deep
         __syncthreads();
         deep_stage(sm, F + t.W0t, (H0p * t.ldt) >> 2);
         __syncthreads();
+        if (emit_gA && th.live) {  // forward-KL attack: the differentiated pass is this one
+            const ActBuf<2> g0 = deep_act(a, 0, th.col);
+            float* gAk = a.gA + (size_t)k * H0 * a.B + th.b;
+            for (int u0 = 0; u0 < H0; u0 += 4) {
+                const float4 v = g0.ld4(u0);
+                atomicAdd(gAk + (size_t)u0 * a.B, v.x);
+                if (u0 + 1 < H0) atomicAdd(gAk + (size_t)(u0 + 1) * a.B, v.y);
+                if (u0 + 2 < H0) atomicAdd(gAk + (size_t)(u0 + 2) * a.B, v.z);
+                if (u0 + 3 < H0) atomicAdd(gAk + (size_t)(u0 + 3) * a.B, v.w);
+            }
+        }
         float o[DP];
         gtdot_block<DP>(sm, t.ldt, 0, H0p, deep_act(a, 0, th.col), o);
 #pragma unroll
@@ -567,7 +593,7 @@ __global__ void __launch_bounds__(512, 1) kd_full_bwd(const MafImg g, const Deep
 // Reverse of the sampling pass of transform k: D steps in descending order, pull style (every cotangent is produced
 // once, when all its consumers are final); emits d loss / d A_p.
 template <int DP>
-__global__ void __launch_bounds__(512, 1) kd_seq_bwd(const MafImg g, const DeepArgs a, const int k) {
+__global__ void __launch_bounds__(384, 1) kd_seq_bwd(const MafImg g, const DeepArgs a, const int k) {
     extern __shared__ __align__(16) float sm[];
     const DeepThread th = deep_thread(a);
     const TImg& t = g.t[k];
@@ -583,7 +609,9 @@ __global__ void __launch_bounds__(512, 1) kd_seq_bwd(const MafImg g, const DeepA
     const int R = 2 * D, Rp = (R + 3) & ~3;
     for (int i = 0; i < Rp; ++i) ob.st1(i, 0.f);
     ActBuf<2> h[RABI_MAXL];
-    for (int l = 0; l < L; ++l) h[l] = deep_act(a, l, th.col);
+#pragma unroll
+    for (int l = 0; l < RABI_MAXL; ++l)
+        if (l < L) h[l] = deep_act(a, l, th.col);
     float* gAk = a.gA + (size_t)k * H0 * a.B + th.b;
     for (int j = D - 1; j >= 0; --j) {
         {
@@ -601,7 +629,9 @@ __global__ void __launch_bounds__(512, 1) kd_seq_bwd(const MafImg g, const DeepA
         int off[RABI_MAXL + 1], c0[RABI_MAXL], gw[RABI_MAXL], r0[RABI_MAXL + 1];
         {
             int o = 0;
-            for (int l = L - 1; l >= 0; --l) {
+#pragma unroll
+            for (int l = RABI_MAXL - 1; l >= 0; --l) {
+                if (l >= L) continue;
                 const int ua = M[t.grp[l] + j], ub = M[t.grp[l] + j + 1];
                 c0[l] = ua & ~3;
                 gw[l] = ub > ua ? ((ub + 3) & ~3) - c0[l] : 0;
@@ -614,9 +644,10 @@ __global__ void __launch_bounds__(512, 1) kd_seq_bwd(const MafImg g, const DeepA
             off[0] = o;  // layer-0 rows of the group: [n0][ldt]
         }
         __syncthreads();
-        for (int l = L - 1; l >= 0; --l) {
-            if (gw[l] == 0) continue;
-            if (l == L - 1) deep_stage_strip(sm + off[L], F + t.Wo, t.ldo, 0, Rp, c0[l], gw[l]);
+#pragma unroll
+        for (int l = RABI_MAXL - 1; l >= 0; --l) {
+            if (l >= L || gw[l] == 0) continue;
+            if (l == L - 1) deep_stage_strip(sm + off[l + 1], F + t.Wo, t.ldo, 0, Rp, c0[l], gw[l]);
             else deep_stage_strip(sm + off[l + 1], F + t.W[l + 1], t.ld[l + 1], r0[l + 1], ((g.H[l + 1] + 3) & ~3) - r0[l + 1], c0[l], gw[l]);
         }
         {
@@ -624,11 +655,13 @@ __global__ void __launch_bounds__(512, 1) kd_seq_bwd(const MafImg g, const DeepA
             deep_stage(sm + off[0], F + t.W0t + (size_t)ua * t.ldt, (n * t.ldt) >> 2);
         }
         __syncthreads();
-        for (int l = L - 1; l >= 0; --l) {
+#pragma unroll
+        for (int l = RABI_MAXL - 1; l >= 0; --l) {
+            if (l >= L) continue;
             const int ua = M[t.grp[l] + j], ub = M[t.grp[l] + j + 1];
             if (ub <= ua) continue;
             const uint32_t* bw = deep_bits(a, g, 0, k, l, th.col);
-            const ActBuf<2> in = l == L - 1 ? ob : h[l + 1];
+            const ActBuf<2> in = l == L - 1 ? ob : h[l + 1 < RABI_MAXL ? l + 1 : l];
             const int va4 = r0[l + 1], vb4 = l == L - 1 ? Rp : ((g.H[l + 1] + 3) & ~3);
             // strip row r holds consumer row r0 + r: shift the base so that the absolute row index works
             const float* S = sm + off[l + 1] - (size_t)va4 * gw[l];
@@ -686,6 +719,20 @@ __global__ void __launch_bounds__(512, 1) kd_seq_bwd(const MafImg g, const DeepA
 #pragma unroll
     for (int jj = 0; jj < DP; ++jj)
         if (jj < D) DV(SU, M[t.perm + jj]) = DV(TC, jj);
+}
+
+// LOGPROB: theta -> chain slot v_K;   RSAMPLE: v_K -> theta_out, log q(own sample) -> diff
+__global__ void kd_load_theta(const MafImg g, const DeepArgs a) {
+    const DeepThread th = deep_thread(a);
+    const int D = g.D, K = g.K;
+    for (int d = 0; d < D; ++d) DV(K, d) = th.live ? a.z[(size_t)th.p * D + d] : 0.f;
+}
+__global__ void kd_store_theta(const MafImg g, const DeepArgs a) {
+    const DeepThread th = deep_thread(a);
+    const int D = g.D, K = g.K;
+    if (!th.live) return;
+    for (int d = 0; d < D; ++d) a.theta_out[(size_t)th.p * D + d] = DV(K, d);
+    if (a.diff) a.diff[th.p] = a.lp[th.col];
 }
 
 #undef DV

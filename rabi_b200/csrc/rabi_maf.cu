@@ -838,6 +838,8 @@ extern "C" double rabi_fma_peak_tflops(int device, int repeats) {
 
 template <int MODE>
 static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st);  // defined below
+static int launch_deep(rabi_maf* h, const DeepArgs& a, int mode, cudaStream_t st);
+static int env_int(const char* name, int dflt);
 
 extern "C" int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const float* theta_dev, int S, int B,
                                      float* logp_dev, rabi_stream_t s) {
@@ -856,7 +858,16 @@ extern "C" int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const fl
         fa.diff = logp_dev;
         fa.S = S;
         fa.B = B;
-        int rc = launch_fast<FAST_LOGPROB>(h, fa, (cudaStream_t)s);
+        int rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_LOGPROB>(h, fa, (cudaStream_t)s);
+        if (rc != 2) return rc;
+        DeepArgs da = {};
+        da.A_p = A_dev;
+        da.A_q = A_dev;
+        da.z = theta_dev;
+        da.diff = logp_dev;
+        da.S = S;
+        da.B = B;
+        rc = launch_deep(h, da, DEEP_LOGPROB, (cudaStream_t)s);
         if (rc != 2) return rc;
     }
     return launch_pairs<MODE_LOGPROB>(h, a, (cudaStream_t)s);
@@ -881,7 +892,17 @@ extern "C" int rabi_maf_rsample_fwd(rabi_maf_t* h, const float* A_dev, const flo
         fa.diff = logq_dev;
         fa.S = S;
         fa.B = B;
-        int rc = launch_fast<FAST_RSAMPLE>(h, fa, (cudaStream_t)s);
+        int rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_RSAMPLE>(h, fa, (cudaStream_t)s);
+        if (rc != 2) return rc;
+        DeepArgs da = {};
+        da.A_p = A_dev;
+        da.A_q = A_dev;
+        da.z = z_dev;
+        da.theta_out = theta_dev;
+        da.diff = logq_dev;
+        da.S = S;
+        da.B = B;
+        rc = launch_deep(h, da, DEEP_RSAMPLE, (cudaStream_t)s);
         if (rc != 2) return rc;
     }
     return launch_pairs<MODE_RSAMPLE>(h, a, (cudaStream_t)s);
@@ -1056,7 +1077,7 @@ static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaSt
     CU_OK(h, cudaFuncSetAttribute(kd_full_bwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(full * 4)));
     CU_OK(h, cudaFuncSetAttribute(kd_seq_bwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(seqb * 4)));
     // batches: at most one CTA of <= Tmax threads per SM, every SM gets the same number of pairs
-    const int Tmax = std::max(64, std::min(512, env_int("RABI_DEEP_T", 512) & ~31));
+    const int Tmax = std::max(64, std::min(384, env_int("RABI_DEEP_T", 384) & ~31));  // __launch_bounds__ of kd_*
     const long long cap = (long long)h->sm_count * Tmax;
     const long long nbatch = (N + cap - 1) / cap;
     const int nmax = (int)((N + nbatch - 1) / nbatch);
@@ -1091,8 +1112,8 @@ static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaSt
     a.Np = Np;
     a.Hq = Hq;
     a.Oq = Oq;
-    a.record = mode == DEEP_GRAD;
-    const bool prof = h->profiling && mode == DEEP_GRAD;
+    a.record = mode == DEEP_GRAD || mode == DEEP_FKL;
+    const bool prof = h->profiling && a.record;
     if (prof) {
         if (h->prof_used == h->prof_events.size()) {
             cudaEvent_t e0, e1;
@@ -1106,19 +1127,33 @@ static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaSt
         a.p0 = p0;
         a.n = (int)std::min<long long>(nmax, N - p0);
         const int grid = (a.n + T - 1) / T;
-        for (int k = 0; k < K; ++k) {
-            kd_seq_fwd<DP><<<grid, T, seqf * 4, st>>>(g, a, k);
+        if (mode == DEEP_LOGPROB) {
+            kd_load_theta<<<grid, T, 0, st>>>(g, a);
             LAUNCH_CHECK(h);
+        } else {
+            DeepArgs as = a;
+            if (mode == DEEP_FKL) as.record = 0;  // the sampling pass is not differentiated
+            for (int k = 0; k < K; ++k) {
+                kd_seq_fwd<DP><<<grid, T, seqf * 4, st>>>(g, as, k);
+                LAUNCH_CHECK(h);
+            }
+        }
+        if (mode == DEEP_RSAMPLE) {
+            kd_store_theta<<<grid, T, 0, st>>>(g, a);
+            LAUNCH_CHECK(h);
+            continue;
         }
         for (int k = K - 1; k >= 0; --k) {
             kd_full_fwd<DP><<<grid, T, full * 4, st>>>(g, a, k, mode);
             LAUNCH_CHECK(h);
         }
-        if (mode == DEEP_GRAD) {
+        if (mode == DEEP_GRAD || mode == DEEP_FKL) {
             for (int k = 0; k < K; ++k) {
-                kd_full_bwd<DP><<<grid, T, full * 4, st>>>(g, a, k);
+                kd_full_bwd<DP><<<grid, T, full * 4, st>>>(g, a, k, mode == DEEP_FKL);
                 LAUNCH_CHECK(h);
             }
+        }
+        if (mode == DEEP_GRAD) {
             for (int k = K - 1; k >= 0; --k) {
                 kd_seq_bwd<DP><<<grid, T, seqb * 4, st>>>(g, a, k);
                 LAUNCH_CHECK(h);
@@ -1207,8 +1242,22 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
     if (forward_kl) {  // KL(target || q(.|x+delta)): sample from the target's projection, differentiate the density pass
         fa.A_p = A_q;
         fa.A_q = A_p;
-        rc = launch_fast<FAST_FKL>(h, fa, st);
-        if (rc == 2) return fail(h, "the forward-KL attack loss is only available on the fast path (two hidden layers, D <= 12)");
+        rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_FKL>(h, fa, st);
+        if (rc == 2) {
+            CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
+            DeepArgs da = {};
+            da.A_p = A_q;   // samples come from the fixed target
+            da.A_q = A_p;   // the density pass under x + delta is the differentiated one
+            da.z = z;
+            da.diff = kl ? diff : nullptr;
+            da.gA = gA;
+            da.S = S;
+            da.B = B;
+            da.w = inv_B / (float)S;
+            rc = launch_deep(h, da, DEEP_FKL, st);
+            if (rc == 2) return fail(h, "the forward-KL attack loss needs the fast or the deep path (2..4 hidden layers, D <= 32)");
+            if (rc == 0) rc = 3;
+        }
     } else {
         rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_GRAD>(h, fa, st);
     }

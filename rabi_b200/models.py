@@ -230,6 +230,31 @@ class MAFPosterior(Distribution):
         return lp
 
 
+def _map_transform_tensors(obj, fn, _seen=None):
+    """Apply ``fn`` to every tensor held by a (possibly composed) torch.distributions transform, in place."""
+    if obj is None:
+        return
+    _seen = set() if _seen is None else _seen
+    if id(obj) in _seen:
+        return
+    _seen.add(id(obj))
+    if isinstance(obj, (list, tuple)):
+        for o in obj:
+            _map_transform_tensors(o, fn, _seen)
+        return
+    if not isinstance(obj, (Transform, constraints.Constraint)):
+        return
+    for name, val in list(vars(obj).items()):
+        if name == "_inv":
+            continue
+        if isinstance(val, Tensor):
+            setattr(obj, name, fn(val))
+        elif name == "_cached_x_y":
+            obj._cached_x_y = (None, None)
+        elif isinstance(val, (Transform, constraints.Constraint, list, tuple)):
+            _map_transform_tensors(val, fn, _seen)
+
+
 # ----------------------------------------------------------------------------------------------- model
 class InverseAffineAutoregressiveModel(nn.Module):
     """Masked autoregressive flow posterior ("MAF": fast density, sequential sampling) on sm_100a kernels.
@@ -303,6 +328,9 @@ class InverseAffineAutoregressiveModel(nn.Module):
         out = super()._apply(fn, *a, **k)
         self._engine = None
         self.__dict__.pop("_ag_struct", None)
+        # the output transform is not a module: move its tensors along (the reference's ``to`` does the same through
+        # ``move_all_tensor_to_device``, models/base.py:365-382)
+        _map_transform_tensors(self._output_transform, fn)
         return out
 
     def load_state_dict(self, state_dict, *a, **k):

@@ -198,7 +198,7 @@ def test_size_independent_properties_at_config2_scale(dev):
     assert float(kl_adv.mean()) > float(kl_rand.mean())  # the attack beats a random direction of the same norm
 
 
-@pytest.mark.parametrize("shape", ["gaussian_linear", "lotka_volterra"])
+@pytest.mark.parametrize("shape", ["gaussian_linear", "lotka_volterra", "pyloric"])
 def test_forward_kl_attack_vs_oracle(shape, dev):
     """ForwardKLLoss as the attack loss (the default of config/eval_rob/attack/l2pgd.yaml):
     gradient of mean_B KL(q(.|x) || q(.|x~)) w.r.t. x~ and the L2-PGD trajectory, against the live oracle."""
@@ -400,6 +400,14 @@ def test_deep_path_matches_reference_fixtures(case, dev, force_deep):
         xa = atk.perturb(x, delta_init=p["delta0"].to(dev))
     assert_trajectories_match(xa.cpu() - g["x"], p["x_adv_5"] - g["x"], RTOL)
     assert model.engine().launches > launches0
+    # the single-chain modes: density of given theta, sampling (+ free log-density)
+    with torch.no_grad():
+        assert rel_err(model(x).log_prob(g["theta"].to(dev)), g["log_prob"]) < RTOL
+        with noise.injected([g["z_rsample"]]):
+            qq = model(x)
+            th = qq.rsample((4,))
+            lp_own = qq.log_prob(th)
+    assert rel_err(th, g["rsample"]) < RTOL and rel_err(lp_own, g["rsample_log_prob"]) < RTOL
 
 
 def test_deep_path_equals_generic_kernel_across_batches(dev):
