@@ -331,12 +331,16 @@ def main():
     except Exception:
         pass
     traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_fast_traffic.json")))["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    on_chip = len(w["hidden"]) == 2 and w["D"] <= 12  # k_fast holds the per-pair state on chip; deeper / wider: kd_*
+    if args.workload == "lotka_volterra_l2pgd_rkl":
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k_fast_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    kernel_name = ("k_fast<GRAD> (per-pair rKL forward + reverse, one launch per PGD iteration)" if on_chip else
+                   f"kd_seq_fwd/kd_full_fwd/kd_full_bwd/kd_seq_bwd ({4 * w['K']} launches per PGD iteration, timed as a group)")
     roofline = {
-        "bound": "fp32_fma", "kernel": "k_fast<GRAD> (per-pair rKL forward + reverse, one launch per PGD iteration)",
+        "bound": "fp32_fma", "kernel": kernel_name,
         "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s",
         "frac": (achieved / fma_peak) if (achieved and fma_peak > 0) else None, "traffic": traffic,
         "algorithmic_bytes_per_launch": int(4 * (w["rows"] * w["S_att"] * w["D"] + 3 * w["K"] * w["hidden"][0] * w["rows"])),

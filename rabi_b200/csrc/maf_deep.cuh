@@ -137,6 +137,117 @@ __device__ __forceinline__ void gtdot_block(const float* __restrict__ W, int ld,
 
 // DEEP_FKL: forward-KL attack loss KL(target || q(.|x+delta)): samples from the fixed target (A_p), gradient through the
 // density pass only (d/dA_q, emitted by kd_full_bwd).  DEEP_LOGPROB / DEEP_RSAMPLE: one chain only.
+// ---- sequential passes: staged weights at COMPILE-TIME strides, zero-padded to whole batches -----------------------
+// The staged rows are zero beyond the prefix / group and the scratch vectors carry slack (DEEP_SLACK floats), so the
+// loops below run over whole batches of 16 inputs without clamps or predicates, every shared-memory address is
+// base + immediate, and the next batch of the scratch vector is always in flight.
+constexpr int DEEP_SLD = 256;   // row stride (floats) of staged weight rows   => hidden widths <= 256
+constexpr int DEEP_SW = 16;     // row stride of staged column strips (one strip = up to 16 producer units)
+constexpr int DEEP_SLACK = 36;  // readable floats past the padded width of every scratch vector
+
+//   out[c] = sum_{i<e16} W[c*STRIDE + i] * x[i]            (e16 multiple of 16; W zero beyond the prefix)
+// One batch (16 inputs) of look-ahead, fetched unconditionally: the last batch over-reads 16 floats of slack.  (A deeper
+// ring with guarded loads was measured slower: the guards serialise the schedule.)
+template <int NR, int STRIDE>
+__device__ __forceinline__ void gdotz(const float* __restrict__ W, int e16, const ActBuf<2>& x, float (&out)[NR]) {
+    float2 acc[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = make_float2(0.f, 0.f);
+    float4 cur[4], nxt[4];
+    const float* xp = x.p;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        cur[q] = *reinterpret_cast<const float4*>(xp);
+        xp += x.q;
+    }
+    for (int i = 0; i < e16; i += 16, W += 16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            nxt[q] = *reinterpret_cast<const float4*>(xp);
+            xp += x.q;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 h = cur[q];
+#pragma unroll
+            for (int c = 0; c < NR; ++c) {
+                const float4 w = *reinterpret_cast<const float4*>(W + c * STRIDE + 4 * q);
+                acc[c] = ffma2(make_float2(w.x, w.y), make_float2(h.x, h.y), acc[c]);
+                acc[c] = ffma2(make_float2(w.z, w.w), make_float2(h.z, h.w), acc[c]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) out[c] = acc[c].x + acc[c].y;
+}
+//   out[c] = sum_{r<n16} S[r*STRIDE + c] * x[v0 + r]        (n16 multiple of 16, v0 multiple of 4; S zero where masked)
+template <int NC, int STRIDE>
+__device__ __forceinline__ void gtdotz(const float* __restrict__ S, int v0, int n16, const ActBuf<2>& x, float (&out)[NC]) {
+    float2 acc[NC / 2];
+#pragma unroll
+    for (int c = 0; c < NC / 2; ++c) acc[c] = make_float2(0.f, 0.f);
+    float4 cur[4], nxt[4];
+    const float* xp = x.p + (size_t)(v0 >> 2) * x.q;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        cur[q] = *reinterpret_cast<const float4*>(xp);
+        xp += x.q;
+    }
+    for (int r = 0; r < n16; r += 16, S += 16 * STRIDE) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            nxt[q] = *reinterpret_cast<const float4*>(xp);
+            xp += x.q;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 g4 = cur[q];
+#pragma unroll
+            for (int dv = 0; dv < 4; ++dv) {
+                const float gv = dv == 0 ? g4.x : dv == 1 ? g4.y : dv == 2 ? g4.z : g4.w;
+                const float2 gg = make_float2(gv, gv);
+#pragma unroll
+                for (int cc = 0; cc < NC / 4; ++cc) {
+                    const float4 w = *reinterpret_cast<const float4*>(S + (4 * q + dv) * STRIDE + 4 * cc);
+                    acc[2 * cc] = ffma2(make_float2(w.x, w.y), gg, acc[2 * cc]);
+                    acc[2 * cc + 1] = ffma2(make_float2(w.z, w.w), gg, acc[2 * cc + 1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+    }
+#pragma unroll
+    for (int c = 0; c < NC / 2; ++c) {
+        out[2 * c] = acc[c].x;
+        out[2 * c + 1] = acc[c].y;
+    }
+}
+// dst[r][0..e16) (row stride DEEP_SLD) = src[(r0 + r)*ld + 0..e16) for r < n, zero for r in [n, n8) and columns >= ld
+__device__ __forceinline__ void deep_stage_rows(float* dst, const float* __restrict__ src, int ld, int r0, int n, int n8,
+                                                int e16) {
+    const int q = e16 >> 2;
+    for (int i = threadIdx.x; i < n8 * q; i += blockDim.x) {
+        const int r = i / q, c4 = i - r * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n && 4 * c4 < ld) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * ld) + c4);
+        *reinterpret_cast<float4*>(dst + (size_t)r * DEEP_SLD + 4 * c4) = v;
+    }
+}
+// strip[r][0..16) (row stride DEEP_SW) = src[(v0 + r)*ld + c0 .. c0+16) for v0 + r < nrows_src and column < ld, else 0
+__device__ __forceinline__ void deep_stage_strip16(float* dst, const float* __restrict__ src, int ld, int v0, int n16,
+                                                   int nrows_src, int c0) {
+    for (int i = threadIdx.x; i < n16 * 4; i += blockDim.x) {
+        const int r = i >> 2, c4 = i & 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v0 + r < nrows_src && c0 + 4 * c4 < ld)
+            v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(v0 + r) * ld + c0) + c4);
+        reinterpret_cast<float4*>(dst)[i] = v;
+    }
+}
+
 enum DeepMode { DEEP_FWD = 0, DEEP_GRAD = 1, DEEP_FKL = 2, DEEP_LOGPROB = 3, DEEP_RSAMPLE = 4 };
 
 struct DeepArgs {
@@ -279,30 +390,41 @@ __global__ void __launch_bounds__(384, 1) kd_seq_fwd(const MafImg g, const DeepA
         bacc[l].on = a.record != 0;
     }
     for (int j = 0; j < D; ++j) {
-        // ---- stage the rows of degree j: [W0t | W[1] | ... | W[L-1] | Wo rows j, D+j]
-        int off[RABI_MAXL + 1];
+        // ---- stage the rows of degree j: [W0t rows | W[1] | ... | W[L-1] | Wo rows j, D+j]; hidden / output rows at the
+        // fixed stride DEEP_SLD, groups padded with zero rows to a multiple of 8, prefixes to a multiple of 16
+        int off[RABI_MAXL + 1], e16[RABI_MAXL + 1];
         {
             int o = 0;
 #pragma unroll
             for (int l = 0; l < RABI_MAXL; ++l) {
                 off[l] = o;
+                e16[l] = 0;
                 if (l < L) {
                     const int n = M[t.grp[l] + j + 1] - M[t.grp[l] + j];
-                    o += n * (l == 0 ? t.ldt : t.ld[l]);
+                    if (l == 0) {
+                        o += n * t.ldt;
+                    } else {
+                        e16[l] = (M[t.grp[l - 1] + j + 1] + 15) & ~15;
+                        o += ((n + 7) & ~7) * DEEP_SLD;
+                    }
                 }
             }
             off[RABI_MAXL] = o;  // output rows follow the last layer's rows
+            e16[RABI_MAXL] = (M[t.grp[L - 1] + j + 1] + 15) & ~15;
         }
         __syncthreads();
+        {
+            const int r0 = M[t.grp[0] + j], n = M[t.grp[0] + j + 1] - r0;
+            deep_stage(sm + off[0], F + t.W0t + (size_t)r0 * t.ldt, (n * t.ldt) >> 2);
+        }
 #pragma unroll
-        for (int l = 0; l < RABI_MAXL; ++l) {
+        for (int l = 1; l < RABI_MAXL; ++l) {
             if (l >= L) continue;
             const int r0 = M[t.grp[l] + j], n = M[t.grp[l] + j + 1] - r0;
-            const int ld = l == 0 ? t.ldt : t.ld[l];
-            deep_stage(sm + off[l], F + (l == 0 ? t.W0t : t.W[l]) + (size_t)r0 * ld, (n * ld) >> 2);
+            deep_stage_rows(sm + off[l], F + t.W[l], t.ld[l], r0, n, (n + 7) & ~7, e16[l]);
         }
-        deep_stage(sm + off[RABI_MAXL], F + t.Wo + (size_t)j * t.ldo, t.ldo >> 2);
-        deep_stage(sm + off[RABI_MAXL] + t.ldo, F + t.Wo + (size_t)(D + j) * t.ldo, t.ldo >> 2);
+        deep_stage_rows(sm + off[RABI_MAXL], F + t.Wo, t.ldo, j, 1, 1, e16[RABI_MAXL]);
+        deep_stage_rows(sm + off[RABI_MAXL] + DEEP_SLD, F + t.Wo, t.ldo, D + j, 1, 1, e16[RABI_MAXL]);
         __syncthreads();
         // ---- layer 0
         {
@@ -328,12 +450,10 @@ __global__ void __launch_bounds__(384, 1) kd_seq_fwd(const MafImg g, const DeepA
         for (int l = 1; l < RABI_MAXL; ++l) {
             if (l >= L) continue;
             const int va = M[t.grp[l] + j], vb = M[t.grp[l] + j + 1];
-            const int e4 = (M[t.grp[l - 1] + j + 1] + 3) & ~3;
-            const int ld = t.ld[l];
             for (int v0 = va; v0 < vb; v0 += 8) {
                 const int nv = min(8, vb - v0);
                 float o[8];
-                gdot_block<8>(sm + off[l] + (size_t)(v0 - va) * ld, ld, nv - 1, e4, h[l - 1], o);
+                gdotz<8, DEEP_SLD>(sm + off[l] + (v0 - va) * DEEP_SLD, e16[l], h[l - 1], o);
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     if (c < nv) {
@@ -346,9 +466,8 @@ __global__ void __launch_bounds__(384, 1) kd_seq_fwd(const MafImg g, const DeepA
         }
         // ---- output position j, then y_j = (z_j - m_j) exp(-clamp(s_j))
         {
-            const int e4 = (M[t.grp[L - 1] + j + 1] + 3) & ~3;
             float o[2];
-            gdot_block<2>(sm + off[RABI_MAXL], t.ldo, 1, e4, deep_act(a, L - 1, th.col), o);
+            gdotz<2, DEEP_SLD>(sm + off[RABI_MAXL], e16[RABI_MAXL], deep_act(a, L - 1, th.col), o);
             const float m = o[0] + __ldg(F + t.bo + j), s = o[1] + __ldg(F + t.bo + D + j);
             const float zj = DV(SV + k, M[t.perm + j]);
             const float sh = fminf(fmaxf(s, g.lo), g.hi);
@@ -625,30 +744,37 @@ __global__ void __launch_bounds__(384, 1) kd_seq_bwd(const MafImg g, const DeepA
             ob.st1(D + j, fmaf(-ybj, yj, w));
             DV(TC, j) = zbj;
         }
-        // ---- stage: column strips of the degree-j units of every layer (+ the layer-0 rows for the theta push)
-        int off[RABI_MAXL + 1], c0[RABI_MAXL], gw[RABI_MAXL], r0[RABI_MAXL + 1];
+        // ---- stage: for the degree-j units of every layer (producers) the column strips of their consumer matrix
+        // (Wo for the last hidden layer, W[l+1] otherwise), 16 columns per strip at stride DEEP_SW, consumer rows from
+        // r0 (first row that can see the group, rounded down to 4) in whole batches of 16, zero beyond the matrix;
+        // plus the layer-0 rows of the group for the push into the theta cotangents
+        int off[RABI_MAXL + 1], c0[RABI_MAXL], nblk[RABI_MAXL], r0[RABI_MAXL], n16[RABI_MAXL];
         {
             int o = 0;
 #pragma unroll
             for (int l = RABI_MAXL - 1; l >= 0; --l) {
+                off[l + 1] = o;
+                c0[l] = nblk[l] = r0[l] = n16[l] = 0;
                 if (l >= L) continue;
                 const int ua = M[t.grp[l] + j], ub = M[t.grp[l] + j + 1];
                 c0[l] = ua & ~3;
-                gw[l] = ub > ua ? ((ub + 3) & ~3) - c0[l] : 0;
-                // consumer rows: output rows 0..Rp for l = L-1, rows >= grp[l+1][j] of W[l+1] otherwise
-                r0[l + 1] = l == L - 1 ? 0 : (M[t.grp[l + 1] + j] & ~3);
-                const int nr = l == L - 1 ? Rp : ((g.H[l + 1] + 3) & ~3) - r0[l + 1];
-                off[l + 1] = o;
-                o += nr * gw[l];
+                nblk[l] = ub > ua ? (ub - c0[l] + 15) >> 4 : 0;
+                r0[l] = l == L - 1 ? 0 : (M[t.grp[l + 1] + j] & ~3);
+                const int rows = l == L - 1 ? Rp : ((g.H[l + 1] + 3) & ~3);
+                n16[l] = (max(rows - r0[l], 0) + 15) & ~15;
+                o += nblk[l] * n16[l] * DEEP_SW;
             }
             off[0] = o;  // layer-0 rows of the group: [n0][ldt]
         }
         __syncthreads();
 #pragma unroll
         for (int l = RABI_MAXL - 1; l >= 0; --l) {
-            if (l >= L || gw[l] == 0) continue;
-            if (l == L - 1) deep_stage_strip(sm + off[l + 1], F + t.Wo, t.ldo, 0, Rp, c0[l], gw[l]);
-            else deep_stage_strip(sm + off[l + 1], F + t.W[l + 1], t.ld[l + 1], r0[l + 1], ((g.H[l + 1] + 3) & ~3) - r0[l + 1], c0[l], gw[l]);
+            if (l >= L) continue;
+            const float* src = l == L - 1 ? F + t.Wo : F + t.W[l + 1];
+            const int ld = l == L - 1 ? t.ldo : t.ld[l + 1];
+            const int rows = l == L - 1 ? Rp : ((g.H[l + 1] + 3) & ~3);
+            for (int bk = 0; bk < nblk[l]; ++bk)
+                deep_stage_strip16(sm + off[l + 1] + bk * n16[l] * DEEP_SW, src, ld, r0[l], n16[l], rows, c0[l] + 16 * bk);
         }
         {
             const int ua = M[t.grp[0] + j], n = M[t.grp[0] + j + 1] - ua;
@@ -662,11 +788,8 @@ __global__ void __launch_bounds__(384, 1) kd_seq_bwd(const MafImg g, const DeepA
             if (ub <= ua) continue;
             const uint32_t* bw = deep_bits(a, g, 0, k, l, th.col);
             const ActBuf<2> in = l == L - 1 ? ob : h[l + 1 < RABI_MAXL ? l + 1 : l];
-            const int va4 = r0[l + 1], vb4 = l == L - 1 ? Rp : ((g.H[l + 1] + 3) & ~3);
-            // strip row r holds consumer row r0 + r: shift the base so that the absolute row index works
-            const float* S = sm + off[l + 1] - (size_t)va4 * gw[l];
-            auto emit = [&](int cc, int c, float val) {
-                const int u = c0[l] + cc + c;
+            auto emit = [&](int cbase, int c, float val) {
+                const int u = cbase + c;
                 if (u >= ua && u < ub) {
                     const bool on = (bw[(size_t)(u >> 5) * a.Np] >> (u & 31)) & 1u;
                     const float gv = on ? val : 0.f;
@@ -686,32 +809,30 @@ __global__ void __launch_bounds__(384, 1) kd_seq_bwd(const MafImg g, const DeepA
                     }
                 }
             };
-            for (int cc = 0; cc < gw[l];) {  // the whole strip in as few passes over the consumer vector as possible
-                const int left = gw[l] - cc;
-                if (left >= 16) {
+            for (int bk = 0; bk < nblk[l]; ++bk) {
+                const float* S = sm + off[l + 1] + bk * n16[l] * DEEP_SW;
+                const int cbase = c0[l] + 16 * bk;
+                const int width = ((ub + 3) & ~3) - cbase;  // columns of this strip that hold units of the group
+                if (width > 12) {
                     float o[16];
-                    gtdot_block<16>(S + cc, gw[l], va4, vb4, in, o);
+                    gtdotz<16, DEEP_SW>(S, r0[l], n16[l], in, o);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) emit(cc, c, o[c]);
-                    cc += 16;
-                } else if (left == 12) {
+                    for (int c = 0; c < 16; ++c) emit(cbase, c, o[c]);
+                } else if (width > 8) {
                     float o[12];
-                    gtdot_block<12>(S + cc, gw[l], va4, vb4, in, o);
+                    gtdotz<12, DEEP_SW>(S, r0[l], n16[l], in, o);
 #pragma unroll
-                    for (int c = 0; c < 12; ++c) emit(cc, c, o[c]);
-                    cc += 12;
-                } else if (left >= 8) {
+                    for (int c = 0; c < 12; ++c) emit(cbase, c, o[c]);
+                } else if (width > 4) {
                     float o[8];
-                    gtdot_block<8>(S + cc, gw[l], va4, vb4, in, o);
+                    gtdotz<8, DEEP_SW>(S, r0[l], n16[l], in, o);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) emit(cc, c, o[c]);
-                    cc += 8;
+                    for (int c = 0; c < 8; ++c) emit(cbase, c, o[c]);
                 } else {
                     float o[4];
-                    gtdot_block<4>(S + cc, gw[l], va4, vb4, in, o);
+                    gtdotz<4, DEEP_SW>(S, r0[l], n16[l], in, o);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) emit(cc, c, o[c]);
-                    cc += 4;
+                    for (int c = 0; c < 4; ++c) emit(cbase, c, o[c]);
                 }
             }
         }

@@ -1055,13 +1055,15 @@ static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaSt
     for (int k = 0; k < K; ++k) {
         const TImg& t = g.t[k];
         for (int j = 0; j < D; ++j) {
-            size_t f = 2 * (size_t)t.ldo, b = 0;
+            size_t f = 2 * (size_t)DEEP_SLD, b = 0;
             for (int l = 0; l < L; ++l) {
                 const int ua = M[t.grp[l] + j], ub = M[t.grp[l] + j + 1];
-                f += (size_t)(ub - ua) * (l == 0 ? t.ldt : t.ld[l]);
-                const int gw = ub > ua ? r4(ub) - (ua & ~3) : 0;
-                const int nr = l == L - 1 ? r4(2 * D) : r4(h->H[l + 1]) - (M[t.grp[l + 1] + j] & ~3);
-                b += (size_t)nr * gw;
+                f += l == 0 ? (size_t)(ub - ua) * t.ldt : (size_t)((ub - ua + 7) & ~7) * DEEP_SLD;
+                const int nblk = ub > ua ? (ub - (ua & ~3) + 15) >> 4 : 0;
+                const int rows = l == L - 1 ? r4(2 * D) : r4(h->H[l + 1]);
+                const int r0 = l == L - 1 ? 0 : (M[t.grp[l + 1] + j] & ~3);
+                const int n16 = (std::max(rows - r0, 0) + 15) & ~15;
+                b += (size_t)nblk * n16 * DEEP_SW;
                 if (l == 0) b += (size_t)(ub - ua) * t.ldt;
             }
             seqf = std::max(seqf, f);
@@ -1086,7 +1088,7 @@ static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaSt
     const int grid_max = (nmax + T - 1) / T;
     const int Np = grid_max * T;
     const int WL = (g.Hmax + 31) / 32;
-    const int Hq = (r4(g.Hmax) + 4) / 4, Oq = (r4(2 * D) + 4) / 4;
+    const int Hq = (r4(g.Hmax) + DEEP_SLACK) / 4, Oq = (r4(2 * D) + DEEP_SLACK) / 4;
     const size_t n_act = (size_t)L * Hq * Np * 4, n_ob = (size_t)Oq * Np * 4, n_vec = (size_t)deep_nvec(K) * D * Np;
     const size_t n_bits = (size_t)2 * K * L * WL * Np, n_lp = (size_t)2 * Np;
     const size_t bytes = (n_act + n_ob + n_vec + n_bits + n_lp) * sizeof(float);
@@ -1172,7 +1174,7 @@ static int launch_deep(rabi_maf* h, const DeepArgs& a, int mode, cudaStream_t st
     const long long N = (long long)a.S * a.B;
     if (N <= 0) return 0;
     if (env_int("RABI_DISABLE_DEEP", 0)) return 2;
-    if (h->L < 2 || h->D > 32) return 2;
+    if (h->L < 2 || h->D > 32 || ((h->img.Hmax + 15) & ~15) > DEEP_SLD) return 2;
     if (h->D <= 4) return launch_deep_dp<4>(h, a, mode, N, st);
     if (h->D <= 12) return launch_deep_dp<12>(h, a, mode, N, st);
     return launch_deep_dp<32>(h, a, mode, N, st);
