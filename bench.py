@@ -204,6 +204,126 @@ def run_reference_arm(args, w, wname):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f rows
+def run_next_rows(args):
+    """Measurements for the SURVEY 8f "next" rows at lotka_volterra shapes on ONE GPU, each beside the oracle port of the
+    reference path timed on the host cores (bounded samples).  Prints its own JSON document (not the bench line)."""
+    from oracle import rbi_oracle as O
+
+    from rabi_b200 import _lib
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.defenses import L2PGDAdversarialTraining, L2PGDTrades, L2UniformNoiseTraining
+    from rabi_b200.loss import ForwardKLLoss, NLLLoss
+    from rabi_b200.metric import ExpectedCoverageMetric, ForwardKLRobMetric, NegativeLogLikelihoodMetric
+    from rabi_b200.models import ZScoreLayer
+
+    w = dict(WORKLOADS["lotka_volterra_l2pgd_rkl"])
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    _lib.build()
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = make_weights(w)
+    state = state_cpu_with_zscore({k: v.clone() for k, v in model.state_dict().items()}, w)
+    model.embedding_net = torch.nn.Sequential(ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])), model.embedding_net)
+    ref = O.OracleMAF(w["dx"], w["D"], hidden_dims=w["hidden"], num_transforms=w["K"], shuffle=False,
+                      embedding_net=torch.nn.Sequential(O.ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])),
+                                                        torch.nn.Identity()),
+                      log_scale_min_clip=-7, log_scale_max_clip=5, stable=False)
+    ref.load_state_dict(state)
+    ref.eval()
+    model = model.to(dev).eval()
+    x = make_rows(w, 0, w["rows"])
+    xd = x.to(dev)
+    eps = float(0.5 * x.std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+    out = {"shapes": "lotka_volterra", "host_threads": threads, "rows": w["rows"]}
+
+    def gpu_ms(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def cpu_s(fn):
+        t0 = time.perf_counter()
+        fn()
+        return time.perf_counter() - t0
+
+    # f1: forward-KL attack + ForwardKLRobMetric
+    atk = L2PGDAttack(model, loss_fn=ForwardKLLoss(mc_samples=w["S_att"]), eps=eps, nb_iter=w["nb_iter"],
+                      eps_iter=eps / 10, clip_min=cmin, clip_max=cmax)
+    met = ForwardKLRobMetric(model, atk, mc_samples=w["S_eval"], attack_attemps=1, device=dev, batch_size=w["chunk"],
+                             reduction=None)
+
+    def f1():
+        met._cached_x = met._cached_xs_tilde = met._cached_losses = None
+        met._eval(xd)
+
+    ms = gpu_ms(f1, 2)
+    pairs = w["rows"] * pairs_per_row(w)
+    xc = x[: w["chunk"]]
+    it = 5
+    t_att = cpu_s(lambda: O.l2pgd_perturb(ref, xc, O.ForwardKLLoss(mc_samples=w["S_att"]), eps, it, eps / 10, cmin, cmax))
+    t_ev = cpu_s(lambda: O.ForwardKLLoss(mc_samples=w["S_eval"], reduction=None)(ref(xc + 0.01), ref(xc)))
+    cpu_rate = w["chunk"] * pairs_per_row(w) / (t_att / it * w["nb_iter"] + t_ev)
+    out["f1_fkl_attack_and_metric"] = {"gpu_pairs_per_s": pairs / (ms * 1e-3), "gpu_ms": ms, "cpu_pairs_per_s": cpu_rate,
+                                       "cpu_sample": f"{w['chunk']} rows, {it} of {w['nb_iter']} iterations + metric"}
+    # f2: approximation metrics on 10 000 rows (coverage: 1000 posterior samples per row)
+    theta = torch.randn(w["rows"], w["D"])
+    mc = 1000
+    cov = ExpectedCoverageMetric(model, mc_samples=mc, device=dev, batch_size=w["chunk"])
+    ms = gpu_ms(lambda: cov.eval(x, theta))
+    n_cpu = 200
+    t_c = cpu_s(lambda: O.expected_coverage(ref, x[:n_cpu], theta[:n_cpu], mc, torch.linspace(0, 1, 100)))
+    out["f2_expected_coverage"] = {"gpu_samples_per_s": w["rows"] * mc / (ms * 1e-3), "gpu_ms": ms,
+                                   "cpu_samples_per_s": n_cpu * mc / t_c, "cpu_sample": f"{n_cpu} rows x {mc} samples"}
+    nllm = NegativeLogLikelihoodMetric(model, reduction="mean", device=dev)
+    ms = gpu_ms(lambda: nllm.eval(x, theta))
+    t_c = cpu_s(lambda: O.nll_metric(ref, x, theta))
+    out["f2_nll_metric"] = {"gpu_rows_per_s": w["rows"] / (ms * 1e-3), "gpu_ms": ms, "cpu_rows_per_s": w["rows"] / t_c}
+    # f3: training steps, batch 512 (config/defense/l2pgdAdvTrain.yaml, l2noiseAdvTrain.yaml, l2pgdTrades.yaml)
+    B = 512
+    xb, tb = xd[:B], theta[:B].to(dev)
+    model.train()
+    ref.train()
+    std = float(x.std(1).mean())
+    for name, make, cpu_fn in (
+        ("f3_l2pgd_adversarial_training",
+         lambda lf: L2PGDAdversarialTraining(model, lf, eps=0.5 * std, eps_iter=0.1 * std, nb_iter=20),
+         lambda: O.train_loss_with_pre_regularizer(ref, x[:B], theta[:B], lambda xi, ti: (O.l2pgd_perturb(
+             ref, xi, O.ForwardKLLoss(mc_samples=1), 0.5 * std, 20, 0.1 * std).detach(), ti))[0].backward()),
+        ("f3_l2_uniform_noise_training",
+         lambda lf: L2UniformNoiseTraining(model, lf, eps=1.0 * std),
+         lambda: O.train_loss_with_pre_regularizer(ref, x[:B], theta[:B], lambda xi, ti: (
+             O.l2_uniform_noise_perturb(xi, 1.0 * std), ti))[0].backward()),
+        ("f3_l2pgd_trades_fkl",
+         lambda lf: L2PGDTrades(model, lf, eps=0.5 * std, eps_iter=0.1 * std, nb_iter=20, beta=0.1),
+         lambda: O.train_loss_with_regularizer(ref, x[:B], theta[:B], lambda xi, qi, ti: O.trades_regularizer(
+             ref, xi, 0.1, 0.5 * std, 0.1 * std, 20, O.ForwardKLLoss, 1)[0]).backward()),
+    ):
+        lf = NLLLoss(model).train()
+        d = make(lf)
+        d.activate()
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            lf(xb, tb).backward()
+
+        ms = gpu_ms(step, 5)
+        d.deactivate()
+        ref.zero_grad()
+        cpu_fn()
+        t_c = cpu_s(cpu_fn)
+        out[name] = {"gpu_ms_per_step": ms, "cpu_ms_per_step": 1e3 * t_c, "batch": B}
+    print(json.dumps(out), flush=True)
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -214,7 +334,11 @@ def main():
     ap.add_argument("--workload", default="lotka_volterra_l2pgd_rkl", choices=list(WORKLOADS))
     ap.add_argument("--rows", type=int, default=None, help="observations per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--next-rows", action="store_true",
+                    help="measure the SURVEY 8f rows (fKL eval, coverage / NLL metrics, defenses) instead of the bench line")
     args = ap.parse_args()
+    if args.next_rows:
+        return run_next_rows(args)
     w = dict(WORKLOADS[args.workload])
     if args.rows:
         w["rows"] = args.rows
