@@ -40,6 +40,10 @@ WORKLOADS = {
     # BASELINE configs[4], ctx-space variant: h ~ N(0, I_100) given, 12 500 rows per GPU
     "pyloric_ctx_l2pgd_rkl": dict(dx=100, D=31, hidden=[200, 200, 200], K=3, rows=12500, chunk=500, nb_iter=200,
                                   S_att=5, S_eval=256),
+    # x-space variant: raw 2400-sample traces through a stand-in 1-D CNN embedding (torch) -> 100 features;
+    # the PGD gradient chains through the embedding by autograd, the flow runs on the kernels
+    "pyloric_x_l2pgd_rkl": dict(dx=2400, D=31, hidden=[200, 200, 200], K=3, rows=12500, chunk=500, nb_iter=200,
+                                S_att=5, S_eval=256, embed="cnn1d"),
 }
 METRIC = "attacked (x, MC-sample) MAF posterior evals/sec"
 UNIT = "pairs/s"
@@ -50,13 +54,25 @@ def pairs_per_row(w):
 
 
 # ------------------------------------------------------------------------------------------------ model / data
+def make_embedding(w):
+    """Stand-in for sbi's CNNEmbedding (absent): 1-D CNN, dx samples -> 100 summary features."""
+    if w.get("embed") != "cnn1d":
+        return None
+    nn = torch.nn
+    dx = w["dx"]
+    return nn.Sequential(nn.Unflatten(1, (1, dx)), nn.Conv1d(1, 8, 9, stride=4, padding=4), nn.ReLU(),
+                         nn.Conv1d(8, 16, 9, stride=4, padding=4), nn.ReLU(), nn.Flatten(),
+                         nn.Linear(16 * (dx // 16), 100))
+
+
 def make_weights(w, seed=0):
     """state_dict of the MAF (reference layout) + z-score stats + observations; CPU tensors."""
     from rabi_b200.models import InverseAffineAutoregressiveModel
 
     torch.manual_seed(seed)
     m = InverseAffineAutoregressiveModel(w["dx"], w["D"], hidden_dims=w["hidden"], num_transforms=w["K"], shuffle=False,
-                                         log_scale_min_clip=-7, log_scale_max_clip=5, stable=False)
+                                         log_scale_min_clip=-7, log_scale_max_clip=5, stable=False,
+                                         embedding_net=make_embedding(w))
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():  # non-trivial means / log-scales (plain init gives a nearly Gaussian posterior)
         for p in m.parameters():
@@ -137,7 +153,7 @@ def cpu_reference_sample(w, model_state, threads, it_sample=10, seed=0):
     torch.set_num_threads(threads)
     ref = O.OracleMAF(w["dx"], w["D"], hidden_dims=w["hidden"], num_transforms=w["K"], shuffle=False,
                       embedding_net=torch.nn.Sequential(O.ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])),
-                                                        torch.nn.Identity()),
+                                                        make_embedding(w) or torch.nn.Identity()),
                       log_scale_min_clip=-7, log_scale_max_clip=5, stable=False)
     sd = {k: v for k, v in model_state.items()}
     ref.load_state_dict(sd, strict=True)
@@ -368,8 +384,8 @@ def main():
     _lib.build()
 
     model = make_weights(w)
-    state_cpu = {k: v.clone() for k, v in model.state_dict().items()}
     model.embedding_net = torch.nn.Sequential(ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])), model.embedding_net)
+    state_cpu = {k: v.clone() for k, v in model.state_dict().items()}
     flops = algorithmic_flops(model, w)
     model = model.to(dev).eval()
     x_host = make_rows(w, rank, w["rows"]).pin_memory()
@@ -483,7 +499,7 @@ def main():
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sample, _ = cpu_reference_sample(w, state_cpu_with_zscore(state_cpu, w), os.cpu_count() or 1, it_sample=10)
+        v, sample, _ = cpu_reference_sample(w, state_cpu, os.cpu_count() or 1, it_sample=10)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
