@@ -200,12 +200,16 @@ class TradesAdversarialRegularizer(AdditiveRegularizer):
     """beta * D(q(.|x) || q(.|x')) with x' = attack(x)   (clean distribution FIRST)."""
 
     def __init__(self, model: Module, loss_fn: TrainLoss, attack: Attack, reg_loss_fn: Callable, beta: float = 1.0,
-                 reduce: str = "mean", **kwargs):
+                 reduce: str = "mean", cuda_graph: bool = True, **kwargs):
         super().__init__(model, loss_fn, reduce)
         self.attack = attack
         self.reg_loss_fn = reg_loss_fn
         self.beta = beta
         self._regularizer = self._regularizer_attack
+        # ``cuda_graph``: after two eager calls of a batch shape the regulariser and its weight gradient are replayed as
+        # CUDA graphs with the base noise drawn into a static buffer (rabi_b200/graphs.py)
+        self.cuda_graph = cuda_graph
+        self._graphed = None
 
     def _set_algorithm(self, method: str):
         self._regularizer = self._regularizer_attack
@@ -217,6 +221,24 @@ class TradesAdversarialRegularizer(AdditiveRegularizer):
         # ``p.grad`` (an unintended side effect of advertorch's loop).  The fused attack has no weight
         # gradient, so that pollution is NOT reproduced; the regulariser value and its own gradient are identical.
         x_pert = self.attack.perturb(input)
+        from . import noise
+        S = getattr(self.reg_loss_fn, "mc_samples", None)
+        if (self.cuda_graph and S is not None and input.is_cuda and input.dim() == 2 and torch.is_grad_enabled()
+                and noise._queue is None and not input.requires_grad
+                and getattr(self.reg_loss_fn, "reduction", None) == "mean"):
+            if self._graphed is None:
+                from .graphs import GraphedParamFunction
+
+                def reg(x, xp, z):
+                    with noise.injected([z]):
+                        return self.reg_loss_fn(self.model(x), self.model(xp)).reshape(1)
+
+                self._graphed = GraphedParamFunction(self.model, reg)
+            z = noise.standard_normal((int(S), input.shape[0], self.model.output_dim), input.device)
+            if self._graphed.ready((input, x_pert, z)):
+                return self.beta * self._graphed(input, x_pert, z)
+            with noise.injected([z]):
+                return self.beta * self.reg_loss_fn(self.model(input), self.model(x_pert))
         return self.beta * self.reg_loss_fn(self.model(input), self.model(x_pert))
 
 

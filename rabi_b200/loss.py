@@ -188,8 +188,28 @@ class TrainLoss(Loss):
 
 
 class NLLLoss(TrainLoss):
+    """-log q(theta | x) per row (rbi/rbi/loss/train_loss.py:16-29).  ``cuda_graph``: after two eager calls of a batch
+    shape, forward and parameter-gradient computation are replayed as CUDA graphs (rabi_b200/graphs.py)."""
+
+    def __init__(self, model, reduction: Optional[str] = "mean", cuda_graph: bool = True) -> None:
+        super().__init__(model, reduction)
+        self.cuda_graph = cuda_graph
+        self._graphed = None
+
+    def _nll(self, x: Tensor, theta: Tensor) -> Tensor:
+        q = self.model(x)
+        return -q.log_prob(theta.reshape(*(q.batch_shape + q.event_shape)))
+
     def _loss(self, output: Distribution, target: Tensor, input: Tensor) -> Tensor:
         if not isinstance(target, Tensor):
             raise ValueError("This loss function requires events y ~ p(y|x) given as tensors.")
+        if (self.cuda_graph and self.training and torch.is_grad_enabled() and isinstance(output, MAFPosterior)
+                and input.is_cuda and input.dim() == 2 and target.dim() == 2 and not input.requires_grad
+                and not target.requires_grad and noise._queue is None):
+            if self._graphed is None or self._graphed.module is not self.model:
+                from .graphs import GraphedParamFunction
+                self._graphed = GraphedParamFunction(self.model, self._nll)
+            if self._graphed.ready((input, target)):
+                return self._graphed(input, target.to(input.dtype))
         sample_shape = output.batch_shape + output.event_shape
         return -output.log_prob(target.reshape(*sample_shape))

@@ -155,3 +155,46 @@ def test_fim_regularizer_cuda_graph_replay_equals_eager(dev):
         for a, b in zip(*grads):
             assert float((a - b).abs().max()) <= 2e-4 * scale, (step, float((a - b).abs().max()), scale)
     assert regs[0][2]._graphs, "the graph path was not taken"
+
+
+def test_graphed_nll_and_trades_steps_equal_eager_over_optimizer_steps(dev):
+    """rabi_b200/graphs.py: after the two eager warm-up calls of a batch shape, NLLLoss and the TRADES regulariser replay
+    CUDA graphs.  Two copies of a model trained for 6 Adam steps -- one with graphs, one eager -- on identical batches,
+    base noise and attack starts must stay together (graphs see the in-place parameter updates)."""
+    import copy
+
+    from rabi_b200.defenses import L2PGDrKLTrades
+    from rabi_b200.loss import NLLLoss
+
+    g = load_golden("lotka_volterra")
+    m1 = build_product(g, dev, with_output_transform=False).train()
+    m2 = copy.deepcopy(m1).to(dev).train()
+    B = 96
+    gen = torch.Generator().manual_seed(3)
+    x = (torch.randn(B, g["cfg"]["dx"], generator=gen) * g["zs_std"] + g["zs_mean"]).to(dev)
+    th = torch.randn(B, g["cfg"]["D"], generator=gen).to(dev)
+    eps = 0.5 * float(x.std(1).mean())
+    runs = []
+    for m, graph in ((m1, True), (m2, False)):
+        lf = NLLLoss(m, cuda_graph=graph).train()
+        d = L2PGDrKLTrades(m, lf, eps=eps, eps_iter=eps / 5, nb_iter=3, beta=0.1, cuda_graph=graph)
+        d.activate()
+        runs.append((m, lf, d, torch.optim.Adam(m.parameters(), lr=1e-3)))
+    for step in range(6):
+        losses = []
+        for m, lf, d, opt in runs:
+            # same attack start and base noise for both copies: both paths draw from torch's CUDA generator in the same
+            # order and shapes (delta0, attack noise [nb_iter, S, B, D], regulariser noise [S, B, D])
+            torch.manual_seed(100 + step)
+            opt.zero_grad(set_to_none=(step % 2 == 0))
+            loss = lf(x, th)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        assert abs(losses[0] - losses[1]) < 1e-4 * abs(losses[1]), (step, losses)
+    assert runs[0][1]._graphed is not None and runs[0][1]._graphed._graphs, "NLL graph path was not taken"
+    assert runs[0][2]._graphed is not None and runs[0][2]._graphed._graphs, "TRADES graph path was not taken"
+    assert runs[1][1]._graphed is None
+    scale = max(float(p.abs().max()) for p in m2.parameters())
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert float((a - b).abs().max()) <= 2e-4 * scale
