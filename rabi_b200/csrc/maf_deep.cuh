@@ -9,8 +9,9 @@
 //  * the weights a CTA needs next are staged in shared memory once per CTA and read as warp-broadcast 128-bit loads:
 //    a whole layer for the full (density) passes, the rows / column strips of one MADE degree group per step of the
 //    sequential (sampling) passes;
-//  * products are register-blocked over 16 (8) units x 4 inputs with packed fma.rn.f32x2 (dot_block / tdot_block of
-//    maf_fast.cuh on an ActBuf that points into the scratch);
+//  * products are register-blocked over 16 (8) units x 4 inputs with packed fma.rn.f32x2 on scratch vectors, with one
+//    batch of inputs of look-ahead (gdot_block / gtdot_block, and the stride-templated gdotz / gtdotz of the sequential
+//    passes);
 //  * every (transform, pass) is its own launch: 4K launches per attack iteration, state carried by the scratch.
 //
 // Reference arithmetic replaced: as maf_pairs.cuh (ConditionalAutoRegressiveNN._forward, AffineAutoregressive._call /
@@ -319,16 +320,6 @@ __device__ __forceinline__ void deep_stage(float* dst, const float* __restrict__
             if (base + q * T < n4) d[base + q * T] = v[q];
     }
 }
-// column strip: dst[r][0..gw) = src[(r0 + r) * ld + c0 .. c0 + gw)  for r < nr   (c0, gw multiples of 4)
-__device__ __forceinline__ void deep_stage_strip(float* dst, const float* __restrict__ src, int ld, int r0, int nr, int c0,
-                                                 int gw) {
-    const int q = gw >> 2;
-    for (int i = threadIdx.x; i < nr * q; i += blockDim.x) {
-        const int r = i / q, c4 = i - r * q;
-        reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * ld + c0) + c4);
-    }
-}
-
 struct BitAcc {  // ReLU masks of one layer, units arrive in increasing order
     uint32_t w;
     uint32_t* base;  // &bits[slot*WL][col]
