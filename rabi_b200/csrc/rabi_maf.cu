@@ -14,6 +14,7 @@
 #include "maf_pairs.cuh"
 #include "maf_fast.cuh"
 #include "maf_deep.cuh"
+#include "maf_warp.cuh"
 
 using namespace rabi;
 
@@ -347,7 +348,8 @@ extern "C" int rabi_maf_finalize_structure(rabi_maf_t* h) {
     h->n_int = meta.size();
     CU_OK(h, cudaMalloc(&h->f_dev, nf * sizeof(float)));
     CU_OK(h, cudaMemset(h->f_dev, 0, nf * sizeof(float)));
-    CU_OK(h, cudaMalloc(&h->m_dev, meta.size() * sizeof(int)));
+    CU_OK(h, cudaMalloc(&h->m_dev, (meta.size() + 4) * sizeof(int)));  // +4: k_warp stages it in whole quads
+    CU_OK(h, cudaMemset(h->m_dev, 0, (meta.size() + 4) * sizeof(int)));
     CU_OK(h, cudaMemcpy(h->m_dev, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice));
     g.f = h->f_dev;
     g.m = h->m_dev;
@@ -1221,6 +1223,50 @@ extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_
     return 0;
 }
 
+// ---- small batches: one warp per pair (maf_warp.cuh).  Returns 0 = launched, 1 = error, 2 = not applicable.
+template <int MODE>
+static int launch_warp(rabi_maf* h, const PairArgs& a, cudaStream_t st) {
+    const long long N = (long long)a.S * a.B;
+    if (N <= 0) return 0;
+    if (N > env_int("RABI_WARP_MAX_PAIRS", 1024)) return 2;
+    // warps per CTA: about one CTA per SM (every CTA stages the weights once)
+    const int wpc = (int)std::max<long long>(2, std::min<long long>(8, (N + h->sm_count - 1) / h->sm_count));
+    const size_t per = (warp_smem_floats(h->K, h->D, h->L, h->img.Hmax) + 3) & ~(size_t)3;
+    // weights [W0t .. bo] of all K transforms resident if they fit, else one transform at a time, else global memory
+    const TImg& t0 = h->img.t[0];
+    int wblock = (t0.bo + round4(2 * h->D) + 4 - t0.W0t + 3) & ~3;
+    const int nmeta = ((int)h->n_int + 3) & ~3;
+    const size_t budget = (size_t)h->max_smem_optin - 2048;
+    int wall = 1;
+    if (env_int("RABI_WARP_STAGE", 1) == 0) {
+        wblock = 0;
+        wall = 0;
+    } else if (((size_t)wblock * h->K + nmeta + wpc * per) * sizeof(float) > budget) {
+        wall = 0;
+        if (((size_t)wblock + nmeta + wpc * per) * sizeof(float) > 100 * 1024) wblock = 0;
+    }
+    const size_t smem = ((size_t)wblock * (wall ? h->K : 1) + nmeta + wpc * per) * sizeof(float);
+    if (smem > (size_t)h->max_smem_optin) return 2;
+    CU_OK(h, cudaFuncSetAttribute(k_warp<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = h->profiling;
+    if (prof) {
+        if (h->prof_used == h->prof_events.size()) {
+            cudaEvent_t e0, e1;
+            CU_OK(h, cudaEventCreate(&e0));
+            CU_OK(h, cudaEventCreate(&e1));
+            h->prof_events.push_back({e0, e1});
+        }
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].first, st));
+    }
+    k_warp<MODE><<<(unsigned)((N + wpc - 1) / wpc), wpc * 32, smem, st>>>(h->img, a, wblock, wall, nmeta);
+    LAUNCH_CHECK(h);
+    if (prof) {
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].second, st));
+        h->prof_used++;
+    }
+    return 0;
+}
+
 // workspace layout for the PGD step: [A_p: K*H0*B][gA: K*H0*B][gx: B*C][diff: S*B]
 static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float* zm, const float* zs, const float* A_q,
                          const float* z, int S, int B, float eps, float eps_iter, float cmin, float cmax, float inv_B,
@@ -1241,6 +1287,23 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
     fa.B = B;
     fa.w = inv_B / (float)S;
     int rc;
+    {   // small batches (training-time attacks): one warp per pair
+        PairArgs wa = {};
+        wa.A_p = forward_kl ? A_q : A_p;   // forward KL: samples come from the fixed target
+        wa.A_q = forward_kl ? A_p : A_q;
+        wa.in = z;
+        wa.out_lp = kl ? diff : nullptr;
+        wa.gA = gA;
+        wa.S = S;
+        wa.B = B;
+        wa.w = inv_B / (float)S;
+        if ((long long)S * B <= env_int("RABI_WARP_MAX_PAIRS", 1024) && !env_int("RABI_FORCE_DEEP", 0)) {
+            CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
+            rc = forward_kl ? launch_warp<WARP_FKL_GRAD>(h, wa, st) : launch_warp<WARP_RKL_GRAD>(h, wa, st);
+            if (rc == 1) return 1;
+            if (rc == 0) goto grad_done;
+        }
+    }
     if (forward_kl) {  // KL(target || q(.|x+delta)): sample from the target's projection, differentiate the density pass
         fa.A_p = A_q;
         fa.A_q = A_p;
@@ -1292,6 +1355,7 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
         a.w = inv_B / (float)S;
         if (launch_pairs<MODE_RKL_GRAD>(h, a, st)) return 1;
     }
+grad_done:
     if (launch_ctx_project_bwd(h, gA, zs, B, gx, 0, st)) return 1;
     if (!delta) {  // gradient-only mode (rabi_rkl_input_grad)
         if (kl) {
