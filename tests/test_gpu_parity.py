@@ -475,3 +475,36 @@ def test_size_independent_properties_at_config5_scale(dev):
                 model(x + eps * torch.nn.functional.normalize(torch.randn_like(x), dim=-1)), model(x))
         assert torch.isfinite(kl_adv).all()
         assert float(kl_adv.mean()) > float(kl_rand.mean())
+
+
+@pytest.mark.parametrize("shape", [dict(dx=100, D=4, hidden=[100, 100], B=301), dict(dx=10, D=10, hidden=[100, 100], B=97),
+                                   dict(dx=20, D=31, hidden=[64, 64, 64], B=45), dict(dx=12, D=9, hidden=[40, 36, 44], B=130)])
+def test_warp_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
+    """maf_warp.cuh (launches of <= 1024 pairs: training-time attacks) against the thread-per-pair kernels, reverse- and
+    forward-KL gradient, with the weights staged in shared memory and read from global memory, ragged pair counts."""
+    import os
+
+    ref, model, x = _fresh(shape, dev, seed=8)
+    xd = x.to(dev)
+    eng = model.engine()
+    g = torch.Generator().manual_seed(2)
+    S = 3
+    z = torch.randn(S, xd.shape[0], shape["D"], generator=g).to(dev)
+    with torch.no_grad():
+        q = model(xd)
+        _, zs, _ = model.condition_inputs(xd)
+        th = q.rsample((2,))
+        lp_scale = max(1.0, float(q.log_prob(th.clone()).abs().max()))  # KL values are differences of log-densities
+        for fkl in (False, True):
+            outs = []
+            for env in ({"RABI_WARP_MAX_PAIRS": "0"}, {}, {"RABI_WARP_STAGE": "0"}):
+                os.environ.update(env)
+                try:
+                    gx, kl = eng.rkl_input_grad(xd + 0.05, zs[0], zs[1], q.A, z, 1.0 / xd.shape[0], forward_kl=fkl)
+                finally:
+                    for k in env:
+                        os.environ.pop(k, None)
+                outs.append((gx, kl))
+            for gx, kl in outs[1:]:
+                assert float((kl - outs[0][1]).abs().max()) < 1e-5 * lp_scale
+                assert_trajectories_match(gx, outs[0][0], 1e-4)
