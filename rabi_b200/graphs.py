@@ -25,18 +25,26 @@ from torch.nn.utils import stateless
 
 class _Replay(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, owner, st, *params):
-        ctx.owner, ctx.st = owner, st
+    def forward(ctx, st, n_in, *args):
+        inputs = args[:n_in]
+        ctx.st = st
+        # every call keeps its own copy of the inputs: its backward re-stages them, so several forwards of one signature
+        # may precede their backwards (gradient accumulation, several pre-loss regularisers)
+        ctx.inputs = [t.detach().clone() for t in inputs]
+        for dst, src in zip(st["in"], ctx.inputs):
+            dst.copy_(src)
         st["fwd"].replay()
         return st["out"].clone()
 
     @staticmethod
     def backward(ctx, gout):
         st = ctx.st
+        for dst, src in zip(st["in"], ctx.inputs):
+            dst.copy_(src)
         st["gout"].copy_(gout)
         st["bwd"].replay()
         # clones: autograd may adopt the returned tensors as .grad, and the static buffers are rewritten next step
-        return (None, None) + tuple(g.clone() for g in st["grads"])
+        return (None, None) + (None,) * len(ctx.inputs) + tuple(g.clone() for g in st["grads"])
 
 
 class GraphedParamFunction:
@@ -89,6 +97,4 @@ class GraphedParamFunction:
         st = self._graphs.get(key)
         if st is None:
             st = self._capture(key, inputs)
-        for dst, src in zip(st["in"], inputs):
-            dst.copy_(src.detach())
-        return _Replay.apply(self, st, *self.module.parameters())
+        return _Replay.apply(st, len(inputs), *inputs, *self.module.parameters())

@@ -198,3 +198,29 @@ def test_graphed_nll_and_trades_steps_equal_eager_over_optimizer_steps(dev):
     scale = max(float(p.abs().max()) for p in m2.parameters())
     for a, b in zip(m1.parameters(), m2.parameters()):
         assert float((a - b).abs().max()) <= 2e-4 * scale
+
+
+def test_graphed_nll_with_two_forwards_before_one_backward(dev):
+    """Two forward calls of the same batch shape before a single backward (gradient accumulation, several pre-loss
+    regularisers): every call re-stages its own inputs in its backward, so both gradients are right."""
+    import copy
+
+    from rabi_b200.loss import NLLLoss
+
+    g = load_golden("tiny")
+    m1 = build_product(g, dev, with_output_transform=False).train()
+    m2 = copy.deepcopy(m1).to(dev).train()
+    gen = torch.Generator().manual_seed(5)
+    xs = [torch.randn(16, g["cfg"]["dx"], generator=gen).to(dev) for _ in range(2)]
+    ths = [torch.randn(16, g["cfg"]["D"], generator=gen).to(dev) for _ in range(2)]
+    lf1, lf2 = NLLLoss(m1, cuda_graph=True).train(), NLLLoss(m2, cuda_graph=False).train()
+    for _ in range(3):  # warm-up + capture
+        m1.zero_grad()
+        lf1(xs[0], ths[0]).backward()
+    for m, lf in ((m1, lf1), (m2, lf2)):
+        m.zero_grad()
+        (lf(xs[0], ths[0]) + lf(xs[1], ths[1])).backward()
+    assert lf1._graphed._graphs
+    scale = max(float(p.grad.abs().max()) for p in m2.parameters())
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert float((a.grad - b.grad).abs().max()) <= 1e-4 * scale
