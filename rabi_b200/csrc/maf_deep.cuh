@@ -237,6 +237,30 @@ __device__ __forceinline__ void deep_stage_rows(float* dst, const float* __restr
         *reinterpret_cast<float4*>(dst + (size_t)r * DEEP_SLD + 4 * c4) = v;
     }
 }
+// as deep_stage_rows, but the copied rows are zero at columns >= ccut (partner rows of a paired step: old prefix only)
+__device__ __forceinline__ void deep_stage_rows_cut(float* dst, const float* __restrict__ src, int ld, int r0, int n, int n8,
+                                                    int e16, int ccut) {
+    const int q = e16 >> 2;
+    for (int i = threadIdx.x; i < n8 * q; i += blockDim.x) {
+        const int r = i / q, c4 = i - r * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n && 4 * c4 < ld && 4 * c4 < ccut) {
+            v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * ld) + c4);
+            if (4 * c4 + 1 >= ccut) v.y = 0.f;
+            if (4 * c4 + 2 >= ccut) v.z = 0.f;
+            if (4 * c4 + 3 >= ccut) v.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(dst + (size_t)r * DEEP_SLD + 4 * c4) = v;
+    }
+}
+// dst[r][c] (8 x 8) = src[(r0 + r)*ld + c0 + c] for r < n, c < nc, else 0   (diagonal block of a paired step)
+__device__ __forceinline__ void deep_stage_diag(float* dst, const float* __restrict__ src, int ld, int r0, int n, int c0,
+                                                int nc) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        const int r = i >> 3, c = i & 7;
+        dst[i] = (r < n && c < nc) ? __ldg(src + (size_t)(r0 + r) * ld + c0 + c) : 0.f;
+    }
+}
 // strip[r][0..16) (row stride DEEP_SW) = src[(v0 + r)*ld + c0 .. c0+16) for v0 + r < nrows_src and column < ld, else 0
 __device__ __forceinline__ void deep_stage_strip16(float* dst, const float* __restrict__ src, int ld, int v0, int n16,
                                                    int nrows_src, int c0) {
@@ -342,8 +366,8 @@ __device__ __forceinline__ uint32_t* deep_bits(const DeepArgs& a, const MafImg& 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Sampling pass of transform k under A_p: D steps; step j evaluates the units of MADE degree j of every layer.
-template <int DP>
-__global__ void __launch_bounds__(384, 1) kd_seq_fwd(const MafImg g, const DeepArgs a, const int k) {
+template <int DP, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) kd_seq_fwd(const MafImg g, const DeepArgs a, const int k) {
     extern __shared__ __align__(16) float sm[];
     const DeepThread th = deep_thread(a);
     const TImg& t = g.t[k];
@@ -381,6 +405,159 @@ __global__ void __launch_bounds__(384, 1) kd_seq_fwd(const MafImg g, const DeepA
         bacc[l].on = a.record != 0;
     }
     for (int j = 0; j < D; ++j) {
+        // ---- paired steps (j, j+1) when every group of both degrees has <= 8 units (pyloric: 6-7): ONE sweep over the
+        // prefix of each layer serves the rows of both degrees (16 rows per block instead of 8, half the prefix
+        // traffic, half the barriers); the rows of degree j+1 only lack the contribution of the degree-(j+1) units of
+        // the layer below, which step j+1 adds from registers through an 8 x 8 diagonal block.
+        bool pair = j + 1 < D;
+#pragma unroll
+        for (int l = 0; l < RABI_MAXL; ++l)
+            if (l < L) pair = pair && M[t.grp[l] + j + 1] - M[t.grp[l] + j] <= 8 && M[t.grp[l] + j + 2] - M[t.grp[l] + j + 1] <= 8;
+        if (pair) {
+            // shared-memory layout: [W0t rows of both groups][per layer l >= 1: 16 sweep rows | 8 x 8 diagonal]
+            //                       [4 output sweep rows (m_j, s_j, m_j+1, s_j+1) | 2 x 8 output diagonal]
+            int offs[RABI_MAXL + 1], eA[RABI_MAXL + 1];
+            const int n0a = M[t.grp[0] + j + 1] - M[t.grp[0] + j], n0b = M[t.grp[0] + j + 2] - M[t.grp[0] + j + 1];
+            {
+                int o = (n0a + n0b) * t.ldt;
+#pragma unroll
+                for (int l = 1; l <= RABI_MAXL; ++l) {
+                    offs[l == RABI_MAXL ? 0 : l] = o;  // slot 0 holds the output block's offset
+                    eA[l == RABI_MAXL ? 0 : l] = 0;
+                    if (l < L) {
+                        eA[l] = (M[t.grp[l - 1] + j + 1] + 15) & ~15;
+                        o += 16 * DEEP_SLD + 64;
+                    }
+                }
+                eA[0] = (M[t.grp[L - 1] + j + 1] + 15) & ~15;
+            }
+            __syncthreads();
+            deep_stage(sm, F + t.W0t + (size_t)M[t.grp[0] + j] * t.ldt, ((n0a + n0b) * t.ldt) >> 2);
+#pragma unroll
+            for (int l = 1; l < RABI_MAXL; ++l) {
+                if (l >= L) continue;
+                const int ra = M[t.grp[l] + j], rb = M[t.grp[l] + j + 1], rc = M[t.grp[l] + j + 2];
+                const int ca = M[t.grp[l - 1] + j + 1], cb = M[t.grp[l - 1] + j + 2];
+                deep_stage_rows(sm + offs[l], F + t.W[l], t.ld[l], ra, rb - ra, 8, eA[l]);
+                deep_stage_rows_cut(sm + offs[l] + 8 * DEEP_SLD, F + t.W[l], t.ld[l], rb, rc - rb, 8, eA[l], ca);
+                deep_stage_diag(sm + offs[l] + 16 * DEEP_SLD, F + t.W[l], t.ld[l], rb, rc - rb, ca, cb - ca);
+            }
+            {
+                const int ca = M[t.grp[L - 1] + j + 1], cb = M[t.grp[L - 1] + j + 2];
+                float* so = sm + offs[0];
+                deep_stage_rows(so, F + t.Wo, t.ldo, j, 1, 1, eA[0]);
+                deep_stage_rows(so + DEEP_SLD, F + t.Wo, t.ldo, D + j, 1, 1, eA[0]);
+                deep_stage_rows_cut(so + 2 * DEEP_SLD, F + t.Wo, t.ldo, j + 1, 1, 1, eA[0], ca);
+                deep_stage_rows_cut(so + 3 * DEEP_SLD, F + t.Wo, t.ldo, D + j + 1, 1, 1, eA[0], ca);
+                for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+                    const int r = i >> 3, c = i & 7;
+                    so[4 * DEEP_SLD + i] = c < cb - ca ? __ldg(F + t.Wo + (size_t)(r == 0 ? j + 1 : D + j + 1) * t.ldo + ca + c) : 0.f;
+                }
+            }
+            __syncthreads();
+            float part[RABI_MAXL][8], pout[2] = {0.f, 0.f};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int jj0 = j + half;
+                // ---- layer 0 of degree jj0 (the new activations stay in registers for the diagonal blocks)
+                float prev[8];
+                {
+                    const int ua = M[t.grp[0] + jj0], n = M[t.grp[0] + jj0 + 1] - ua;
+                    const float* w0 = sm + (size_t)(half ? n0a : 0) * t.ldt;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        prev[c] = 0.f;
+                        if (c < n) {
+                            float pre = th.live ? __ldg(Ap + (size_t)(ua + c) * a.B) : 0.f;
+                            const float* w = w0 + (size_t)c * t.ldt;
+#pragma unroll
+                            for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                const float4 w4 = *reinterpret_cast<const float4*>(w + 4 * q4);
+                                pre = fmaf(w4.x, y[4 * q4], pre);
+                                pre = fmaf(w4.y, y[4 * q4 + 1], pre);
+                                pre = fmaf(w4.z, y[4 * q4 + 2], pre);
+                                pre = fmaf(w4.w, y[4 * q4 + 3], pre);
+                            }
+                            const bool on = pre > 0.f;
+                            bacc[0].put(ua + c, on);
+                            prev[c] = on ? pre : 0.f;
+                            h[0].st1(ua + c, prev[c]);
+                        }
+                    }
+                }
+                // ---- hidden layers
+#pragma unroll
+                for (int l = 1; l < RABI_MAXL; ++l) {
+                    if (l >= L) continue;
+                    const int va = M[t.grp[l] + jj0], n = M[t.grp[l] + jj0 + 1] - va;
+                    float val[8];
+                    if (half == 0) {
+                        float o[16];
+                        gdotz<16, DEEP_SLD>(sm + offs[l], eA[l], h[l - 1], o);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            val[c] = o[c];
+                            part[l][c] = o[8 + c];
+                        }
+                    } else {
+                        const float* dg = sm + offs[l] + 16 * DEEP_SLD;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 d0 = *reinterpret_cast<const float4*>(dg + 8 * c);
+                            const float4 d1 = *reinterpret_cast<const float4*>(dg + 8 * c + 4);
+                            float acc = part[l][c];
+                            acc = fmaf(d0.x, prev[0], acc); acc = fmaf(d0.y, prev[1], acc);
+                            acc = fmaf(d0.z, prev[2], acc); acc = fmaf(d0.w, prev[3], acc);
+                            acc = fmaf(d1.x, prev[4], acc); acc = fmaf(d1.y, prev[5], acc);
+                            acc = fmaf(d1.z, prev[6], acc); acc = fmaf(d1.w, prev[7], acc);
+                            val[c] = acc;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        prev[c] = 0.f;
+                        if (c < n) {
+                            const float x = val[c] + __ldg(F + t.b[l] + va + c);
+                            const bool on = x > 0.f;
+                            bacc[l].put(va + c, on);
+                            prev[c] = on ? x : 0.f;
+                            h[l].st1(va + c, prev[c]);
+                        }
+                    }
+                }
+                // ---- output position jj0
+                float m, sraw;
+                if (half == 0) {
+                    float o[4];
+                    gdotz<4, DEEP_SLD>(sm + offs[0], eA[0], deep_act(a, L - 1, th.col), o);
+                    m = o[0];
+                    sraw = o[1];
+                    pout[0] = o[2];
+                    pout[1] = o[3];
+                } else {
+                    const float* dg = sm + offs[0] + 4 * DEEP_SLD;
+                    m = pout[0];
+                    sraw = pout[1];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        m = fmaf(dg[c], prev[c], m);
+                        sraw = fmaf(dg[8 + c], prev[c], sraw);
+                    }
+                }
+                m += __ldg(F + t.bo + jj0);
+                sraw += __ldg(F + t.bo + D + jj0);
+                const float zj = DV(SV + k, M[t.perm + jj0]);
+                const float sh = fminf(fmaxf(sraw, g.lo), g.hi);
+                const float yj = (zj - m) * expf(-sh);
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) y[jj] = jj == jj0 ? yj : y[jj];
+                logp += sh;
+                DV(SHP + k, jj0) = sh;
+                DV(SV + k + 1, M[t.permy + jj0]) = yj;
+            }
+            ++j;  // the partner step is done
+            continue;
+        }
         // ---- stage the rows of degree j: [W0t rows | W[1] | ... | W[L-1] | Wo rows j, D+j]; hidden / output rows at the
         // fixed stride DEEP_SLD, groups padded with zero rows to a multiple of 8, prefixes to a multiple of 16
         int off[RABI_MAXL + 1], e16[RABI_MAXL + 1];
@@ -475,8 +652,8 @@ __global__ void __launch_bounds__(384, 1) kd_seq_fwd(const MafImg g, const DeepA
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Density pass of transform k under A_q (one full MADE pass) + the chain update u_k = exp(clamp(s)) u_{k+1} + m.
-template <int DP>
-__global__ void __launch_bounds__(384, 1) kd_full_fwd(const MafImg g, const DeepArgs a, const int k, const int mode) {
+template <int DP, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) kd_full_fwd(const MafImg g, const DeepArgs a, const int k, const int mode) {
     extern __shared__ __align__(16) float sm[];
     const DeepThread th = deep_thread(a);
     const TImg& t = g.t[k];
@@ -596,8 +773,8 @@ __global__ void __launch_bounds__(384, 1) kd_full_fwd(const MafImg g, const Deep
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Reverse of the density pass of transform k (input gradient only).  The running cotangent lives in vec slot SU.
-template <int DP>
-__global__ void __launch_bounds__(384, 1) kd_full_bwd(const MafImg g, const DeepArgs a, const int k, const int emit_gA) {
+template <int DP, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) kd_full_bwd(const MafImg g, const DeepArgs a, const int k, const int emit_gA) {
     extern __shared__ __align__(16) float sm[];
     const DeepThread th = deep_thread(a);
     const TImg& t = g.t[k];
@@ -702,8 +879,8 @@ __global__ void __launch_bounds__(384, 1) kd_full_bwd(const MafImg g, const Deep
 // ---------------------------------------------------------------------------------------------------------------------
 // Reverse of the sampling pass of transform k: D steps in descending order, pull style (every cotangent is produced
 // once, when all its consumers are final); emits d loss / d A_p.
-template <int DP>
-__global__ void __launch_bounds__(384, 1) kd_seq_bwd(const MafImg g, const DeepArgs a, const int k) {
+template <int DP, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) kd_seq_bwd(const MafImg g, const DeepArgs a, const int k) {
     extern __shared__ __align__(16) float sm[];
     const DeepThread th = deep_thread(a);
     const TImg& t = g.t[k];

@@ -1043,7 +1043,9 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
 }
 
 // ---- deep / wide conditioners: per-(transform, pass) launches over a global-memory scratch (maf_deep.cuh) ----------
-template <int DP>
+// MAXT: __launch_bounds__ of the kernel variant (384: 168 registers per thread; 512: 128).  A batch runs in the time one
+// thread needs for its pair, so the launcher minimises the NUMBER of batches first and only then picks the variant.
+template <int DP, int MAXT>
 static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaStream_t st) {
     const int K = h->K, D = h->D, L = h->L;
     const MafImg& g = h->img;
@@ -1070,18 +1072,24 @@ static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaSt
             }
             seqf = std::max(seqf, f);
             seqb = std::max(seqb, b);
+            if (j + 1 < D) {  // paired step of kd_seq_fwd (groups of <= 8 units): W0t rows of both groups, per hidden
+                              // layer 16 sweep rows + an 8 x 8 diagonal, 4 output rows + a 2 x 8 diagonal
+                size_t fp = (size_t)(M[t.grp[0] + j + 2] - M[t.grp[0] + j]) * t.ldt + (size_t)(L - 1) * (16 * DEEP_SLD + 64) +
+                            4 * DEEP_SLD + 16;
+                seqf = std::max(seqf, fp);
+            }
         }
     }
     seqf += 64;
     seqb += 64;
     const size_t budget = (size_t)h->max_smem_optin - 1024;
     if (full * 4 > budget || seqf * 4 > budget || seqb * 4 > budget) return 2;
-    CU_OK(h, cudaFuncSetAttribute(kd_seq_fwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(seqf * 4)));
-    CU_OK(h, cudaFuncSetAttribute(kd_full_fwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(full * 4)));
-    CU_OK(h, cudaFuncSetAttribute(kd_full_bwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(full * 4)));
-    CU_OK(h, cudaFuncSetAttribute(kd_seq_bwd<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(seqb * 4)));
+    CU_OK(h, cudaFuncSetAttribute(kd_seq_fwd<DP, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(seqf * 4)));
+    CU_OK(h, cudaFuncSetAttribute(kd_full_fwd<DP, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(full * 4)));
+    CU_OK(h, cudaFuncSetAttribute(kd_full_bwd<DP, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(full * 4)));
+    CU_OK(h, cudaFuncSetAttribute(kd_seq_bwd<DP, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(seqb * 4)));
     // batches: at most one CTA of <= Tmax threads per SM, every SM gets the same number of pairs
-    const int Tmax = std::max(64, std::min(384, env_int("RABI_DEEP_T", 384) & ~31));  // __launch_bounds__ of kd_*
+    const int Tmax = std::max(64, std::min(MAXT, env_int("RABI_DEEP_T", MAXT) & ~31));
     const long long cap = (long long)h->sm_count * Tmax;
     const long long nbatch = (N + cap - 1) / cap;
     const int nmax = (int)((N + nbatch - 1) / nbatch);
@@ -1138,7 +1146,7 @@ static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaSt
             DeepArgs as = a;
             if (mode == DEEP_FKL) as.record = 0;  // the sampling pass is not differentiated
             for (int k = 0; k < K; ++k) {
-                kd_seq_fwd<DP><<<grid, T, seqf * 4, st>>>(g, as, k);
+                kd_seq_fwd<DP, MAXT><<<grid, T, seqf * 4, st>>>(g, as, k);
                 LAUNCH_CHECK(h);
             }
         }
@@ -1148,18 +1156,18 @@ static int launch_deep_dp(rabi_maf* h, DeepArgs a, int mode, long long N, cudaSt
             continue;
         }
         for (int k = K - 1; k >= 0; --k) {
-            kd_full_fwd<DP><<<grid, T, full * 4, st>>>(g, a, k, mode);
+            kd_full_fwd<DP, MAXT><<<grid, T, full * 4, st>>>(g, a, k, mode);
             LAUNCH_CHECK(h);
         }
         if (mode == DEEP_GRAD || mode == DEEP_FKL) {
             for (int k = 0; k < K; ++k) {
-                kd_full_bwd<DP><<<grid, T, full * 4, st>>>(g, a, k, mode == DEEP_FKL);
+                kd_full_bwd<DP, MAXT><<<grid, T, full * 4, st>>>(g, a, k, mode == DEEP_FKL);
                 LAUNCH_CHECK(h);
             }
         }
         if (mode == DEEP_GRAD) {
             for (int k = K - 1; k >= 0; --k) {
-                kd_seq_bwd<DP><<<grid, T, seqb * 4, st>>>(g, a, k);
+                kd_seq_bwd<DP, MAXT><<<grid, T, seqb * 4, st>>>(g, a, k);
                 LAUNCH_CHECK(h);
             }
         }
@@ -1177,9 +1185,12 @@ static int launch_deep(rabi_maf* h, const DeepArgs& a, int mode, cudaStream_t st
     if (N <= 0) return 0;
     if (env_int("RABI_DISABLE_DEEP", 0)) return 2;
     if (h->L < 2 || h->D > 32 || ((h->img.Hmax + 15) & ~15) > DEEP_SLD) return 2;
-    if (h->D <= 4) return launch_deep_dp<4>(h, a, mode, N, st);
-    if (h->D <= 12) return launch_deep_dp<12>(h, a, mode, N, st);
-    return launch_deep_dp<32>(h, a, mode, N, st);
+    // fewest batches: one CTA per SM of up to 512 threads; the 384-thread variant (more registers) when it needs no more
+    const long long nb512 = (N + (long long)h->sm_count * 512 - 1) / ((long long)h->sm_count * 512);
+    const long long nb384 = (N + (long long)h->sm_count * 384 - 1) / ((long long)h->sm_count * 384);
+    const bool big = nb512 < nb384 && env_int("RABI_DEEP_T", 512) > 384;
+    if (h->D <= 12) return big ? launch_deep_dp<12, 512>(h, a, mode, N, st) : launch_deep_dp<12, 384>(h, a, mode, N, st);
+    return big ? launch_deep_dp<32, 512>(h, a, mode, N, st) : launch_deep_dp<32, 384>(h, a, mode, N, st);
 }
 
 extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_q_dev, const float* z_dev, int S, int B,
