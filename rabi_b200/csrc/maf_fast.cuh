@@ -441,10 +441,10 @@ __global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g,
                         auto block = [&](auto NRtag, int v0, int nv) {
                             constexpr int NR = decltype(NRtag)::value;
                             float h[RP][NR];
-                            dot_block<RP, NR, TM, LDC>(W1 + (size_t)v0 * ld1, ld1, nv - 1, e4, ab, h);
+                            dot_block<RP, NR, TM, LDC>(W1 + (size_t)v0 * ld1, ld1, NR - 1, e4, ab, h);  // blocks are exact: nv == NR
 #pragma unroll
                             for (int c = 0; c < NR; ++c) {
-                                if (c < nv) {
+                                {
                                     const int v = v0 + c;
                                     const float bias = b1[v];
                                     const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
