@@ -201,7 +201,7 @@ struct FastRel {
 };
 
 template <int MODE, int RP, int DP, bool TM, int LDC>
-__global__ void __launch_bounds__(RP == 1 ? 384 : 256, 1) k_fast(const MafImg g, const FastArgs a, const FastRel rel) {
+__global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 512), 1) k_fast(const MafImg g, const FastArgs a, const FastRel rel) {
     extern __shared__ __align__(16) float sm[];
     const int T = blockDim.x, tid = threadIdx.x;
     const int K = g.K, D = g.D, H0 = g.H[0], H1 = g.H[1];

@@ -978,7 +978,9 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     const size_t per_slot = (size_t)((TM ? 0 : fa.AS) + fa.VS + fa.BWS) * sizeof(float);
     const size_t fixed = (size_t)(fa.wfloats + fa.wints) * sizeof(float);
     const size_t budget = (size_t)h->max_smem_optin - 1024;
-    const int Tmax = RP == 1 ? 384 : 256;  // matches __launch_bounds__ of k_fast
+    // matches __launch_bounds__ of k_fast; the forward-only modes keep less state per thread and run 512-thread tiles
+    // (a tile takes the time one thread needs for its pair, so wider tiles mean fewer waves)
+    const int Tmax = RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 512);
     int T = env_int("RABI_FAST_T", Tmax);
     T = std::max(32, std::min(Tmax, (T / 32) * 32));
     if (TM) {  // every group of 4 warps needs RP*AS of the 512 tensor-memory columns
