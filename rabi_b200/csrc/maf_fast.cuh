@@ -475,6 +475,14 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                         };
                         int v = va;
                         for (; v + 16 <= vb; v += 16) block(std::integral_constant<int, 16>{}, v, 16);
+                        // a remainder of 9..15 units as ONE exact block (25 units per degree at lotka_volterra shapes = 16 + 9,
+                        // 10 at gaussian_linear shapes): every extra block is another pass over the activations
+#define RABI_REM(N) case N: block(std::integral_constant<int, N>{}, v, N); v += N; break;
+                        switch (vb - v) {
+                            RABI_REM(9) RABI_REM(10) RABI_REM(11) RABI_REM(12) RABI_REM(13) RABI_REM(14) RABI_REM(15)
+                            default: break;
+                        }
+#undef RABI_REM
                         if (v + 8 <= vb) { block(std::integral_constant<int, 8>{}, v, 8); v += 8; }
                         if (v + 4 <= vb) { block(std::integral_constant<int, 4>{}, v, 4); v += 4; }
                         if (v + 2 <= vb) { block(std::integral_constant<int, 2>{}, v, 2); v += 2; }
@@ -622,7 +630,9 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                             tdot_block<RP, NC, TM, LDC>(W1 + u0, ld1, va4, vb4, ab, g0);
                             uint32_t wb[RP];
 #pragma unroll
-                            for (int r = 0; r < RP; ++r) wb[r] = bitp[r][bs * WL + (u0 >> 5)] >> (u0 & 31);
+                            for (int r = 0; r < RP; ++r)  // 32 mask bits starting at unit u0 (a block may straddle two words; the
+                                                          // slot array ends with a padding word, so word + 1 is readable)
+                                wb[r] = __funnelshift_r(bitp[r][bs * WL + (u0 >> 5)], bitp[r][bs * WL + (u0 >> 5) + 1], u0 & 31);
 #pragma unroll
                             for (int c = 0; c < NC; ++c) {
                                 const int u = u0 + c;
@@ -645,10 +655,11 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                         };
                         int u = ua & ~3;
                         const int uend = (ub + 3) & ~3;
-                        while (u < uend) {  // wide blocks only where they stay inside one 32-bit mask word
+                        while (u < uend) {  // as few passes over the layer-1 cotangents as possible
                             const int left = uend - u;
-                            if (left >= 16 && ((u & 31) + 16 <= 32)) { cblock(std::integral_constant<int, 16>{}, u); u += 16; }
-                            else if (left >= 8 && ((u & 31) + 8 <= 32)) { cblock(std::integral_constant<int, 8>{}, u); u += 8; }
+                            if (left >= 16) { cblock(std::integral_constant<int, 16>{}, u); u += 16; }
+                            else if (left == 12) { cblock(std::integral_constant<int, 12>{}, u); u += 12; }
+                            else if (left >= 8) { cblock(std::integral_constant<int, 8>{}, u); u += 8; }
                             else { cblock(std::integral_constant<int, 4>{}, u); u += 4; }
                         }
                     }

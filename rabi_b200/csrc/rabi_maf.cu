@@ -966,7 +966,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     rel.first1 = t0.first[1] - t0.perm;
     fa.wfloats = t0.fast_end - t0.W0t;
     fa.wints = (t0.meta_fast_end - t0.perm + 3) & ~3;
-    const int RP = env_int("RABI_FAST_RP", 1) == 2 ? 2 : 1;
+    const int RP = 1;  // two pairs per thread (shared weight loads) was measured 1.8x slower: half the warps, more spills
     // activations in tensor memory (default) or in shared memory
     const bool TM = env_int("RABI_FAST_TMEM", 1) != 0 && RP * std::max(round4(H0), round4(H1)) <= 512 && (RP == 1 || DP == 4);
     int AS = std::max(round4(H0), round4(H1));
@@ -1038,8 +1038,6 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     RABI_FAST_CASE(1, 8, true, 0)
     RABI_FAST_CASE(1, 12, true, 0)
     RABI_FAST_CASE(1, 4, false, 0)
-    RABI_FAST_CASE(2, 4, false, 0)
-    RABI_FAST_CASE(2, 4, true, 0)
 #undef RABI_FAST_CASE
     return 2;
 }
