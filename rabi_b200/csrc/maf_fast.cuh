@@ -20,7 +20,20 @@
 
 #include "maf_image.h"
 
+#ifdef RABI_X_NOCLOBBER
+#define RABI_TM_CLOBBER
+#else
+#define RABI_TM_CLOBBER "memory"
+#endif
+#ifndef RABI_X_DOT_UNROLL
+#define RABI_X_DOT_UNROLL 2
+#endif
+#ifndef RABI_X_TDOT_UNROLL
+#define RABI_X_TDOT_UNROLL 2
+#endif
+
 namespace rabi {
+constexpr int kDotUnroll = RABI_X_DOT_UNROLL, kTdotUnroll = RABI_X_TDOT_UNROLL;
 
 struct FastArgs {
     const float* A_p;
@@ -74,7 +87,7 @@ struct ActBuf<1> {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                      : "r"(t + (uint32_t)i)
-                     : "memory");
+                     : RABI_TM_CLOBBER);
         return v;
     }
     __device__ __forceinline__ void st4(int i, float4 v) const {
@@ -87,7 +100,7 @@ struct ActBuf<1> {
     }
     // the loaded registers are only valid after wait::ld; tie them to the wait so nothing is scheduled above it
     __device__ __forceinline__ static void wait_ld(float4& v) {
-        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)::"memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)::RABI_TM_CLOBBER);
     }
     __device__ __forceinline__ static void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
@@ -108,7 +121,7 @@ __device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld_rt
     float4 hn[RP];
 #pragma unroll
     for (int r = 0; r < RP; ++r) hn[r] = ab[r].ld4(0);
-#pragma unroll 2
+#pragma unroll(kDotUnroll)
     for (int i = 0; i < e4; i += 4) {
         float4 h[RP];
 #pragma unroll
@@ -116,7 +129,7 @@ __device__ __forceinline__ void dot_block(const float* __restrict__ W, int ld_rt
             ActBuf<TM>::wait_ld(hn[r]);
             h[r] = hn[r];
         }
-        if (i + 4 < e4) {
+        {  // unconditional look-ahead: the quad after the last one is inside the CTA's shared / tensor memory, never used
 #pragma unroll
             for (int r = 0; r < RP; ++r) hn[r] = ab[r].ld4(i + 4);
         }
@@ -151,6 +164,7 @@ __device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld_r
     float4 gn[RP];
 #pragma unroll
     for (int r = 0; r < RP; ++r) gn[r] = ab[r].ld4(va4);
+#pragma unroll(kTdotUnroll)
     for (int v = va4; v < vb4; v += 4, wbase += 4 * ld) {
         float4 g4[RP];
 #pragma unroll
@@ -158,7 +172,7 @@ __device__ __forceinline__ void tdot_block(const float* __restrict__ W, int ld_r
             ActBuf<TM>::wait_ld(gn[r]);
             g4[r] = gn[r];
         }
-        if (v + 4 < vb4) {
+        {
 #pragma unroll
             for (int r = 0; r < RP; ++r) gn[r] = ab[r].ld4(v + 4);
         }
@@ -414,22 +428,24 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
 #pragma unroll
                             for (int r = 0; r < RP; ++r) {
                                 float nv[4] = {av[r].x, av[r].y, av[r].z, av[r].w};
+                                uint32_t nib = 0u;  // relu bits of the quad (units outside [ua, ub) contribute nothing)
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
                                     const int u = u0 + c;
                                     if (u >= ua && u < ub) {
                                         const bool on = pre[r][c] > 0.f;
                                         nv[c] = on ? pre[r][c] : 0.f;
-                                        if (fast_is_grad(MODE)) {
-                                            if (on) w0[r] |= 1u << (u & 31);
-                                            if ((u & 31) == 31 || u == H0 - 1) {
-                                                bitp[r][bs * WL + (u >> 5)] = w0[r];
-                                                w0[r] = 0u;
-                                            }
-                                        }
+                                        nib |= on ? (1u << c) : 0u;
                                     }
                                 }
                                 ab[r].st4(u0, make_float4(nv[0], nv[1], nv[2], nv[3]));
+                                if (fast_is_grad(MODE)) {  // the word is complete after its last quad / the layer's last quad
+                                    w0[r] |= nib << (u0 & 31);
+                                    if (ub >= min(u0 + 4, H0) && ((u0 & 31) == 28 || u0 + 4 >= H0)) {
+                                        bitp[r][bs * WL + (u0 >> 5)] = w0[r];
+                                        w0[r] = 0u;
+                                    }
+                                }
                             }
                         }
                         ActBuf<TM>::wait_st();
@@ -442,6 +458,9 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                             constexpr int NR = decltype(NRtag)::value;
                             float h[RP][NR];
                             dot_block<RP, NR, TM, LDC>(W1 + (size_t)v0 * ld1, ld1, NR - 1, e4, ab, h);  // blocks are exact: nv == NR
+                            uint32_t bm[RP];
+#pragma unroll
+                            for (int r = 0; r < RP; ++r) bm[r] = 0u;
 #pragma unroll
                             for (int c = 0; c < NR; ++c) {
                                 {
@@ -462,13 +481,22 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                                             oms[r][2 * q2] = ffma2(make_float2(wq[q2].x, wq[q2].y), hh, oms[r][2 * q2]);
                                             oms[r][2 * q2 + 1] = ffma2(make_float2(wq[q2].z, wq[q2].w), hh, oms[r][2 * q2 + 1]);
                                         }
-                                        if (fast_is_grad(MODE)) {
-                                            if (on) w1[r] |= 1u << (v & 31);
-                                            if ((v & 31) == 31 || v == H1 - 1) {
-                                                bitp[r][(bs + 1) * WL + (v >> 5)] = w1[r];
-                                                w1[r] = 0u;
-                                            }
-                                        }
+                                        if (fast_is_grad(MODE)) bm[r] |= on ? (1u << c) : 0u;
+                                    }
+                                }
+                            }
+                            if (fast_is_grad(MODE)) {  // relu bits of the block -> the running word; store it when it is complete
+                                const int sh = v0 & 31;
+#pragma unroll
+                                for (int r = 0; r < RP; ++r) {
+                                    w1[r] |= bm[r] << sh;
+                                    if (sh + NR >= 32) {
+                                        bitp[r][(bs + 1) * WL + (v0 >> 5)] = w1[r];
+                                        w1[r] = sh + NR > 32 ? bm[r] >> (32 - sh) : 0u;
+                                    }
+                                    if (v0 + NR == H1 && (H1 & 31) != 0) {
+                                        bitp[r][(bs + 1) * WL + ((H1 - 1) >> 5)] = w1[r];
+                                        w1[r] = 0u;
                                     }
                                 }
                             }

@@ -13,6 +13,7 @@
 #include "maf_image.h"
 #include "maf_pairs.cuh"
 #include "maf_fast.cuh"
+#include "maf_fast2.cuh"
 #include "maf_deep.cuh"
 #include "maf_warp.cuh"
 
@@ -984,7 +985,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     int T = env_int("RABI_FAST_T", Tmax);
     T = std::max(32, std::min(Tmax, (T / 32) * 32));
     if (TM) {  // every group of 4 warps needs RP*AS of the 512 tensor-memory columns
-        while (T > 32 && ((T / 32 + 3) / 4) * RP * AS > 512) T -= 32;
+        while (T > 32 && ((T / 32 + 3) / 4) * RP * AS + 4 > 512) T -= 32;  // + 4: the look-ahead quad of the product loops
     }
     int grid = 0;
     size_t smem = 0;
@@ -1026,20 +1027,111 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     }
     fa.tm_cols = 32;
     if (TM) {
-        int need = ((T / 32 + 3) / 4) * RP * AS;
+        int need = ((T / 32 + 3) / 4) * RP * AS + 4;
         while (fa.tm_cols < need) fa.tm_cols *= 2;
     }
 #define RABI_FAST_CASE(RPv, DPv, TMv, LDv) \
     if (RP == RPv && DP == DPv && TM == TMv && (LDv == 0 || rel.ld1 == LDv))  \
         return launch_fast_inst<MODE, RPv, DPv, TMv, LDv>(h, fa, rel, grid, T, smem, st);
     RABI_FAST_CASE(1, 4, true, 100)   // lotka_volterra: hidden [100, 100]
+#ifndef RABI_LEAN
     RABI_FAST_CASE(1, 12, true, 100)  // gaussian_linear
     RABI_FAST_CASE(1, 4, true, 0)
     RABI_FAST_CASE(1, 8, true, 0)
     RABI_FAST_CASE(1, 12, true, 0)
     RABI_FAST_CASE(1, 4, false, 0)
+#endif
 #undef RABI_FAST_CASE
     return 2;
+}
+
+// ---- k_fast2 (maf_fast2.cuh): the attack gradient with two lanes per pair, for launches that leave the SMs short of warps
+template <int LDC>
+static int launch_fast2_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel, int grid, int T, size_t smem, cudaStream_t st) {
+    CU_OK(h, cudaFuncSetAttribute(k_fast2<LDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = h->profiling;
+    if (prof) {
+        if (h->prof_used == h->prof_events.size()) {
+            cudaEvent_t e0, e1;
+            CU_OK(h, cudaEventCreate(&e0));
+            CU_OK(h, cudaEventCreate(&e1));
+            h->prof_events.push_back({e0, e1});
+        }
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].first, st));
+    }
+    k_fast2<LDC><<<grid, T, smem, st>>>(h->img, fa, rel);
+    LAUNCH_CHECK(h);
+    if (prof) {
+        CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].second, st));
+        h->prof_used++;
+    }
+    return 0;
+}
+
+// returns 2 when the shape or the launch size is not one for k_fast2 (the caller then takes k_fast)
+static int launch_fast2(rabi_maf* h, FastArgs fa, cudaStream_t st) {
+    if ((long long)fa.S * fa.B <= 0) return 0;
+    if (!env_int("RABI_FAST2", 1) || env_int("RABI_DISABLE_FAST", 0)) return 2;
+    if (h->L != 2 || h->D > 4 || h->H[0] > 104 || h->H[1] > 104) return 2;
+    const MafImg& g = h->img;
+    const TImg& t0 = g.t[0];
+    const int K = h->K, D = h->D, H0 = h->H[0], H1 = h->H[1];
+    // pays when a thread per pair leaves the schedulers short of warps (measured on lotka_volterra shapes: 1.11-1.2x up to
+    // ~100 pairs per SM, even at ~170, slower once k_fast has its full 11 warps per SM); RABI_FAST2=2 forces it
+    if (env_int("RABI_FAST2", 1) != 2 && (long long)fa.S * fa.B > (long long)h->sm_count * env_int("RABI_FAST2_MAX_PER_SM", 128)) return 2;
+    if ((long long)fa.S * fa.B > (long long)h->sm_count * 352) return 2;  // one wave of 704-thread tiles
+    FastRel rel;
+    rel.W0t = 0;
+    rel.b1 = t0.b[1] - t0.W0t;
+    rel.W1 = t0.W[1] - t0.W0t;
+    rel.ld1 = t0.ld[1];
+    rel.WoT = t0.WoT - t0.W0t;
+    rel.bo = t0.boF - t0.W0t;
+    rel.perm = 0;
+    rel.permy = t0.permy - t0.perm;
+    rel.deg0 = t0.deg0 - t0.perm;
+    rel.pre1 = t0.pre[1] - t0.perm;
+    rel.grp0 = t0.grp[0] - t0.perm;
+    rel.grp1 = t0.grp[1] - t0.perm;
+    rel.first1 = t0.first[1] - t0.perm;
+    if (t0.ldt != 4) return 2;
+    fa.wfloats = t0.fast_end - t0.W0t;
+    fa.wints = (t0.meta_fast_end - t0.perm + 3) & ~3;
+    const int nq = (std::max(H0, H1) + 3) / 4;
+    fa.AS = 4 * ((nq + 1) / 2);  // own TMEM columns of a lane
+    fa.VS = ((4 * K + 2) * D) | 1;
+    const int WL = (g.Hmax + 31) / 32;
+    fa.BWS = (2 * K * 2 * WL) | 1;
+    const size_t per_slot = (size_t)(fa.VS + fa.BWS) * sizeof(float);
+    const size_t fixed = (size_t)(fa.wfloats + fa.wints) * sizeof(float);
+    const size_t budget = (size_t)h->max_smem_optin - 1024;
+    auto gat_bytes = [&](int tbp) { return (((size_t)H0 * tbp + 3) & ~(size_t)3) * sizeof(float); };
+    int T = 704;
+    while (T > 64 && ((T / 32 + 3) / 4) * fa.AS + 4 > 512) T -= 64;  // + 4: the look-ahead quad of the product loops
+    size_t smem = 0;
+    for (;; T -= 64) {
+        if (T < 64) return 2;
+        const int tb = (T / 2) / fa.S;
+        if (tb < 1) return 2;
+        smem = fixed + gat_bytes(tb | 1) + (size_t)(T / 2) * per_slot;
+        if (smem <= budget) break;
+    }
+    const int tb_cap = (T / 2) / fa.S;
+    const int ntiles0 = (fa.B + tb_cap - 1) / tb_cap;
+    const int waves = (ntiles0 + h->sm_count - 1) / h->sm_count;
+    const int want = std::min(fa.B, waves * h->sm_count);
+    fa.TB = std::min(tb_cap, (fa.B + want - 1) / want);
+    fa.ntiles = (fa.B + fa.TB - 1) / fa.TB;
+    const int Tneed = (2 * fa.TB * fa.S + 63) & ~63;
+    T = std::min(T, std::max(64, Tneed));
+    fa.TBp = fa.TB | 1;
+    smem = fixed + gat_bytes(fa.TBp) + (size_t)(T / 2) * per_slot;
+    const int grid = std::min(fa.ntiles, h->sm_count);
+    fa.tm_cols = 32;
+    const int need = ((T / 32 + 3) / 4) * fa.AS + 4;
+    while (fa.tm_cols < need) fa.tm_cols *= 2;
+    if (rel.ld1 == 100) return launch_fast2_inst<100>(h, fa, rel, grid, T, smem, st);
+    return launch_fast2_inst<0>(h, fa, rel, grid, T, smem, st);
 }
 
 // ---- deep / wide conditioners: per-(transform, pass) launches over a global-memory scratch (maf_deep.cuh) ----------
@@ -1184,6 +1276,9 @@ static int launch_deep(rabi_maf* h, const DeepArgs& a, int mode, cudaStream_t st
     const long long N = (long long)a.S * a.B;
     if (N <= 0) return 0;
     if (env_int("RABI_DISABLE_DEEP", 0)) return 2;
+#ifdef RABI_LEAN  // development builds (kernel experiments): only the lotka_volterra k_fast instantiations, 1 min instead of 6
+    return 2;
+#else
     if (h->L < 2 || h->D > 32 || ((h->img.Hmax + 15) & ~15) > DEEP_SLD) return 2;
     // fewest batches: one CTA per SM of up to 512 threads; the 384-thread variant (more registers) when it needs no more
     const long long nb512 = (N + (long long)h->sm_count * 512 - 1) / ((long long)h->sm_count * 512);
@@ -1191,6 +1286,7 @@ static int launch_deep(rabi_maf* h, const DeepArgs& a, int mode, cudaStream_t st
     const bool big = nb512 < nb384 && env_int("RABI_DEEP_T", 512) > 384;
     if (h->D <= 12) return big ? launch_deep_dp<12, 512>(h, a, mode, N, st) : launch_deep_dp<12, 384>(h, a, mode, N, st);
     return big ? launch_deep_dp<32, 512>(h, a, mode, N, st) : launch_deep_dp<32, 384>(h, a, mode, N, st);
+#endif
 }
 
 extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_q_dev, const float* z_dev, int S, int B,
@@ -1335,7 +1431,8 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
             if (rc == 0) rc = 3;
         }
     } else {
-        rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_GRAD>(h, fa, st);
+        rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast2(h, fa, st);
+        if (rc == 2 && !env_int("RABI_FORCE_DEEP", 0)) rc = launch_fast<FAST_GRAD>(h, fa, st);
     }
     if (rc == 1) return 1;
     if (rc == 2) {  // deep path (global-memory scratch), gA accumulated with atomics

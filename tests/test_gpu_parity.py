@@ -508,3 +508,38 @@ def test_warp_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
             for gx, kl in outs[1:]:
                 assert float((kl - outs[0][1]).abs().max()) < 1e-5 * lp_scale
                 assert_trajectories_match(gx, outs[0][0], 1e-4)
+
+
+@pytest.mark.parametrize("shape", [dict(dx=100, D=4, hidden=[100, 100], B=301), dict(dx=100, D=4, hidden=[100, 100], B=2000),
+                                   dict(dx=12, D=3, hidden=[64, 48], B=130), dict(dx=7, D=2, hidden=[20, 36], B=77),
+                                   dict(dx=9, D=4, hidden=[104, 97], B=50)])
+def test_two_lanes_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
+    """maf_fast2.cuh (the attack gradient with two lanes per pair, used when a launch has at most 148 x 384 pairs) against
+    k_fast (RABI_FAST2=0) and the generic kernel (RABI_DISABLE_FAST=1): lotka_volterra shapes (compile-time leading
+    dimension), D < 4, widths that are not multiples of 8, ragged tiles."""
+    import os
+
+    ref, model, x = _fresh(shape, dev, seed=9)
+    xd = x.to(dev)
+    eng = model.engine()
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        q = model(xd)
+        _, zs, _ = model.condition_inputs(xd)
+        th = q.rsample((2,))
+        lp_scale = max(1.0, float(q.log_prob(th.clone()).abs().max()))
+        for S in (5, 1):
+            z = torch.randn(S, xd.shape[0], shape["D"], generator=g).to(dev)
+            outs = []
+            for env in ({"RABI_FAST2": "0"}, {}, {"RABI_DISABLE_FAST": "1"}):
+                env = dict(env, RABI_WARP_MAX_PAIRS="0")
+                os.environ.update(env)
+                try:
+                    gx, kl = eng.rkl_input_grad(xd + 0.05, zs[0], zs[1], q.A, z, 1.0 / xd.shape[0])
+                finally:
+                    for k in env:
+                        os.environ.pop(k, None)
+                outs.append((gx, kl))
+            for gx, kl in outs[1:]:
+                assert float((kl - outs[0][1]).abs().max()) < 1e-5 * lp_scale
+                assert_trajectories_match(gx, outs[0][0], 1e-4)
