@@ -381,11 +381,27 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                 // flight per pair); layer 0 then updates it in place, so the hot loop has no global-memory dependence
                 for (int u0 = 0; u0 < H0; u0 += 16) {
                     float av[RP][16];
+                    const float* ap[RP];  // walks the rows u0, u0 + 1, ... of A (idle slots read row 0 of the batch)
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const int u = min(u0 + c, H0 - 1);
+                    for (int r = 0; r < RP; ++r) ap[r] = Aptr[r] + (size_t)u0 * a.B;
+                    if (u0 + 16 <= H0) {
 #pragma unroll
-                        for (int r = 0; r < RP; ++r) av[r][c] = live[r] ? __ldg(Aptr[r] + (size_t)u * a.B) : 0.f;
+                        for (int c = 0; c < 16; ++c) {
+#pragma unroll
+                            for (int r = 0; r < RP; ++r) {
+                                av[r][c] = __ldg(ap[r]);
+                                ap[r] += a.B;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+#pragma unroll
+                            for (int r = 0; r < RP; ++r) {
+                                av[r][c] = __ldg(ap[r]);
+                                if (u0 + c + 1 < H0) ap[r] += a.B;  // units past the layer repeat its last row
+                            }
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -412,7 +428,7 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                             }
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                const int u = min(u0 + c, H0 - 1);
+                                const int u = u0 + c;  // W0t has round4(H0) + 4 rows: no clamp
 #pragma unroll
                                 for (int q4 = 0; q4 < DP / 4; ++q4) {
                                     const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
@@ -613,12 +629,11 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                     // ---- layer-1 cotangents of the degree-j units: g = relu'(.) * (WoT[v] . (mbar, sbar)) -> buffer
                     {
                         const int va = grp1[j], vb = grp1[j + 1];
-                        for (int v0 = va; v0 < vb; v0 += 4) {
+                        for (int v0 = va & ~3; v0 < vb; v0 += 4) {  // aligned quads: one relu nibble and one 128-bit store each
                             float gs[RP][4];
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                const int v = min(v0 + c, vb - 1);
-                                const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
+                                const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)(v0 + c) * 2 * DP);  // rows < round4(H1) + 4
                                 float2 g2[RP];
 #pragma unroll
                                 for (int r = 0; r < RP; ++r) g2[r] = make_float2(0.f, 0.f);
@@ -635,13 +650,21 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                                 for (int r = 0; r < RP; ++r) gs[r][c] = g2[r].x + g2[r].y;
                             }
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const int v = v0 + c;
-                                if (v < vb) {
+                            for (int r = 0; r < RP; ++r) {
+                                const uint32_t nib = bitp[r][(bs + 1) * WL + (v0 >> 5)] >> (v0 & 31);
 #pragma unroll
-                                    for (int r = 0; r < RP; ++r) {
-                                        const bool on = (bitp[r][(bs + 1) * WL + (v >> 5)] >> (v & 31)) & 1u;
-                                        ab[r].st1(v, on ? gs[r][c] : 0.f);
+                                for (int c = 0; c < 4; ++c) gs[r][c] = ((nib >> c) & 1u) ? gs[r][c] : 0.f;
+                            }
+                            if (v0 >= va && v0 + 4 <= vb) {
+#pragma unroll
+                                for (int r = 0; r < RP; ++r) ab[r].st4(v0, make_float4(gs[r][0], gs[r][1], gs[r][2], gs[r][3]));
+                            } else {  // a quad shared with a neighbouring degree group: only the own units
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    const int v = v0 + c;
+                                    if (v >= va && v < vb) {
+#pragma unroll
+                                        for (int r = 0; r < RP; ++r) ab[r].st1(v, gs[r][c]);
                                     }
                                 }
                             }
