@@ -192,8 +192,8 @@ def run_reference_arm(args, w, wname):
                               "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", wname],
                              env=env, capture_output=True, text=True)
         sys.stderr.write(out.stderr[-2000:])
-        print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else
-              json.dumps({"impl": "reference", "unavailable": "reference arm subprocess failed"}), flush=True)
+        emit(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else
+             json.dumps({"impl": "reference", "unavailable": "reference arm subprocess failed"}))
         return
     from rabi_b200.models import ZScoreLayer
 
@@ -217,7 +217,7 @@ def run_reference_arm(args, w, wname):
         "note": "the reference (pyro/advertorch/sbi) cannot be installed here; this arm times the oracle port of its "
                 "CPU path on all host threads",
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 
@@ -339,9 +339,20 @@ def run_next_rows(args):
         cpu_fn()
         t_c = cpu_s(cpu_fn)
         out[name] = {"gpu_ms_per_step": ms, "cpu_ms_per_step": 1e3 * t_c, "batch": B}
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+_RESULT_FD = None
+
+
+def emit(text):
+    """Write a result line to the process' original stdout (see main)."""
+    if _RESULT_FD is None:
+        print(text, flush=True)
+    else:
+        os.write(_RESULT_FD, (text + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -354,6 +365,12 @@ def main():
     ap.add_argument("--next-rows", action="store_true",
                     help="measure the SURVEY 8f rows (fKL eval, coverage / NLL metrics, defenses) instead of the bench line")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: whatever libraries print while the bench runs (e.g. NCCL's version banner under
+    # torchrun) is sent to stderr, and the result lines below are written to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.next_rows:
         return run_next_rows(args)
     w = dict(WORKLOADS[args.workload])
@@ -518,7 +535,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
