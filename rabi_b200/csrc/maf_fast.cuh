@@ -20,11 +20,8 @@
 
 #include "maf_image.h"
 
-#ifdef RABI_X_NOCLOBBER
-#define RABI_TM_CLOBBER
-#else
+// Tuning knobs of the product loops (compile-time; the defaults are the measured best on lotka_volterra shapes).
 #define RABI_TM_CLOBBER "memory"
-#endif
 #ifndef RABI_X_DOT_UNROLL
 #define RABI_X_DOT_UNROLL 2
 #endif
