@@ -705,7 +705,7 @@ static int launch_ctx_project(rabi_maf* h, const float* x, const float* delta, c
     const int slots = std::max(1, h->sm_count * per_sm / h->K);
     int rows = 64;
     {
-        int waves = (B + slots * 64 - 1) / (slots * 64);
+        int waves = (B + slots * CP_MAXROWS - 1) / (slots * CP_MAXROWS);  // as few waves as the largest tile allows
         int tiles = std::max(1, waves * slots);
         rows = std::min(CP_MAXROWS, std::max(4, ((B + tiles - 1) / tiles + 3) & ~3));
     }
