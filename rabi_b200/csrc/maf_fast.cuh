@@ -11,7 +11,7 @@
 //    dot-product direction), ReLU'd into a bit mask and folded straight into the 2D output accumulators;
 //  * the sequential sampling pass evaluates, at step j, only the units of MADE degree j (one pass-equivalent);
 //  * reverse mode is pull-style: the buffer holds the layer-1 cotangents, layer-0 cotangents are produced in
-//    registers per block, pushed into d/dy and reduced over the S samples of a row with shared-memory atomics.
+//    registers per block, pushed into d/dy and reduced over the S samples of a row with global float reductions.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,7 +38,8 @@ struct FastArgs {
     const float* z;     // [S,B,D]
     float* diff;        // [S,B] log p - log q (optional in GRAD mode); RSAMPLE: log q(own sample); LOGPROB: log q(theta)
     float* theta_out;   // RSAMPLE: [S,B,D]
-    float* gA;          // GRAD: [K,H0,B] d loss / d A_p (plain stores: every row belongs to exactly one tile)
+    float* gA;          // GRAD: [K,H0,B] d loss / d A_p, zeroed by the caller: the S samples of a row add their parts with
+                        // global reductions (shared-memory float atomics are CAS loops, and a tile needs flush barriers)
     int S, B;
     float w;
     int TB;             // GRAD: rows per tile; FWD: unused
@@ -46,7 +47,6 @@ struct FastArgs {
     int ntiles;
     int AS, VS, BWS;    // per-slot strides: activations (floats), vectors (floats), relu bit words
     int wfloats, wints; // per-transform weight / index block sizes (identical for all transforms)
-    int TBp;            // padded row count of the gA tile
     int tm_cols;        // TMEM columns to allocate (power of two >= 32) when the activations live in tensor memory
 };
 
@@ -219,8 +219,7 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
     const int WL = (g.Hmax + 31) >> 5;
     float* Ws = sm;
     int* Ms = reinterpret_cast<int*>(Ws + a.wfloats);
-    float* gAt = reinterpret_cast<float*>(Ms + a.wints);                    // [H0][TBp]  (GRAD only)
-    float* act = gAt + (fast_is_grad(MODE) ? (((size_t)H0 * a.TBp + 3) & ~(size_t)3) : 0);  // [RP*T][AS], 16-B aligned
+    float* act = reinterpret_cast<float*>(Ms + a.wints);                    // [RP*T][AS], 16-B aligned
     float* vec = act + (TM ? 0 : (size_t)RP * T * a.AS);                    // [RP*T][VS]  (TM: no smem activations)
     uint32_t* bits = reinterpret_cast<uint32_t*>(vec + (size_t)RP * T * a.VS);  // [RP*T][BWS] (GRAD only)
 
@@ -326,10 +325,6 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
             const int b = (int)(pidx[r] % a.B);
             Ap[r] = a.A_p + b;
             Aq[r] = a.A_q + b;
-        }
-        if (fast_is_grad(MODE)) {
-            __syncthreads();
-            for (int i = tid; i < H0 * a.TBp; i += T) gAt[i] = 0.f;
         }
         float logp[RP], logq[RP];
 #pragma unroll
@@ -696,7 +691,8 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                                         const float gv = ((wb[r] >> c) & 1u) ? g0[r][c] : 0.f;
 #pragma unroll
                                         for (int jj = 0; jj < DP; ++jj) yb[r][jj] = fmaf(wrow[jj], gv, yb[r][jj]);
-                                        if ((seq || MODE == FAST_FKL) && live[r]) atomicAdd(gAt + (size_t)u * a.TBp + rrow[r], gv);
+                                        if ((seq || MODE == FAST_FKL) && live[r])  // sum over the S samples of the row: RED.ADD.F32 into the zeroed gA
+                                            atomicAdd(a.gA + ((size_t)k * H0 + u) * a.B + b0 + rrow[r], gv);
                                     }
                                 }
                             }
@@ -720,15 +716,6 @@ __global__ void __launch_bounds__(RP != 1 ? 256 : (fast_is_grad(MODE) ? 384 : 51
                             if (seq) vecp[r][oG + perm[jj]] = zb[r][jj];
                             else vecp[r][oG + permy[jj]] = yb[r][jj];
                         }
-                if (seq || MODE == FAST_FKL) {  // flush the gA tile of this transform (rows of this tile are owned by this CTA alone)
-                    __syncthreads();
-                    for (int i = tid; i < H0 * rows_here; i += T) {
-                        const int u = i / rows_here, rr = i % rows_here;
-                        a.gA[((size_t)k * H0 + u) * a.B + b0 + rr] = gAt[(size_t)u * a.TBp + rr];
-                        gAt[(size_t)u * a.TBp + rr] = 0.f;
-                    }
-                    __syncthreads();
-                }
             }
         }
         if (MODE == FAST_RSAMPLE) {

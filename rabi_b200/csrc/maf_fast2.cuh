@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(704, 1) k_fast2(const MafImg g, const FastArgs
     const int WL = (g.Hmax + 31) >> 5;
     float* Ws = sm;
     int* Ms = reinterpret_cast<int*>(Ws + a.wfloats);
-    float* gAt = reinterpret_cast<float*>(Ms + a.wints);                        // [H0][TBp]
-    float* vec = gAt + (((size_t)H0 * a.TBp + 3) & ~(size_t)3);                 // [NPS][VS]
+    float* vec = reinterpret_cast<float*>(Ms + a.wints);                        // [NPS][VS]
     uint32_t* bits = reinterpret_cast<uint32_t*>(vec + (size_t)NPS * a.VS);     // [NPS][BWS]
 
     const float* W0t = Ws + rel.W0t;
@@ -177,8 +176,6 @@ __global__ void __launch_bounds__(704, 1) k_fast2(const MafImg g, const FastArgs
         const long long pidx = (long long)s * a.B + b0 + rrow;
         const float* Ap = a.A_p + (b0 + rrow);
         const float* Aq = a.A_q + (b0 + rrow);
-        __syncthreads();
-        for (int i = tid; i < H0 * a.TBp; i += T) gAt[i] = 0.f;
         float logp, logq = 0.f;
         {
             float ssq = 0.f;
@@ -455,7 +452,7 @@ __global__ void __launch_bounds__(704, 1) k_fast2(const MafImg g, const FastArgs
                                     const float2 wt = *reinterpret_cast<const float2*>(W0t + (size_t)u * DP + 2 * L);
                                     ybo[0] = fmaf(wt.x, gv, ybo[0]);
                                     ybo[1] = fmaf(wt.y, gv, ybo[1]);
-                                    if (seq && live && (c & 1) == L) atomicAdd(gAt + (size_t)u * a.TBp + rrow, gv);
+                                    if (seq && live && (c & 1) == L) atomicAdd(a.gA + ((size_t)k * H0 + u) * a.B + b0 + rrow, gv);
                                 }
                             }
                         };
@@ -478,15 +475,6 @@ __global__ void __launch_bounds__(704, 1) k_fast2(const MafImg g, const FastArgs
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
                         if (2 * L + i < D) vecp[oG + permy[2 * L + i]] = ybo[i];
-                }
-                if (seq) {  // flush the gA tile of this transform (rows of this tile are owned by this CTA alone)
-                    __syncthreads();
-                    for (int i = tid; i < H0 * rows_here; i += T) {
-                        const int u = i / rows_here, rr = i % rows_here;
-                        a.gA[((size_t)k * H0 + u) * a.B + b0 + rr] = gAt[(size_t)u * a.TBp + rr];
-                        gAt[(size_t)u * a.TBp + rr] = 0.f;
-                    }
-                    __syncthreads();
                 }
             }
         }

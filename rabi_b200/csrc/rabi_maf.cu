@@ -990,7 +990,6 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     int grid = 0;
     size_t smem = 0;
     const long long npairs = (long long)fa.S * fa.B;
-    auto gat_bytes = [&](int tbp) { return (((size_t)H0 * tbp + 3) & ~(size_t)3) * sizeof(float); };
     if (fast_is_grad(MODE)) {
         // largest T whose slots (+ the gA tile for the rows they hold) fit
         for (;; T -= 32) {
@@ -998,7 +997,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
             int slots = RP * T;
             int tb = slots / fa.S;
             if (tb < 1) return 2;  // one row's samples do not fit in a tile
-            smem = fixed + gat_bytes(tb | 1) + (size_t)slots * per_slot;
+            smem = fixed + (size_t)slots * per_slot;
             if (smem <= budget) break;
         }
         int tb_cap = (RP * T) / fa.S;
@@ -1009,8 +1008,7 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
         fa.ntiles = (fa.B + fa.TB - 1) / fa.TB;
         int Tneed = ((fa.TB * fa.S + RP - 1) / RP + 31) & ~31;     // no idle warps
         T = std::min(T, std::max(32, Tneed));
-        fa.TBp = fa.TB | 1;
-        smem = fixed + gat_bytes(fa.TBp) + (size_t)RP * T * per_slot;
+        smem = fixed + (size_t)RP * T * per_slot;
         grid = std::min(fa.ntiles, h->sm_count);
     } else {
         for (;; T -= 32) {
@@ -1019,7 +1017,6 @@ static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st) {
             if (smem <= budget) break;
         }
         fa.NP = RP * T;
-        fa.TBp = 0;
         long long nt = (npairs + fa.NP - 1) / fa.NP;
         if (nt > 0x7fffffff) return 2;
         fa.ntiles = (int)nt;
@@ -1076,9 +1073,9 @@ static int launch_fast2(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     const MafImg& g = h->img;
     const TImg& t0 = g.t[0];
     const int K = h->K, D = h->D, H0 = h->H[0], H1 = h->H[1];
-    // pays when a thread per pair leaves the schedulers short of warps (measured on lotka_volterra shapes: 1.11-1.2x up to
-    // ~100 pairs per SM, even at ~170, slower once k_fast has its full 11 warps per SM); RABI_FAST2=2 forces it
-    if (env_int("RABI_FAST2", 1) != 2 && (long long)fa.S * fa.B > (long long)h->sm_count * env_int("RABI_FAST2_MAX_PER_SM", 128)) return 2;
+    // pays only while a thread per pair leaves the schedulers nearly empty (measured on lotka_volterra shapes after k_fast's
+    // own trimming: 2-3 % below ~40 pairs per SM, even at ~150, 14 % slower with the SMs full); RABI_FAST2=2 forces it
+    if (env_int("RABI_FAST2", 1) != 2 && (long long)fa.S * fa.B > (long long)h->sm_count * env_int("RABI_FAST2_MAX_PER_SM", 40)) return 2;
     if ((long long)fa.S * fa.B > (long long)h->sm_count * 352) return 2;  // one wave of 704-thread tiles
     FastRel rel;
     rel.W0t = 0;
@@ -1105,7 +1102,6 @@ static int launch_fast2(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     const size_t per_slot = (size_t)(fa.VS + fa.BWS) * sizeof(float);
     const size_t fixed = (size_t)(fa.wfloats + fa.wints) * sizeof(float);
     const size_t budget = (size_t)h->max_smem_optin - 1024;
-    auto gat_bytes = [&](int tbp) { return (((size_t)H0 * tbp + 3) & ~(size_t)3) * sizeof(float); };
     int T = 704;
     while (T > 64 && ((T / 32 + 3) / 4) * fa.AS + 4 > 512) T -= 64;  // + 4: the look-ahead quad of the product loops
     size_t smem = 0;
@@ -1113,7 +1109,7 @@ static int launch_fast2(rabi_maf* h, FastArgs fa, cudaStream_t st) {
         if (T < 64) return 2;
         const int tb = (T / 2) / fa.S;
         if (tb < 1) return 2;
-        smem = fixed + gat_bytes(tb | 1) + (size_t)(T / 2) * per_slot;
+        smem = fixed + (size_t)(T / 2) * per_slot;
         if (smem <= budget) break;
     }
     const int tb_cap = (T / 2) / fa.S;
@@ -1124,8 +1120,7 @@ static int launch_fast2(rabi_maf* h, FastArgs fa, cudaStream_t st) {
     fa.ntiles = (fa.B + fa.TB - 1) / fa.TB;
     const int Tneed = (2 * fa.TB * fa.S + 63) & ~63;
     T = std::min(T, std::max(64, Tneed));
-    fa.TBp = fa.TB | 1;
-    smem = fixed + gat_bytes(fa.TBp) + (size_t)(T / 2) * per_slot;
+    smem = fixed + (size_t)(T / 2) * per_slot;
     const int grid = std::min(fa.ntiles, h->sm_count);
     fa.tm_cols = 32;
     const int need = ((T / 32 + 3) / 4) * fa.AS + 4;
@@ -1394,6 +1389,8 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
     fa.B = B;
     fa.w = inv_B / (float)S;
     int rc;
+    // every kernel family adds the S samples' parts of d/dA_p into gA (float reductions in global memory)
+    CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
     {   // small batches (training-time attacks): one warp per pair
         PairArgs wa = {};
         wa.A_p = forward_kl ? A_q : A_p;   // forward KL: samples come from the fixed target
@@ -1405,7 +1402,6 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
         wa.B = B;
         wa.w = inv_B / (float)S;
         if ((long long)S * B <= env_int("RABI_WARP_MAX_PAIRS", 1024) && !env_int("RABI_FORCE_DEEP", 0)) {
-            CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
             rc = forward_kl ? launch_warp<WARP_FKL_GRAD>(h, wa, st) : launch_warp<WARP_RKL_GRAD>(h, wa, st);
             if (rc == 1) return 1;
             if (rc == 0) goto grad_done;
@@ -1416,7 +1412,6 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
         fa.A_q = A_p;
         rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_FKL>(h, fa, st);
         if (rc == 2) {
-            CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
             DeepArgs da = {};
             da.A_p = A_q;   // samples come from the fixed target
             da.A_q = A_p;   // the density pass under x + delta is the differentiated one
@@ -1436,7 +1431,6 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
     }
     if (rc == 1) return 1;
     if (rc == 2) {  // deep path (global-memory scratch), gA accumulated with atomics
-        CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
         DeepArgs da = {};
         da.A_p = A_p;
         da.A_q = A_q;
@@ -1451,7 +1445,6 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
         if (rc == 0) rc = 3;  // done
     }
     if (rc == 2) {  // generic per-pair kernel (accumulates gA with atomics)
-        CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
         PairArgs a = {};
         a.A_p = A_p;
         a.A_q = A_q;

@@ -514,7 +514,7 @@ def test_warp_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
                                    dict(dx=12, D=3, hidden=[64, 48], B=130), dict(dx=7, D=2, hidden=[20, 36], B=77),
                                    dict(dx=9, D=4, hidden=[104, 97], B=50)])
 def test_two_lanes_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
-    """maf_fast2.cuh (the attack gradient with two lanes per pair, used when a launch has at most 148 x 384 pairs) against
+    """maf_fast2.cuh (the attack gradient with two lanes per pair, by default only for launches of at most 40 pairs per SM) against
     k_fast (RABI_FAST2=0) and the generic kernel (RABI_DISABLE_FAST=1): lotka_volterra shapes (compile-time leading
     dimension), D < 4, widths that are not multiples of 8, ragged tiles."""
     import os
@@ -531,7 +531,7 @@ def test_two_lanes_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
         for S in (5, 1):
             z = torch.randn(S, xd.shape[0], shape["D"], generator=g).to(dev)
             outs = []
-            for env in ({"RABI_FAST2": "0"}, {}, {"RABI_DISABLE_FAST": "1"}):
+            for env in ({"RABI_FAST2": "0"}, {"RABI_FAST2": "2"}, {"RABI_DISABLE_FAST": "1"}):  # k_fast, k_fast2 (forced), generic
                 env = dict(env, RABI_WARP_MAX_PAIRS="0")
                 os.environ.update(env)
                 try:
