@@ -18,9 +18,14 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
-SOURCES = ["rabi_maf.cu"]
+# translation units and the headers each one depends on (an object is rebuilt when one of them is newer)
+_COMMON = ["rabi_internal.h", "maf_image.h", "maf_tc.h"]
+SOURCES = {
+    "rabi_maf.cu": _COMMON + ["maf_pairs.cuh", "maf_fast.cuh", "maf_fast2.cuh", "maf_deep.cuh", "maf_warp.cuh"],
+    "maf_tc.cu": _COMMON,
+}
 
 EXPORTS = [
     "rabi_build_info", "rabi_last_error", "rabi_maf_create", "rabi_maf_destroy", "rabi_maf_set_permutation",
@@ -36,31 +41,46 @@ class RabiError(RuntimeError):
     pass
 
 
-def _sources():
-    out = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "rabi_b200.h")]
-    return out, deps
+def _nvcc() -> str:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return nvcc if os.path.exists(nvcc) else "nvcc"
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu -> _lib/librabi_b200.so (sm_100a).  Rebuilds when a source is newer than the .so."""
-    srcs, deps = _sources()
-    if not force and os.path.exists(LIB_PATH):
-        so_m = os.path.getmtime(LIB_PATH)
-        if all(os.path.getmtime(d) <= so_m for d in deps):
-            return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if not os.path.exists(nvcc):
-        nvcc = "nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, *srcs]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RabiError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    """Compile csrc/*.cu -> _lib/obj/*.o -> _lib/librabi_b200.so (sm_100a; cross-compiles without a GPU).  Every
+    translation unit is rebuilt only when it or one of its headers is newer than its object; the units compile in
+    parallel.  ``RABI_NVCC_EXTRA`` adds flags (e.g. ``-DRABI_LEAN`` for kernel experiments)."""
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    extra = os.environ.get("RABI_NVCC_EXTRA", "").split()
+    stamp = os.path.join(obj_dir, "flags.txt")
+    flags_now = " ".join(NVCC_FLAGS + extra)
+    if not os.path.exists(stamp) or open(stamp).read() != flags_now:
+        force = True
+    jobs, objs = [], []
+    for src, hdrs in SOURCES.items():
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, x) for x in hdrs] + [os.path.join(INCLUDE, "rabi_b200.h")]
+        if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+            continue
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, proc in jobs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RabiError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
+        if verbose:
+            print(out)
+    if jobs or not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH, *objs]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RabiError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    with open(stamp, "w") as f:
+        f.write(flags_now)
     return LIB_PATH
 
 

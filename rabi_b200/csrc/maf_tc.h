@@ -1,0 +1,25 @@
+// Tensor-core path (maf_tc.cu): interface towards the launch dispatch in rabi_maf.cu.
+#pragma once
+#include "rabi_internal.h"
+
+namespace rabi {
+
+// same numbering as FastMode (maf_fast.cuh)
+enum TcMode { TC_FWD = 0, TC_GRAD = 1, TC_FKL = 2, TC_RSAMPLE = 3, TC_LOGPROB = 4 };
+
+struct TcCall {
+    const float* A_p;   // [K,H0,B] projection of the sampled-from posterior (LOGPROB: unused)
+    const float* A_q;   // [K,H0,B] projection of the posterior whose density is evaluated
+    const float* z;     // [S,B,D] base noise (LOGPROB: theta)
+    float* diff;        // [S,B] log p - log q | log q(own sample) | log q(theta); optional in the gradient modes
+    float* theta_out;   // RSAMPLE: [S,B,D]
+    float* gA;          // GRAD / FKL: [K,H0,B], zeroed by the caller; the pairs add their parts with float reductions
+    int S, B;
+    float w;            // weight of one pair in the loss (inv_B / S)
+};
+
+// returns 0 = launched, 1 = error (message on the handle), 2 = shape / launch not eligible for this path
+int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st);
+void rabi_tc_destroy(rabi_maf* h);
+
+}  // namespace rabi

@@ -9,47 +9,19 @@
 #include <string>
 #include <vector>
 
-#include "../../include/rabi_b200.h"
-#include "maf_image.h"
+#include "rabi_internal.h"
 #include "maf_pairs.cuh"
 #include "maf_fast.cuh"
 #include "maf_fast2.cuh"
 #include "maf_deep.cuh"
 #include "maf_warp.cuh"
+#include "maf_tc.h"
 
 using namespace rabi;
 
 static std::string g_create_error;
 
-struct rabi_maf {
-    int device = 0;
-    int K = 0, D = 0, C = 0, L = 0;
-    int H[RABI_MAXL] = {0, 0, 0, 0};
-    float lo = -5.f, hi = 3.f;
-    bool finalized = false;
-    std::vector<std::vector<int64_t>> perm;               // [K][D]
-    std::vector<std::vector<int64_t>> post;               // [K][D] optional Permute layer after transform k
-    std::vector<std::vector<std::vector<float>>> masks;   // [K][L+1][out*in]
-    MafImg img;                                           // device pointers inside
-    std::vector<int> meta_host;
-    float* f_dev = nullptr;
-    int* m_dev = nullptr;
-    size_t n_float = 0, n_int = 0;
-    void* ws = nullptr;
-    size_t ws_bytes = 0;
-    void* deep_ws = nullptr;   // per-pair scratch of the deep path (maf_deep.cuh), zero-initialised on allocation
-    size_t deep_ws_bytes = 0;
-    unsigned long long launches = 0;
-    // optional CUDA-event timing of the dominant kernel (k_pairs<RKL_GRAD>) on its launch stream
-    bool profiling = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
-    size_t prof_used = 0;
-    std::string err;
-    int sm_count = 148;
-    int max_smem_optin = 0;
-};
-
-static int fail(rabi_maf* h, const char* fmt, ...) {
+int rabi_fail(rabi_maf* h, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
     va_start(ap, fmt);
@@ -61,6 +33,13 @@ static int fail(rabi_maf* h, const char* fmt, ...) {
         g_create_error = buf;
     return 1;
 }
+#define fail rabi_fail
+
+int rabi_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+#define env_int rabi_env_int
 
 #define CU_OK(h, expr)                                                                      \
     do {                                                                                    \
@@ -113,6 +92,7 @@ extern "C" int rabi_maf_create(rabi_maf_t** out, int device, int K, int D, int C
 extern "C" int rabi_maf_destroy(rabi_maf_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    rabi_tc_destroy(h);
     if (h->f_dev) cudaFree(h->f_dev);
     if (h->m_dev) cudaFree(h->m_dev);
     if (h->ws) cudaFree(h->ws);
@@ -355,6 +335,8 @@ extern "C" int rabi_maf_finalize_structure(rabi_maf_t* h) {
     g.f = h->f_dev;
     g.m = h->m_dev;
     h->finalized = true;
+    rabi_tc_destroy(h);   // derived images are rebuilt for the new structure
+    h->weights_version++;
     return 0;
 }
 
@@ -432,6 +414,7 @@ extern "C" int rabi_maf_set_weights(rabi_maf_t* h, int k, int layer, const float
     else
         k_pack_out<<<nb, 256, 0, st>>>(h->img, k, W_dev, b_dev, h->f_dev);
     LAUNCH_CHECK(h);
+    h->weights_version++;
     return 0;
 }
 
@@ -796,6 +779,24 @@ extern "C" int rabi_profile_read(rabi_maf_t* h, double* total_ms, unsigned long 
     return 0;
 }
 
+int rabi_prof_begin(rabi_maf* h, cudaStream_t st) {
+    if (!h->profiling) return 0;
+    if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t e0, e1;
+        CU_OK(h, cudaEventCreate(&e0));
+        CU_OK(h, cudaEventCreate(&e1));
+        h->prof_events.push_back({e0, e1});
+    }
+    CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].first, st));
+    return 0;
+}
+int rabi_prof_end(rabi_maf* h, cudaStream_t st) {
+    if (!h->profiling) return 0;
+    CU_OK(h, cudaEventRecord(h->prof_events[h->prof_used].second, st));
+    h->prof_used++;
+    return 0;
+}
+
 // fp32 FMA-pipe peak (roofline denominator for the FMA-bound kernels; MEASURED_PEAKS.json has no fp32 entry)
 __global__ void k_fma_peak(float* out, int iters, float a, float b) {
     float acc[16];
@@ -842,7 +843,6 @@ extern "C" double rabi_fma_peak_tflops(int device, int repeats) {
 template <int MODE>
 static int launch_fast(rabi_maf* h, FastArgs fa, cudaStream_t st);  // defined below
 static int launch_deep(rabi_maf* h, const DeepArgs& a, int mode, cudaStream_t st);
-static int env_int(const char* name, int dflt);
 
 extern "C" int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const float* theta_dev, int S, int B,
                                      float* logp_dev, rabi_stream_t s) {
@@ -861,7 +861,12 @@ extern "C" int rabi_maf_log_prob_fwd(rabi_maf_t* h, const float* A_dev, const fl
         fa.diff = logp_dev;
         fa.S = S;
         fa.B = B;
-        int rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_LOGPROB>(h, fa, (cudaStream_t)s);
+        int rc = 2;
+        if (!env_int("RABI_FORCE_DEEP", 0)) {
+            TcCall tc = {nullptr, A_dev, theta_dev, logp_dev, nullptr, nullptr, S, B, 0.f};
+            rc = rabi_tc_launch(h, tc, TC_LOGPROB, (cudaStream_t)s);
+            if (rc == 2) rc = launch_fast<FAST_LOGPROB>(h, fa, (cudaStream_t)s);
+        }
         if (rc != 2) return rc;
         DeepArgs da = {};
         da.A_p = A_dev;
@@ -895,7 +900,12 @@ extern "C" int rabi_maf_rsample_fwd(rabi_maf_t* h, const float* A_dev, const flo
         fa.diff = logq_dev;
         fa.S = S;
         fa.B = B;
-        int rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_RSAMPLE>(h, fa, (cudaStream_t)s);
+        int rc = 2;
+        if (!env_int("RABI_FORCE_DEEP", 0)) {
+            TcCall tc = {A_dev, A_dev, z_dev, logq_dev, theta_dev, nullptr, S, B, 0.f};
+            rc = rabi_tc_launch(h, tc, TC_RSAMPLE, (cudaStream_t)s);
+            if (rc == 2) rc = launch_fast<FAST_RSAMPLE>(h, fa, (cudaStream_t)s);
+        }
         if (rc != 2) return rc;
         DeepArgs da = {};
         da.A_p = A_dev;
@@ -914,10 +924,6 @@ extern "C" int rabi_maf_rsample_fwd(rabi_maf_t* h, const float* A_dev, const flo
 // ---------------------------------------------------------------------------------------------------------
 // fast path launcher (maf_fast.cuh).  Returns 0 = launched, 1 = error, 2 = configuration not eligible (caller
 // falls back to the generic per-pair kernel).
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
 
 template <int MODE, int RP, int DP, bool TM, int LDC>
 static int launch_fast_inst(rabi_maf* h, const FastArgs& fa, const FastRel& rel, int grid, int T, size_t smem,
@@ -1305,7 +1311,12 @@ extern "C" int rabi_rkl_fwd(rabi_maf_t* h, const float* A_p_dev, const float* A_
         fa.diff = (float*)h->ws;
         fa.S = S;
         fa.B = B;
-        int rc = env_int("RABI_FORCE_DEEP", 0) ? 2 : launch_fast<FAST_FWD>(h, fa, st);
+        int rc = 2;
+        if (!env_int("RABI_FORCE_DEEP", 0)) {
+            TcCall tc = {A_p_dev, A_q_dev, z_dev, (float*)h->ws, nullptr, nullptr, S, B, 0.f};
+            rc = rabi_tc_launch(h, tc, TC_FWD, st);
+            if (rc == 2) rc = launch_fast<FAST_FWD>(h, fa, st);
+        }
         if (rc == 1) return 1;
         if (rc == 2) {
             DeepArgs da = {};
@@ -1391,6 +1402,13 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
     int rc;
     // every kernel family adds the S samples' parts of d/dA_p into gA (float reductions in global memory)
     CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
+    if (!env_int("RABI_FORCE_DEEP", 0) && (long long)S * B >= env_int("RABI_TC_GRAD_MIN_PAIRS", 1)) {
+        // tensor-core path (maf_tc.cu): two-hidden-layer conditioners up to 104 units wide
+        TcCall tc = {forward_kl ? A_q : A_p, forward_kl ? A_p : A_q, z, kl ? diff : nullptr, nullptr, gA, S, B, inv_B / (float)S};
+        rc = rabi_tc_launch(h, tc, forward_kl ? TC_FKL : TC_GRAD, st);
+        if (rc == 1) return 1;
+        if (rc == 0) goto grad_done;
+    }
     {   // small batches (training-time attacks): one warp per pair
         PairArgs wa = {};
         wa.A_p = forward_kl ? A_q : A_p;   // forward KL: samples come from the fixed target
