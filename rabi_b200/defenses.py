@@ -96,6 +96,7 @@ class FIMTraceRegularizer(AdditiveRegularizer):
         # every step -- the unfused path is ~1.7k tiny launches, i.e. launch-bound; replay runs them back to back.
         self.cuda_graph = cuda_graph
         self._graphs = {}
+        self._ema_static = None
         self.beta = beta
         self.algorithm = algorithm
         self.mc_samples = mc_samples
@@ -140,14 +141,26 @@ class FIMTraceRegularizer(AdditiveRegularizer):
         from . import noise
         params = list(self.model.parameters())
         key = (tuple(input.shape), input.device, tuple(id(p) for p in params))
-        st = self._graphs.get(key)
         D = self.model.output_dim
+        # ONE set of static EMA buffers (average m, step count t) shared by every captured graph: a second input shape
+        # (e.g. the smaller last batch of an epoch) must continue the same average, not start its own
+        shared = self._ema_static
+        if shared is None or shared["key"] != (input.device, tuple(id(p) for p in params)):
+            shared = self._ema_static = {"key": (input.device, tuple(id(p) for p in params)),
+                                         "t": torch.zeros((), device=input.device),
+                                         "m": [m.detach().clone() for m in self.ema._x_old]}
+            self._graphs = {}
+        if self.ema._x_old is not shared["m"]:   # an eager step ran in between: take its state over
+            for m_s, m_h in zip(shared["m"], self.ema._x_old):
+                m_s.copy_(m_h.detach())
+        shared["t"].fill_(float(self.ema.t))
+        st = self._graphs.get(key)
         if st is None:
             d = float(self.ema.decay)
             st = {"x": input.detach().clone(),
                   "z": torch.empty((self.ema_mc_samples, input.shape[0], D), device=input.device),
-                  "t": torch.full((), float(self.ema.t), device=input.device),
-                  "m": [m.detach().clone() for m in self.ema._x_old],
+                  "t": shared["t"],
+                  "m": shared["m"],
                   "grads": [torch.zeros_like(p) for p in params]}
             side = torch.cuda.Stream(device=input.device)
             side.wait_stream(torch.cuda.current_stream(input.device))
@@ -176,7 +189,7 @@ class FIMTraceRegularizer(AdditiveRegularizer):
         st["z"].normal_()
         st["graph"].replay()
         self.ema.t += 1
-        self.ema._x_old = st["m"]
+        self.ema._x_old = shared["m"]
         for p, g_ in zip(params, st["grads"]):
             p.grad = g_
         if self.grad_clamp_val is not None:

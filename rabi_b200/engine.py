@@ -48,6 +48,10 @@ class MafEngine:
             self.h = None
             raise ValueError(msg) if "Hidden dimension" in msg else RabiError(msg)
         self._versions = None
+        self.epoch = 0   # bumped whenever a layer is re-packed: projections computed before are stale
+
+    def invalidate(self):
+        self._versions = None
 
     def __del__(self):
         try:
@@ -101,6 +105,9 @@ class MafEngine:
     def set_weights(self, params: List[List[Tuple[torch.Tensor, torch.Tensor]]]):
         """params[k][layer] = (weight, bias) CUDA fp32 tensors; re-packs only what changed since the last call."""
         vers = [[(w.data_ptr(), w._version, b.data_ptr(), b._version) for (w, b) in pk] for pk in params]
+        if self._versions == vers:
+            return
+        self.epoch += 1
         with torch.cuda.device(self.device):
             for k, pk in enumerate(params):
                 for l, (w, b) in enumerate(pk):

@@ -133,12 +133,13 @@ class MAFPosterior(Distribution):
     has_rsample = True
 
     def __init__(self, model: "InverseAffineAutoregressiveModel", ctx_in: Tensor, zscore, batch_shape,
-                 output_transform: Optional[Transform], A: Optional[Tensor] = None):
+                 output_transform: Optional[Transform], A: Optional[Tensor] = None, A_epoch: Optional[int] = None):
         self.model = model
         self.ctx_in = ctx_in          # [Bf, C] flattened rows: raw x when the z-score is fused, else embedded h
         self.zscore = zscore          # (mean, std) or None
         self.output_transform = output_transform
         self._A = A
+        self._A_epoch = A_epoch       # weight epoch of the engine the projection was computed with
         self._last = None             # (theta object, log q) of the last rsample: the "free" log_prob (Q9)
         super().__init__(torch.Size(batch_shape), torch.Size([model.output_dim]), validate_args=False)
 
@@ -152,10 +153,11 @@ class MAFPosterior(Distribution):
     @property
     def A(self) -> Tensor:
         """Layer-0 context projection of all K transforms, [K, H0, Bf] (computed once per conditioned object)."""
-        if self._A is None:
-            eng = self.model.engine()
+        eng = self.model.engine()   # re-packs the weight image if a parameter changed since the last call
+        if self._A is None or self._A_epoch != eng.epoch:   # a projection made with older weights is stale
             zs = self.zscore if self.zscore is not None else (None, None)
             self._A = eng.ctx_project(self.ctx_in, zs[0], zs[1])
+            self._A_epoch = eng.epoch
         return self._A
 
     def expand(self, batch_shape, _instance=None):
@@ -164,7 +166,8 @@ class MAFPosterior(Distribution):
             return self
         Bf = self.ctx_in.shape[0]
         if batch_shape.numel() == Bf:  # pure reshape (e.g. [B] -> [1, B])
-            return MAFPosterior(self.model, self.ctx_in, self.zscore, batch_shape, self.output_transform, self._A)
+            return MAFPosterior(self.model, self.ctx_in, self.zscore, batch_shape, self.output_transform, self._A,
+                                self._A_epoch)
         ctx = self.ctx_in.reshape(self.batch_shape + self.ctx_in.shape[-1:]).expand(batch_shape + self.ctx_in.shape[-1:])
         return MAFPosterior(self.model, ctx.reshape(-1, ctx.shape[-1]).contiguous(), self.zscore, batch_shape,
                             self.output_transform)
@@ -212,7 +215,17 @@ class MAFPosterior(Distribution):
 
     def log_prob(self, value: Tensor) -> Tensor:
         if self._last is not None and value is self._last[0]:
-            return self._last[1]  # samples just drawn from this very object: no MADE pass (reference cache hit)
+            # samples just drawn from this very object: no MADE pass (the reference's cache hit) -- but only
+            # when the cached value carries what the caller can ask of it: a sample drawn under no_grad has a detached
+            # log q, and a later differentiable log_prob(theta) must be recomputed with its graph
+            if self._last[1].requires_grad or not self._needs_grad(value):
+                return self._last[1]
+        nb = len(self.batch_shape)
+        full = torch.broadcast_shapes(value.shape[:-1], self.batch_shape)
+        if nb and full[len(full) - nb:] != self.batch_shape:
+            # the value's batch dims are larger than ours (e.g. q = model(x[1, dx]); q.log_prob(thetas[N, D])): Pyro's
+            # ConditionalAutoRegressiveNN expands the context, so do we
+            return self.expand(full[len(full) - nb:]).log_prob(value)
         ldj = None
         if self.output_transform is not None:
             u = self.output_transform.inv(value)
@@ -340,6 +353,13 @@ class InverseAffineAutoregressiveModel(nn.Module):
 
     def transforms_params(self):
         return [[(l.weight, l.bias) for l in getattr(self, "t" + str(i)).nn.layers] for i in range(self.num_transforms)]
+
+    def invalidate(self):
+        """Force a re-pack of the device weight image on the next call.  Needed only after in-place updates that do
+        not bump the parameters' version counters (``p.data.copy_()`` / ``p.data.mul_()``, e.g. EMA-of-weights or
+        weight-clipping code); optimizer steps, ``load_state_dict`` and ``.to()`` are detected automatically."""
+        if self._engine is not None:
+            self._engine.invalidate()
 
     def engine(self) -> MafEngine:
         dev = self.base_dist_mean.device
