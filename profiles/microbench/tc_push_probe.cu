@@ -318,8 +318,12 @@ static int run_single(int K, int N, int NP, int ss) {
     return e != cudaSuccess;
 }
 
+int run_ldalign();
+int run_rt();
 int main(int argc, char** argv) {
     const char* t = argc > 1 ? argv[1] : "push";
+    if (!strcmp(t, "rt")) return run_rt();
+    if (!strcmp(t, "ldalign")) return run_ldalign();
     if (!strcmp(t, "push")) {
         int bad = 0;
         bad |= run_push(1, 96, 112, 24, 0, 1, 1);      // lotka_volterra-like chunks
@@ -341,4 +345,145 @@ int main(int argc, char** argv) {
         return run_single(32, N, ((N + 15) / 16) * 16, 0);
     }
     return 2;
+}
+
+// ---- "ldalign": tcgen05.ld / st .32x32b.x8 / .x2 at column addresses that are not multiples of the vector width
+__global__ void __launch_bounds__(128, 1) k_ldalign(float* out, int* bad) {
+    __shared__ uint32_t tbase_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(&tbase_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tbase_s + ((uint32_t)(32 * warp) << 16);
+    for (int c = 0; c < 128; ++c) {
+        const float v = (float)(tid * 1000 + c);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(trow + c), "f"(v) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    int nbad = 0;
+    for (int c0 = 0; c0 < 24; ++c0) {
+        float v[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(trow + c0) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int e = 0; e < 8; ++e) nbad += v[e] != (float)(tid * 1000 + c0 + e);
+        float w0, w1;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(w0), "=f"(w1) : "r"(trow + 40 + c0) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        nbad += (w0 != (float)(tid * 1000 + 40 + c0)) + (w1 != (float)(tid * 1000 + 41 + c0));
+    }
+    // unaligned x8 store, read back with x1
+    for (int c0 = 65; c0 < 70; ++c0) {
+        float v[8];
+        for (int e = 0; e < 8; ++e) v[e] = (float)(-(tid * 1000 + c0 * 10 + e));
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     :: "r"(trow + c0), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        for (int e = 0; e < 8; ++e) {
+            float r;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(r) : "r"(trow + c0 + e) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            nbad += r != v[e];
+        }
+    }
+    if (nbad) atomicAdd(bad, nbad);
+    out[tid] = (float)nbad;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tbase_s) : "memory");
+}
+int run_ldalign() {
+    float* od; int* bd; int bad = -1;
+    cudaMalloc(&od, 128 * 4); cudaMalloc(&bd, 4); cudaMemset(bd, 0, 4);
+    k_ldalign<<<1, 128>>>(od, bd);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(&bad, bd, 4, cudaMemcpyDeviceToHost);
+    printf("ldalign: %s  mismatches %d (x8 / x2 loads and x8 stores at arbitrary column offsets)\n", cudaGetErrorString(e), bad);
+    return e != cudaSuccess || bad != 0;
+}
+
+// ---- "rt": the bare staging -> MMA -> read-back round trip (no global memory in the loop), one tile of 128 threads:
+// each step stages 8 columns (hi, lo) derived from the previous read-back, pushes them (3 x tcgen05.mma, K = 8, N as
+// given) and reads 8 accumulator columns back.
+__global__ void __launch_bounds__(128, 1) k_rt(int N, int steps, long long* clk, float* sink) {
+    extern __shared__ __align__(128) float sm[];   // B: [2 k chunks][N][4], hi == lo image (timing only)
+    __shared__ uint32_t tbase_s;
+    __shared__ __align__(8) uint64_t mbar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 2 * N * 4; i += 128) sm[i] = 0.001f * (float)(i % 7);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&tbase_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tcol = tbase_s, trow = tcol + ((uint32_t)(32 * warp) << 16);
+    const uint32_t SH = 256, SL = 264;
+    const uint64_t desc = make_desc(smem_u32(sm), (uint32_t)N * 16u, 128u);
+    const uint32_t idesc = make_idesc(128, N);
+    float v[8];
+    for (int e = 0; e < 8; ++e) v[e] = 0.01f * (float)(tid + e);
+    uint32_t phase = 0;
+    const long long t0 = clock64();
+    for (int s = 0; s < steps; ++s) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float x = fmaxf(v[e], 0.f); hi[e] = tf32_hi(x); lo[e] = x - hi[e]; }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     :: "r"(trow + SH), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]), "f"(hi[4]), "f"(hi[5]), "f"(hi[6]), "f"(hi[7]) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     :: "r"(trow + SL), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]), "f"(lo[4]), "f"(lo[5]), "f"(lo[6]), "f"(lo[7]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            mma_ts(tcol, tcol + SH, desc, idesc, 0u);
+            mma_ts(tcol, tcol + SL, desc, idesc, 1u);
+            mma_ts(tcol, tcol + SH, desc, idesc, 1u);
+            commit(&mbar);
+        }
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+            phase ^= 1u;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(trow + (uint32_t)((s * 8) % (N - 7))) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]) :: "memory");
+    }
+    const long long t1 = clock64();
+    if (tid == 0) clk[0] = (t1 - t0) / steps;
+    sink[tid] = v[0] + v[7];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase_s) : "memory");
+}
+int run_rt() {
+    long long* cd; float* sd;
+    cudaMalloc(&cd, 8); cudaMalloc(&sd, 128 * 4);
+    int bad = 0;
+    for (int N : {8, 64, 104, 200}) {
+        size_t smem = 2 * (size_t)N * 16;
+        k_rt<<<1, 128, smem>>>(N, 2000, cd, sd);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long c = 0;
+        cudaMemcpy(&c, cd, 8, cudaMemcpyDeviceToHost);
+        printf("rt N %3d: %s  %lld clk per stage->mma->readback round trip\n", N, cudaGetErrorString(e), c);
+        bad |= e != cudaSuccess;
+    }
+    return bad;
 }

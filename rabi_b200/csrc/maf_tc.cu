@@ -5,8 +5,9 @@
 // layer-1 contraction (91 % of the masked MACs at lotka_volterra shapes) runs on the 5th-generation tensor cores:
 //
 //  * a CTA holds up to 3 TILES of 128 (observation row, MC sample) pairs, one warpgroup each; thread = pair = TMEM lane;
-//  * per tile 168 tensor-memory columns: [0, 104) fp32 accumulators of the layer being produced (column = unit),
-//    [104, 136) / [136, 168) the TF32 (hi, lo) halves of up to 32 staged inputs;
+//  * per tile 168 tensor-memory columns: [0, 120) fp32 accumulators of the layer being produced (column = unit, the MADE
+//    degree groups each padded to a multiple of 4), [120, 144) / [144, 168) the TF32 (hi, lo) halves of up to 24 staged
+//    inputs;
 //  * "group push": the threads compute a group of layer-0 activations (ReLU(A[u] + W0t[u].y), FMA code, D is tiny),
 //    split them into (hi, lo), store them to the staging columns (tcgen05.st); ONE elected thread issues the 3xTF32
 //    chain  acc[:, n0:] += h_hi*W_hi + h_lo*W_hi + h_hi*W_lo  (tcgen05.mma.cta_group::1.kind::tf32, M = 128 pairs,
@@ -14,8 +15,8 @@
 //    tile's mbarrier; the threads wait and read the accumulator columns that are final now (tcgen05.ld);
 //  * the sequential sampling pass pushes, at autoregressive step j, only the layer-0 units of MADE degree j into the
 //    accumulator columns of the layer-1 units of degree >= j (one pass-equivalent, exactly the masked MACs, N shrinks
-//    with j); the density pass pushes all units in chunks of 32; the reverse passes run the same pattern on the
-//    transposed weight copy (cotangents of layer 1 pushed into the columns of layer 0);
+//    with j); the density pass runs the same pushes without the intermediate read-backs; the reverse passes run the
+//    same pattern on the transposed weight copy (cotangents of layer 1 pushed into the columns of layer 0);
 //  * the weights of one (transform, orientation) -- hi and lo halves plus the small FMA-side arrays and the chunk
 //    tables -- are ONE contiguous block of the packed tensor-core image and arrive in shared memory by cp.async.bulk
 //    (TMA bulk copy, completion on an mbarrier); phases visit the transforms as p0 p1 p2 | q2 q1 q0 | q0' q1' q2' |
@@ -35,29 +36,35 @@
 
 namespace rabi {
 
-constexpr int TC_KC = 32;          // staged inputs per push
-constexpr int TC_ACC = 104;        // accumulator columns (max units per hidden layer on this path)
+constexpr int TC_KC = 24;          // staged inputs per push (columns of the hi half and of the lo half)
+constexpr int TC_ACC = 120;        // accumulator columns = max padded units per hidden layer on this path
 constexpr int TC_SH = TC_ACC;      // staging columns, hi half
 constexpr int TC_SL = TC_ACC + TC_KC;
 constexpr int TC_TILE_COLS = TC_ACC + 2 * TC_KC;  // 168
 constexpr int TC_MAXTILES = 3;
-constexpr int TC_WL = 4;           // relu-mask words per (pass, transform, layer)
-constexpr int TC_MAXCHUNK = 64;    // capacity of one chunk list
+constexpr int TC_MAXP = 24;        // pieces per layer
 
-struct TcChunk {
-    int u0, nu;   // staged (aligned) input-unit range [u0, u0 + nu), nu a multiple of 8, <= 32
-    int ua, ub;   // units of the range that really belong to this push (the others are staged as zeros)
-    int n0, N;    // accumulator columns [n0, n0 + N) receive the product (n0, N multiples of 8)
-    int pad0, pad1;
+// Unit layout inside the tile ("padded"): the MADE degree groups of a layer are laid out one after the other, each
+// padded to a multiple of 4 units, so that 128-bit tensor-memory accesses never straddle two groups.  Padding units have
+// zero weights everywhere (rows and columns), which makes whatever is staged for them harmless.
+// A PIECE is a run of <= TC_KC padded units of one degree group: the unit of staging + push (as the K side of a
+// product) and of read-back (as the N side of the product that feeds the layer).
+struct TcPiece {
+    int u0;      // first padded unit (multiple of 4)
+    int nu;      // staged columns (multiple of 8, <= TC_KC); columns [nz, nu) are staged as zeros
+    int nz;      // padded units of the piece (multiple of 4)
+    int r0, nr;  // real units [r0, r0 + nr) <-> padded [u0, u0 + nr)
+    int n0, N;   // accumulator columns [n0, n0 + N) that receive the piece's product (multiples of 8)
+    int flags;   // degree (bits 0..7) | last piece of its degree group (bit 8) | first piece of its group (bit 9)
 };
 
 // word offsets inside one (transform, orientation) block; identical for all transforms
 struct TcBlk {
     int whi, wlo;        // [NPK/4][NPN][4] TF32 hi / lo halves of layer 1 (orientation 0: n = layer-1 unit, k = layer-0 unit)
     int NPN, NPK;
-    int w0t, b1, wot, bo;  // [R0][DP], [R1], [R1][2*DP], [2*DP]
-    int perm, permy, grp0, grp1;
-    int nfull, cfull, seqstart, cseq;
+    int w0t, b1, wot, bo;  // [R0][DP], [R1], [R1][2*DP], [2*DP]   (padded unit order)
+    int perm, permy;
+    int np, p0start, p1start, P0, P1;   // np: (np0, np1); p?start[D+1]; piece tables
     int words;
 };
 
@@ -75,7 +82,7 @@ struct TcArgs {
     const float* img;    // [K][2][blk_words]
     TcBlk blk[2];
     int blk_words;
-    uint32_t* bits;      // [2K*2][TC_WL][bits_stride]
+    uint32_t* bits;      // [2K][2][TC_MAXP][bits_stride] relu masks, one word per piece
     int bits_stride;
     int VS;
 };
@@ -139,22 +146,11 @@ __device__ __forceinline__ float2 tc_ffma2(float2 a, float2 b, float2 c) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return d;
 }
-// relu-mask words of one layer (<= 128 units) held in registers
-__device__ __forceinline__ void tc_bits_merge(uint32_t (&bw)[TC_WL], int u0, uint32_t m) {
-    const int w = u0 >> 5, sh = u0 & 31;
-    const uint32_t lo = m << sh, hi = sh ? (m >> (32 - sh)) : 0u;
-#pragma unroll
-    for (int i = 0; i < TC_WL; ++i) bw[i] |= (i == w ? lo : 0u) | (i == w + 1 ? hi : 0u);
-}
-__device__ __forceinline__ uint32_t tc_bits_extract(const uint32_t (&bw)[TC_WL], int u0) {  // 32 mask bits from unit u0 on
-    const int w = u0 >> 5, sh = u0 & 31;
-    uint32_t a = 0u, b = 0u;
-#pragma unroll
-    for (int i = 0; i < TC_WL; ++i) {
-        a = i == w ? bw[i] : a;
-        b = i == w + 1 ? bw[i] : b;
-    }
-    return __funnelshift_r(a, b, sh);
+// stage one quad of values as TF32 (hi, lo) halves
+__device__ __forceinline__ void tc_stage4(uint32_t trow, int q, const float (&v)[4]) {
+    const float h0 = tc_hi(v[0]), h1 = tc_hi(v[1]), h2 = tc_hi(v[2]), h3 = tc_hi(v[3]);
+    tc_st4(trow + TC_SH + q, h0, h1, h2, h3);
+    tc_st4(trow + TC_SL + q, v[0] - h0, v[1] - h1, v[2] - h2, v[3] - h3);
 }
 
 // ------------------------------------------------------------------------------------------------- the kernel
@@ -169,7 +165,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
     __shared__ __align__(8) uint64_t mbar[TC_MAXTILES + 1];   // one per tile (MMA completion) + the block loader
     const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2, lane128 = tid & 127;
     const int NT = blockDim.x >> 7;
-    const int K = g.K, D = g.D, H0 = g.H[0], H1 = g.H[1];
+    const int K = g.K, D = g.D, H0 = g.H[0];
     const float HALF_LOG_2PI = 0.91893853320467274178f;
 
     if (tid == 0) {
@@ -186,7 +182,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
     const uint32_t tcol = tmem_base_s + (uint32_t)(wg * TC_TILE_COLS);          // lane 0, first column of the tile
     const uint32_t trow = tcol + ((uint32_t)(32 * (warp & 3)) << 16);           // this thread's lane quadrant
     float* vecp = vec + (size_t)tid * a.VS;
-    const int gslot = blockIdx.x * blockDim.x + tid;
+    uint32_t* bitp = a.bits + (blockIdx.x * blockDim.x + tid);
     uint64_t* my_mbar = &mbar[wg];
     uint32_t mphase = 0, wphase = 0;
 
@@ -212,8 +208,8 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
         resident = id;
     };
 
-    // one push: the staged inputs of chunk c (this tile) times the weight strip, into accumulator columns [n0, n0 + N)
-    auto push = [&](const TcBlk& bk, const TcChunk& c, bool first) {
+    // one push: the staged columns of piece c (this tile) times the weight strip, into accumulator columns [n0, n0 + N)
+    auto push = [&](const TcBlk& bk, const TcPiece& c, bool first) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
@@ -222,16 +218,18 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             const uint32_t idesc = tc_make_idesc(128, c.N);
             const uint32_t lbo = (uint32_t)bk.NPN * 16u;
             const uint32_t strip = (uint32_t)(((c.u0 >> 2) * bk.NPN + c.n0) * 16);
+            const uint64_t dhi = tc_make_desc(tc_smem_u32(Wb) + 4u * (uint32_t)bk.whi + strip, lbo, 128u);
+            const uint64_t dlo = tc_make_desc(tc_smem_u32(Wb) + 4u * (uint32_t)bk.wlo + strip, lbo, 128u);
+            const uint64_t dstep = (uint64_t)((2u * lbo) >> 4);   // one K = 8 step = two k chunks
+            const uint32_t dcol = tcol + (uint32_t)c.n0;
             uint32_t acc = first ? 0u : 1u;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {   // (h_hi, W_hi), (h_lo, W_hi), (h_hi, W_lo)
-                const uint32_t wbase = tc_smem_u32(Wb) + 4u * (uint32_t)(t == 2 ? bk.wlo : bk.whi) + strip;
-                const uint32_t acol = tcol + (uint32_t)(t == 1 ? TC_SL : TC_SH);
-                for (int kk = 0; kk < c.nu; kk += 8) {
-                    tc_mma_ts(tcol + (uint32_t)c.n0, acol + (uint32_t)kk, tc_make_desc(wbase + (uint32_t)(kk >> 2) * lbo, lbo, 128u), idesc, acc);
-                    acc = 1u;
-                }
+            const int nk = c.nu >> 3;
+            for (int kk = 0; kk < nk; ++kk) {   // (h_hi, W_hi)
+                tc_mma_ts(dcol, tcol + TC_SH + 8 * kk, dhi + kk * dstep, idesc, acc);
+                acc = 1u;
             }
+            for (int kk = 0; kk < nk; ++kk) tc_mma_ts(dcol, tcol + TC_SL + 8 * kk, dhi + kk * dstep, idesc, 1u);  // (h_lo, W_hi)
+            for (int kk = 0; kk < nk; ++kk) tc_mma_ts(dcol, tcol + TC_SH + 8 * kk, dlo + kk * dstep, idesc, 1u);  // (h_hi, W_lo)
             tc_commit(my_mbar);
         }
         tc_mbar_wait(my_mbar, mphase);
@@ -273,102 +271,115 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             const float* bo = Wb + bk.bo;
             const int* perm = Wi + bk.perm;
             const int* permy = Wi + bk.permy;
-            const int* grp0 = Wi + bk.grp0;
-            const int* grp1 = Wi + bk.grp1;
-            const int* seqstart = Wi + bk.seqstart;
-            const TcChunk* cseq = reinterpret_cast<const TcChunk*>(Wi + bk.cseq);
-            const TcChunk* cfull = reinterpret_cast<const TcChunk*>(Wi + bk.cfull);
-            const int nfull = Wi[bk.nfull];
-            const int bs = (seq ? k : K + k) * 2;   // relu-mask slots of (pass, k): layer 0, layer 1
+            const int np0 = Wi[bk.np], np1 = Wi[bk.np + 1];
+            const int* p0start = Wi + bk.p0start;
+            const int* p1start = Wi + bk.p1start;
+            const TcPiece* P0 = reinterpret_cast<const TcPiece*>(Wi + bk.P0);
+            const TcPiece* P1 = reinterpret_cast<const TcPiece*>(Wi + bk.P1);
+            // relu masks of (pass, k): one word per piece, layer 0 then layer 1
+            uint32_t* bits0 = bitp + (size_t)((seq ? k : K + k) * 2 * TC_MAXP) * a.bits_stride;
+            uint32_t* bits1 = bits0 + (size_t)TC_MAXP * a.bits_stride;
             const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
-            const int nsteps = seq ? D : 1;
 
             if (kind < 2) {
                 // ===================== forward pass of transform k =====================
-                const float* Aptr = (seq ? a.A_p : a.A_q) + (size_t)k * H0 * a.B + b;
+                const float* Abase = (seq ? a.A_p : a.A_q) + (size_t)k * H0 * a.B + b;
                 float zos[DP], y[DP];
                 float2 oms[DP];
-                uint32_t bw0[TC_WL], bw1[TC_WL];
-#pragma unroll
-                for (int i = 0; i < TC_WL; ++i) bw0[i] = bw1[i] = 0u;
 #pragma unroll
                 for (int jj = 0; jj < DP; ++jj) {
                     zos[jj] = (seq && jj < D) ? vecp[oV + k * D + perm[jj]] : 0.f;
                     y[jj] = (!seq && jj < D) ? vecp[src + permy[jj]] : 0.f;
                     oms[jj] = jj < D ? make_float2(bo[2 * jj], bo[2 * jj + 1]) : make_float2(0.f, 0.f);
                 }
-                bool first = true;
-                for (int step = 0; step < nsteps; ++step) {
-                    const int c_lo = seq ? seqstart[step] : 0, c_hi = seq ? seqstart[step + 1] : nfull;
-                    for (int ci = c_lo; ci < c_hi; ++ci) {
-                        const TcChunk c = seq ? cseq[ci] : cfull[ci];
-                        // ---- layer-0 units of the chunk: h = relu(A[u] + W0t[u] . y), staged as (hi, lo)
-                        float av[TC_KC];
+                float an[TC_KC];   // context projection of the NEXT piece's units (loads in flight during the push)
+                {
+                    const TcPiece c0 = P0[0];
+                    const float* ap = Abase + (size_t)c0.r0 * a.B;
 #pragma unroll
-                        for (int i = 0; i < TC_KC; ++i)
-                            av[i] = i < c.nu ? __ldg(Aptr + (size_t)min(c.u0 + i, H0 - 1) * a.B) : 0.f;
-                        uint32_t cm = 0u;
-#pragma unroll
-                        for (int q = 0; q < TC_KC; q += 4) {
-                            if (q < c.nu) {
-                                float hv[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int u = c.u0 + q + e;
-                                    float pre = av[q + e];
-#pragma unroll
-                                    for (int q4 = 0; q4 < DP / 4; ++q4) {
-                                        const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
-                                        pre = fmaf(w.x, y[4 * q4], pre);
-                                        pre = fmaf(w.y, y[4 * q4 + 1], pre);
-                                        pre = fmaf(w.z, y[4 * q4 + 2], pre);
-                                        pre = fmaf(w.w, y[4 * q4 + 3], pre);
-                                    }
-                                    const bool on = u >= c.ua && u < c.ub && pre > 0.f;
-                                    hv[e] = on ? pre : 0.f;
-                                    cm |= on ? (1u << (q + e)) : 0u;
-                                }
-                                const float h0 = tc_hi(hv[0]), h1 = tc_hi(hv[1]), h2 = tc_hi(hv[2]), h3 = tc_hi(hv[3]);
-                                tc_st4(trow + TC_SH + q, h0, h1, h2, h3);
-                                tc_st4(trow + TC_SL + q, hv[0] - h0, hv[1] - h1, hv[2] - h2, hv[3] - h3);
-                            }
-                        }
-                        if (GRADM) tc_bits_merge(bw0, c.u0, cm);
-                        push(bk, c, first);
-                        first = false;
+                    for (int i = 0; i < TC_KC; ++i) {
+                        an[i] = i < c0.nr ? __ldg(ap) : 0.f;
+                        ap += a.B;
                     }
-                    // ---- layer-1 units that are final now: relu(acc + b1) folded into the (mean, log-scale) accumulators
-                    {
-                        const int va = seq ? grp1[step] : 0, vb = seq ? grp1[step + 1] : H1;
-                        float4 nxt = tc_ld4(trow + (uint32_t)(va & ~3));
-                        for (int v0 = va & ~3; v0 < vb; v0 += 4) {
-                            tc_wait_ld(nxt);
-                            const float4 acc = nxt;
-                            nxt = tc_ld4(trow + (uint32_t)(v0 + 4));   // look-ahead (stays inside the tile's columns)
-                            const float pre[4] = {acc.x, acc.y, acc.z, acc.w};
-                            uint32_t nib = 0u;
+                }
+                for (int pi = 0; pi < np0; ++pi) {
+                    const TcPiece c = P0[pi];
+                    float av[TC_KC];
+#pragma unroll
+                    for (int i = 0; i < TC_KC; ++i) av[i] = an[i];
+                    if (pi + 1 < np0) {
+                        const TcPiece cn = P0[pi + 1];
+                        const float* ap = Abase + (size_t)cn.r0 * a.B;
+#pragma unroll
+                        for (int i = 0; i < TC_KC; ++i) {
+                            an[i] = i < cn.nr ? __ldg(ap) : 0.f;
+                            ap += a.B;
+                        }
+                    }
+                    // ---- layer-0 units of the piece: h = relu(A[u] + W0t[u] . y), staged as (hi, lo)
+                    uint32_t cm = 0u;
+#pragma unroll
+                    for (int q = 0; q < TC_KC; q += 4) {
+                        if (q < c.nz) {
+                            float hv[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const int v = v0 + e;
-                                const float val = pre[e] + b1[v];
-                                const bool on = v >= va && v < vb && val > 0.f;
-                                const float hv = on ? val : 0.f;
-                                nib |= on ? (1u << e) : 0u;
-                                const float2 hh = make_float2(hv, hv);
-                                const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
+                                float pre = av[q + e];
 #pragma unroll
-                                for (int q2 = 0; q2 < DP / 2; ++q2) {
-                                    const float4 wq = wo[q2];   // (m_j, s_j, m_j+1, s_j+1)
-                                    oms[2 * q2] = tc_ffma2(make_float2(wq.x, wq.y), hh, oms[2 * q2]);
-                                    oms[2 * q2 + 1] = tc_ffma2(make_float2(wq.z, wq.w), hh, oms[2 * q2 + 1]);
+                                for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                    const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)(c.u0 + q + e) * DP + 4 * q4);
+                                    pre = fmaf(w.x, y[4 * q4], pre);
+                                    pre = fmaf(w.y, y[4 * q4 + 1], pre);
+                                    pre = fmaf(w.z, y[4 * q4 + 2], pre);
+                                    pre = fmaf(w.w, y[4 * q4 + 3], pre);
+                                }
+                                hv[e] = fmaxf(pre, 0.f);
+                                cm |= pre > 0.f ? (1u << (q + e)) : 0u;
+                            }
+                            tc_stage4(trow, q, hv);
+                        } else if (q < c.nu) {   // columns of the next group inside the last K = 8 step: not known yet
+                            tc_st4(trow + TC_SH + q, 0.f, 0.f, 0.f, 0.f);
+                            tc_st4(trow + TC_SL + q, 0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    if (GRADM) bits0[(size_t)pi * a.bits_stride] = cm;
+                    push(bk, c, pi == 0);
+                    const bool group_done = (c.flags >> 8) & 1;
+                    if (!(seq ? group_done : pi == np0 - 1)) continue;
+                    // ---- layer-1 units that are final now: relu(acc + b1) folded into the (mean, log-scale) accumulators
+                    const int j = c.flags & 255;
+                    const int pj_lo = seq ? p1start[j] : 0, pj_hi = seq ? p1start[j + 1] : np1;
+                    for (int pj = pj_lo; pj < pj_hi; ++pj) {
+                        const TcPiece r = P1[pj];
+                        uint32_t rm = 0u;
+                        float4 nxt = tc_ld4(trow + (uint32_t)r.u0);
+#pragma unroll
+                        for (int q = 0; q < TC_KC; q += 4) {
+                            if (q < r.nz) {
+                                tc_wait_ld(nxt);
+                                const float4 acc = nxt;
+                                nxt = tc_ld4(trow + (uint32_t)(r.u0 + q + 4));   // look-ahead (stays inside the tile's columns)
+                                const float4 bias = *reinterpret_cast<const float4*>(b1 + r.u0 + q);
+                                const float val[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float hv = fmaxf(val[e], 0.f);
+                                    rm |= val[e] > 0.f ? (1u << (q + e)) : 0u;
+                                    const float2 hh = make_float2(hv, hv);
+                                    const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)(r.u0 + q + e) * 2 * DP);
+#pragma unroll
+                                    for (int q2 = 0; q2 < DP / 2; ++q2) {
+                                        const float4 wq = wo[q2];   // (m_j, s_j, m_j+1, s_j+1)
+                                        oms[2 * q2] = tc_ffma2(make_float2(wq.x, wq.y), hh, oms[2 * q2]);
+                                        oms[2 * q2 + 1] = tc_ffma2(make_float2(wq.z, wq.w), hh, oms[2 * q2 + 1]);
+                                    }
                                 }
                             }
-                            if (GRADM) tc_bits_merge(bw1, v0, nib);
                         }
                         tc_wait_ld(nxt);
+                        if (GRADM) bits1[(size_t)pj * a.bits_stride] = rm;
                     }
-                    if (seq) {  // position `step` is final: y_j = (z_j - m_j) exp(-clamp(s_j))
-                        const int j = step;
+                    if (seq) {  // position j is final: y_j = (z_j - m_j) exp(-clamp(s_j))
                         float m = 0.f, s = 0.f, zj = 0.f;
 #pragma unroll
                         for (int jj = 0; jj < DP; ++jj) {
@@ -406,23 +417,10 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                         if (a.diff && live) a.diff[pidx] = MODE == TC_LOGPROB ? logq : logp - logq;
                     }
                 }
-                if (GRADM) {
-#pragma unroll
-                    for (int i = 0; i < TC_WL; ++i) {
-                        a.bits[((size_t)(bs * TC_WL + i)) * a.bits_stride + gslot] = bw0[i];
-                        a.bits[((size_t)((bs + 1) * TC_WL + i)) * a.bits_stride + gslot] = bw1[i];
-                    }
-                }
             } else {
                 // ===================== reverse pass of transform k =====================
                 const float w = a.w;
                 float yb[DP], yv[DP], sh[DP], mb[DP], sb[DP], zb[DP];
-                uint32_t bw0[TC_WL], bw1[TC_WL];
-#pragma unroll
-                for (int i = 0; i < TC_WL; ++i) {
-                    bw0[i] = a.bits[((size_t)(bs * TC_WL + i)) * a.bits_stride + gslot];
-                    bw1[i] = a.bits[((size_t)((bs + 1) * TC_WL + i)) * a.bits_stride + gslot];
-                }
 #pragma unroll
                 for (int jj = 0; jj < DP; ++jj) {
                     zb[jj] = 0.f;
@@ -443,11 +441,16 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                         mb[jj] = sb[jj] = yb[jj] = yv[jj] = sh[jj] = 0.f;
                     }
                 }
-                bool first = true;
-                for (int st = 0; st < nsteps; ++st) {
-                    const int step = seq ? D - 1 - st : 0;
-                    if (seq) {
-                        const int j = step;
+                float* gAbase = a.gA + (size_t)k * H0 * a.B + b;
+                const bool emit = (seq || MODE == TC_FKL) && live;
+                // layer-1 pieces in DESCENDING order (the first push covers every accumulator column)
+                uint32_t cmn = bits1[(size_t)(np1 - 1) * a.bits_stride];
+                for (int pi = np1 - 1; pi >= 0; --pi) {
+                    const TcPiece c = P1[pi];
+                    const int j = c.flags & 255;
+                    const uint32_t cm = cmn;
+                    if (pi > 0) cmn = bits1[(size_t)(pi - 1) * a.bits_stride];
+                    if (seq && ((c.flags >> 8) & 1)) {   // entering degree group j (its last piece comes first): seed of position j
                         float ybj = 0.f, shj = 0.f, yj = 0.f;
 #pragma unroll
                         for (int jj = 0; jj < DP; ++jj) {
@@ -463,63 +466,64 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                             sb[jj] = jj == j ? fmaf(-ybj, yj, w) : sb[jj];
                         }
                     }
-                    // ---- layer-1 cotangents of the chunk's units: g = relu'(.) * (WoT[v] . (mbar, sbar)), staged as (hi, lo)
-                    const int c_lo = seq ? seqstart[step] : 0, c_hi = seq ? seqstart[step + 1] : nfull;
-                    for (int ci = c_lo; ci < c_hi; ++ci) {
-                        const TcChunk c = seq ? cseq[ci] : cfull[ci];
-                        const uint32_t cm = tc_bits_extract(bw1, c.u0);
+                    // ---- layer-1 cotangents of the piece: g = relu'(.) * (WoT[v] . (mbar, sbar)), staged as (hi, lo)
 #pragma unroll
-                        for (int q = 0; q < TC_KC; q += 4) {
-                            if (q < c.nu) {
-                                float gs[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int v = c.u0 + q + e;
-                                    const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)v * 2 * DP);
-                                    float2 g2 = make_float2(0.f, 0.f);
-#pragma unroll
-                                    for (int q2 = 0; q2 < DP / 2; ++q2) {
-                                        const float4 wq = wo[q2];
-                                        g2 = tc_ffma2(make_float2(wq.x, wq.y), make_float2(mb[2 * q2], sb[2 * q2]), g2);
-                                        g2 = tc_ffma2(make_float2(wq.z, wq.w), make_float2(mb[2 * q2 + 1], sb[2 * q2 + 1]), g2);
-                                    }
-                                    const bool on = v >= c.ua && v < c.ub && ((cm >> (q + e)) & 1u);
-                                    gs[e] = on ? g2.x + g2.y : 0.f;
-                                }
-                                const float h0 = tc_hi(gs[0]), h1 = tc_hi(gs[1]), h2 = tc_hi(gs[2]), h3 = tc_hi(gs[3]);
-                                tc_st4(trow + TC_SH + q, h0, h1, h2, h3);
-                                tc_st4(trow + TC_SL + q, gs[0] - h0, gs[1] - h1, gs[2] - h2, gs[3] - h3);
-                            }
-                        }
-                        push(bk, c, first);
-                        first = false;
-                    }
-                    // ---- layer-0 cotangents that are final now: mask, push into d/dy, emit d/dA
-                    {
-                        const int ua = seq ? grp0[step] : 0, ub = seq ? grp0[step + 1] : H0;
-                        const bool emit = (seq || MODE == TC_FKL) && live;
-                        float* gA = a.gA + (size_t)k * H0 * a.B + b;
-                        float4 nxt = tc_ld4(trow + (uint32_t)(ua & ~3));
-                        for (int u0 = ua & ~3; u0 < ub; u0 += 4) {
-                            tc_wait_ld(nxt);
-                            const float4 acc = nxt;
-                            nxt = tc_ld4(trow + (uint32_t)(u0 + 4));
-                            const float g0[4] = {acc.x, acc.y, acc.z, acc.w};
-                            const uint32_t nib = tc_bits_extract(bw0, u0);
+                    for (int q = 0; q < TC_KC; q += 4) {
+                        if (q < c.nz) {
+                            float gs[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const int u = u0 + e;
-                                const bool on = u >= ua && u < ub && ((nib >> e) & 1u);
-                                const float gv = on ? g0[e] : 0.f;
+                                const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)(c.u0 + q + e) * 2 * DP);
+                                float2 g2 = make_float2(0.f, 0.f);
 #pragma unroll
-                                for (int q4 = 0; q4 < DP / 4; ++q4) {
-                                    const float4 w4 = *reinterpret_cast<const float4*>(W0t + (size_t)u * DP + 4 * q4);
-                                    yb[4 * q4] = fmaf(w4.x, gv, yb[4 * q4]);
-                                    yb[4 * q4 + 1] = fmaf(w4.y, gv, yb[4 * q4 + 1]);
-                                    yb[4 * q4 + 2] = fmaf(w4.z, gv, yb[4 * q4 + 2]);
-                                    yb[4 * q4 + 3] = fmaf(w4.w, gv, yb[4 * q4 + 3]);
+                                for (int q2 = 0; q2 < DP / 2; ++q2) {
+                                    const float4 wq = wo[q2];
+                                    g2 = tc_ffma2(make_float2(wq.x, wq.y), make_float2(mb[2 * q2], sb[2 * q2]), g2);
+                                    g2 = tc_ffma2(make_float2(wq.z, wq.w), make_float2(mb[2 * q2 + 1], sb[2 * q2 + 1]), g2);
                                 }
-                                if (emit && on) atomicAdd(gA + (size_t)u * a.B, gv);   // RED.ADD.F32: sum over the S samples of the row
+                                gs[e] = ((cm >> (q + e)) & 1u) ? g2.x + g2.y : 0.f;
+                            }
+                            tc_stage4(trow, q, gs);
+                        } else if (q < c.nu) {
+                            tc_st4(trow + TC_SH + q, 0.f, 0.f, 0.f, 0.f);
+                            tc_st4(trow + TC_SL + q, 0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    const bool group_done = (c.flags >> 9) & 1;   // descending: the group's first piece is staged last
+                    const bool read_now = seq ? group_done : pi == 0;
+                    const int pj_lo = seq ? p0start[j] : 0, pj_hi = seq ? p0start[j + 1] : np0;
+                    uint32_t rmn = 0u;
+                    if (read_now) rmn = bits0[(size_t)pj_lo * a.bits_stride];   // in flight during the push
+                    push(bk, c, pi == np1 - 1);
+                    if (!read_now) continue;
+                    // ---- layer-0 cotangents that are final now: mask, push into d/dy, emit d/dA
+                    for (int pj = pj_lo; pj < pj_hi; ++pj) {
+                        const TcPiece r = P0[pj];
+                        const uint32_t rm = rmn & (r.nr >= 32 ? 0xFFFFFFFFu : ((1u << r.nr) - 1u));   // padding units: no gradient
+                        if (pj + 1 < pj_hi) rmn = bits0[(size_t)(pj + 1) * a.bits_stride];
+                        float* gAp = gAbase + (size_t)r.r0 * a.B;
+                        float4 nxt = tc_ld4(trow + (uint32_t)r.u0);
+#pragma unroll
+                        for (int q = 0; q < TC_KC; q += 4) {
+                            if (q < r.nz) {
+                                tc_wait_ld(nxt);
+                                const float4 acc = nxt;
+                                nxt = tc_ld4(trow + (uint32_t)(r.u0 + q + 4));
+                                const float g0[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const bool on = (rm >> (q + e)) & 1u;
+                                    const float gv = on ? g0[e] : 0.f;
+#pragma unroll
+                                    for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                        const float4 w4 = *reinterpret_cast<const float4*>(W0t + (size_t)(r.u0 + q + e) * DP + 4 * q4);
+                                        yb[4 * q4] = fmaf(w4.x, gv, yb[4 * q4]);
+                                        yb[4 * q4 + 1] = fmaf(w4.y, gv, yb[4 * q4 + 1]);
+                                        yb[4 * q4 + 2] = fmaf(w4.z, gv, yb[4 * q4 + 2]);
+                                        yb[4 * q4 + 3] = fmaf(w4.w, gv, yb[4 * q4 + 3]);
+                                    }
+                                    if (emit && on) atomicAdd(gAp + (size_t)(q + e) * a.B, gv);   // RED.ADD.F32 over the S samples of the row
+                                }
                             }
                         }
                         tc_wait_ld(nxt);
@@ -544,115 +548,124 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
 }
 
 // ------------------------------------------------------------------------------------------------- image packing
-// float part of every block, from the masked order-space image (maf_image.h): grid (blocks, 2 orientations, K)
-__global__ void k_tc_pack(const MafImg g, TcBlk b0, TcBlk b1, int blk_words, int DP, int R0, int R1, float* __restrict__ img) {
+struct TcPackMaps {
+    const int* pu0;   // [K][H0] padded index of layer-0 unit u
+    const int* pu1;   // [K][H1]
+};
+// float part of every block, from the masked order-space image (maf_image.h): grid (blocks, 2 orientations, K).
+// The block was zero-filled by the host; only real units are written.
+__global__ void k_tc_pack(const MafImg g, TcBlk b0, TcBlk b1, int blk_words, int DP, TcPackMaps mp, float* __restrict__ img) {
     const int k = blockIdx.z, ori = blockIdx.y;
     const TcBlk bk = ori == 0 ? b0 : b1;
     const TImg t = g.t[k];
     const int H0 = g.H[0], H1 = g.H[1], ld1 = t.ld[1];
     float* out = img + (size_t)(2 * k + ori) * blk_words;
     const float* f = g.f;
-    const int nW = (bk.NPK / 4) * bk.NPN * 4;
+    const int* pu0 = mp.pu0 + (size_t)k * H0;
+    const int* pu1 = mp.pu1 + (size_t)k * H1;
     const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int o = t0; o < nW; o += stride) {
-        const int kc = o / (bk.NPN * 4), n = (o >> 2) % bk.NPN, r = o & 3, kidx = 4 * kc + r;
+    for (int o = t0; o < H1 * H0; o += stride) {
+        const int v = o / H0, u = o % H0;
         // orientation 0: n = layer-1 unit v, k = layer-0 unit u;  orientation 1: n = u, k = v;  W1 is [v][u]
-        const int v = ori == 0 ? n : kidx, u = ori == 0 ? kidx : n;
-        const float w = (v < H1 && u < H0) ? f[t.W[1] + (size_t)v * ld1 + u] : 0.f;
+        const int n = ori == 0 ? pu1[v] : pu0[u], kidx = ori == 0 ? pu0[u] : pu1[v];
+        const float w = f[t.W[1] + (size_t)v * ld1 + u];
         const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
-        out[bk.whi + o] = hi;
-        out[bk.wlo + o] = w - hi;
+        const int at = ((kidx >> 2) * bk.NPN + n) * 4 + (kidx & 3);
+        out[bk.whi + at] = hi;
+        out[bk.wlo + at] = w - hi;
     }
-    for (int o = t0; o < R0 * DP; o += stride) {
+    for (int o = t0; o < H0 * DP; o += stride) {
         const int u = o / DP, jj = o % DP;
-        out[bk.w0t + o] = (u < H0 && jj < t.ldt) ? f[t.W0t + (size_t)u * t.ldt + jj] : 0.f;
+        out[bk.w0t + pu0[u] * DP + jj] = jj < t.ldt ? f[t.W0t + (size_t)u * t.ldt + jj] : 0.f;
     }
-    for (int o = t0; o < R1; o += stride) out[bk.b1 + o] = o < H1 ? f[t.b[1] + o] : 0.f;
-    for (int o = t0; o < R1 * 2 * DP; o += stride) {
+    for (int o = t0; o < H1; o += stride) out[bk.b1 + pu1[o]] = f[t.b[1] + o];
+    for (int o = t0; o < H1 * 2 * DP; o += stride) {
         const int v = o / (2 * DP), c = o % (2 * DP);
-        out[bk.wot + o] = (v < H1 && c < 2 * t.ldt) ? f[t.WoT + (size_t)v * 2 * t.ldt + c] : 0.f;
+        out[bk.wot + pu1[v] * 2 * DP + c] = c < 2 * t.ldt ? f[t.WoT + (size_t)v * 2 * t.ldt + c] : 0.f;
     }
     for (int o = t0; o < 2 * DP; o += stride) out[bk.bo + o] = o < 2 * t.ldt ? f[t.boF + o] : 0.f;
 }
 
 struct TcState {
     bool built = false, eligible = false;
-    int DP = 4, R0 = 0, R1 = 0;
+    int DP = 4;
     TcBlk blk[2];
     int blk_words = 0;
-    float* img = nullptr;
+    float* img = nullptr;  // [template: integer tables, zeros elsewhere][packed image]
+    size_t img_words = 0;
+    int* maps = nullptr;   // pu0 [K][H0] then pu1 [K][H1]
     unsigned long long packed_version = ~0ull;
     uint32_t* bits = nullptr;
     size_t bits_words = 0;
 };
 
+static inline int r4(int x) { return (x + 3) & ~3; }
 static inline int r8(int x) { return (x + 7) & ~7; }
 
-// chunk lists of one orientation.  in_grp / out_grp: [D+1] group boundaries of the staged (input) layer and of the
-// accumulator (output) layer.  forward: inputs of degree j feed outputs of degree >= j; reverse: cotangents of degree j
-// feed the units of degree <= j of the layer below.
-static void tc_chunks(int D, const int* in_grp, int Hin, const int* out_grp, int NPN, bool reverse,
-                      std::vector<TcChunk>& seq, std::vector<int>& seqstart, std::vector<TcChunk>& full) {
-    seq.clear();
-    full.clear();
-    seqstart.assign(D + 1, 0);
+// pieces of one layer.  grp: [D+1] real group boundaries; gp: [D+1] padded group starts.
+// forward (K side = this layer, N side = next layer with padded starts np_next / width NPN): inputs of degree j feed
+// outputs of degree >= j;  reverse: cotangents of degree j feed the units of degree <= j of the layer below.
+static void tc_pieces(int D, const int* grp, const int* gp, const int* gp_other, int NPN, bool reverse,
+                      std::vector<TcPiece>& out, std::vector<int>& start) {
+    out.clear();
+    start.assign(D + 1, 0);
     for (int j = 0; j < D; ++j) {
-        seqstart[j] = (int)seq.size();
-        const int ua = in_grp[j], ub = in_grp[j + 1];
-        if (ub > ua) {
-            const int a8 = ua & ~7, b8 = r8(ub);
-            for (int u0 = a8; u0 < b8; u0 += TC_KC) {
-                TcChunk c;
-                c.u0 = u0;
-                c.nu = std::min(TC_KC, b8 - u0);
-                c.ua = std::max(ua, u0);
-                c.ub = std::min(ub, u0 + c.nu);
-                if (!reverse) {
-                    c.n0 = out_grp[j] & ~7;
-                    c.N = NPN - c.n0;
-                } else {
-                    c.n0 = 0;
-                    c.N = std::min(NPN, r8(out_grp[j + 1]));
-                }
-                c.pad0 = c.pad1 = 0;
-                seq.push_back(c);
+        start[j] = (int)out.size();
+        const int len = grp[j + 1] - grp[j], plen = r4(len);
+        for (int o = 0; o < plen; o += TC_KC) {
+            TcPiece c;
+            c.u0 = gp[j] + o;
+            c.nz = std::min(TC_KC, plen - o);
+            c.nu = r8(c.nz);
+            c.r0 = grp[j] + o;
+            c.nr = std::min(TC_KC, len - o);
+            if (!reverse) {
+                c.n0 = gp_other[j] & ~7;
+                c.N = NPN - c.n0;
+            } else {
+                c.n0 = 0;
+                c.N = std::min(NPN, r8(gp_other[j + 1]));
             }
+            c.flags = j | ((o + TC_KC >= plen) ? 256 : 0) | (o == 0 ? 512 : 0);
+            out.push_back(c);
         }
     }
-    seqstart[D] = (int)seq.size();
-    for (int u0 = 0; u0 < r8(Hin); u0 += TC_KC) {
-        TcChunk c;
-        c.u0 = u0;
-        c.nu = std::min(TC_KC, r8(Hin) - u0);
-        c.ua = u0;
-        c.ub = std::min(Hin, u0 + c.nu);
-        c.n0 = 0;
-        c.N = NPN;
-        c.pad0 = c.pad1 = 0;
-        full.push_back(c);
-    }
+    start[D] = (int)out.size();
 }
 
 static int tc_build(rabi_maf* h, TcState* s) {
     s->built = true;
     s->eligible = false;
     const int K = h->K, D = h->D, H0 = h->H[0], H1 = h->H[1];
-    if (h->L != 2 || D > 12 || H0 > TC_ACC || H1 > TC_ACC) return 0;
+    if (h->L != 2 || D > 12) return 0;
     const std::vector<int>& M = h->meta_host;
     const MafImg& g = h->img;
-    for (int k = 0; k < K; ++k)
-        for (int l = 0; l < 2; ++l)
-            for (int j = 0; j < D; ++j)
-                if (M[g.t[k].grp[l] + j + 1] <= M[g.t[k].grp[l] + j]) return 0;   // an empty degree group: not a Pyro mask shape we tile
+    // padded layouts (per transform; the block layout must be the same for all of them)
+    std::vector<int> gp0((size_t)K * (D + 1)), gp1((size_t)K * (D + 1)), maps((size_t)K * (H0 + H1));
+    int HP0 = 0, HP1 = 0;
+    for (int k = 0; k < K; ++k) {
+        for (int l = 0; l < 2; ++l) {
+            std::vector<int>& gp = l == 0 ? gp0 : gp1;
+            const int* grp = &M[g.t[k].grp[l]];
+            int at = 0;
+            for (int j = 0; j < D; ++j) {
+                if (grp[j + 1] <= grp[j]) return 0;   // an empty degree group: not a shape this path tiles
+                gp[(size_t)k * (D + 1) + j] = at;
+                for (int u = grp[j]; u < grp[j + 1]; ++u) maps[(size_t)(l == 0 ? 0 : K * H0) + (size_t)k * (l == 0 ? H0 : H1) + u] = at + (u - grp[j]);
+                at += r4(grp[j + 1] - grp[j]);
+            }
+            gp[(size_t)k * (D + 1) + D] = at;
+            (l == 0 ? HP0 : HP1) = std::max(l == 0 ? HP0 : HP1, at);
+        }
+    }
+    if (HP0 > TC_ACC || HP1 > TC_ACC) return 0;
     const int DP = (D + 3) & ~3;
     s->DP = DP;
-    s->R0 = r8(H0) + 8;
-    s->R1 = r8(H1) + 8;
-    // block layout (words); the two orientations share everything but the matrix shape
+    const int R0 = r8(HP0) + 8, R1 = r8(HP1) + 8;
     for (int ori = 0; ori < 2; ++ori) {
         TcBlk& b = s->blk[ori];
-        b.NPN = ori == 0 ? r8(H1) : r8(H0);
-        b.NPK = ori == 0 ? r8(H0) : r8(H1);
+        b.NPN = ori == 0 ? r8(HP1) : r8(HP0);
+        b.NPK = ori == 0 ? R0 : R1;   // the last piece's K = 8 steps may run past the last group
         int o = 0;
         auto take = [&](int n) {
             int at = o;
@@ -662,25 +675,27 @@ static int tc_build(rabi_maf* h, TcState* s) {
         const int nW = (b.NPK / 4) * b.NPN * 4;
         b.whi = take(nW);
         b.wlo = take(nW);
-        b.w0t = take(s->R0 * DP);
-        b.b1 = take(s->R1);
-        b.wot = take(s->R1 * 2 * DP);
+        b.w0t = take(R0 * DP);
+        b.b1 = take(R1);
+        b.wot = take(R1 * 2 * DP);
         b.bo = take(2 * DP);
         b.perm = take(DP);
         b.permy = take(DP);
-        b.grp0 = take(D + 1);
-        b.grp1 = take(D + 1);
-        b.nfull = take(4);
-        b.seqstart = take(D + 1);
-        b.cfull = take(8 * 8);
-        b.cseq = take(TC_MAXCHUNK * 8);
+        b.np = take(4);
+        b.p0start = take(D + 1);
+        b.p1start = take(D + 1);
+        b.P0 = take(TC_MAXP * 8);
+        b.P1 = take(TC_MAXP * 8);
         b.words = o;
     }
     s->blk_words = std::max(s->blk[0].words, s->blk[1].words);
-    // integer tables per (k, orientation)
     std::vector<float> host((size_t)K * 2 * s->blk_words, 0.f);
     for (int k = 0; k < K; ++k) {
         const TImg& t = g.t[k];
+        const int* grp0 = &M[t.grp[0]];
+        const int* grp1 = &M[t.grp[1]];
+        const int* p0 = &gp0[(size_t)k * (D + 1)];
+        const int* p1 = &gp1[(size_t)k * (D + 1)];
         for (int ori = 0; ori < 2; ++ori) {
             const TcBlk& b = s->blk[ori];
             int* w = reinterpret_cast<int*>(host.data() + (size_t)(2 * k + ori) * s->blk_words);
@@ -688,25 +703,31 @@ static int tc_build(rabi_maf* h, TcState* s) {
                 w[b.perm + j] = M[t.perm + j];
                 w[b.permy + j] = M[t.permy + j];
             }
+            std::vector<TcPiece> P0, P1;
+            std::vector<int> s0, s1;
+            // layer-0 pieces carry the forward push (into layer-1 columns), layer-1 pieces the reverse push (into layer-0 columns)
+            tc_pieces(D, grp0, p0, p1, s->blk[0].NPN, false, P0, s0);
+            tc_pieces(D, grp1, p1, p0, s->blk[1].NPN, true, P1, s1);
+            if ((int)P0.size() > TC_MAXP || (int)P1.size() > TC_MAXP) return 0;
+            w[b.np] = (int)P0.size();
+            w[b.np + 1] = (int)P1.size();
             for (int j = 0; j <= D; ++j) {
-                w[b.grp0 + j] = M[t.grp[0] + j];
-                w[b.grp1 + j] = M[t.grp[1] + j];
+                w[b.p0start + j] = s0[j];
+                w[b.p1start + j] = s1[j];
             }
-            std::vector<TcChunk> seq, full;
-            std::vector<int> ss;
-            if (ori == 0) tc_chunks(D, &M[t.grp[0]], H0, &M[t.grp[1]], b.NPN, false, seq, ss, full);
-            else tc_chunks(D, &M[t.grp[1]], H1, &M[t.grp[0]], b.NPN, true, seq, ss, full);
-            if ((int)seq.size() > TC_MAXCHUNK || (int)full.size() > 8) return 0;
-            w[b.nfull] = (int)full.size();
-            for (int j = 0; j <= D; ++j) w[b.seqstart + j] = ss[j];
-            memcpy(w + b.cfull, full.data(), full.size() * sizeof(TcChunk));
-            memcpy(w + b.cseq, seq.data(), seq.size() * sizeof(TcChunk));
+            memcpy(w + b.P0, P0.data(), P0.size() * sizeof(TcPiece));
+            memcpy(w + b.P1, P1.data(), P1.size() * sizeof(TcPiece));
         }
     }
     if (s->img) cudaFree(s->img);
+    if (s->maps) cudaFree(s->maps);
     s->img = nullptr;
-    RABI_CU_OK(h, cudaMalloc(&s->img, host.size() * sizeof(float)));
+    s->maps = nullptr;
+    s->img_words = host.size();
+    RABI_CU_OK(h, cudaMalloc(&s->img, 2 * host.size() * sizeof(float)));
     RABI_CU_OK(h, cudaMemcpy(s->img, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    RABI_CU_OK(h, cudaMalloc(&s->maps, maps.size() * sizeof(int)));
+    RABI_CU_OK(h, cudaMemcpy(s->maps, maps.data(), maps.size() * sizeof(int), cudaMemcpyHostToDevice));
     s->packed_version = ~0ull;
     s->eligible = true;
     return 0;
@@ -747,8 +768,11 @@ int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
     if (!s->eligible) return 2;
     if (npairs < (long long)rabi_env_int("RABI_TC_MIN_PAIRS", 1)) return 2;
     if (s->packed_version != h->weights_version) {
+        // padding entries stay zero: start from the template, then write the real units
+        RABI_CU_OK(h, cudaMemcpyAsync(s->img + s->img_words, s->img, s->img_words * sizeof(float), cudaMemcpyDeviceToDevice, st));
         dim3 grid(16, 2, h->K);
-        k_tc_pack<<<grid, 256, 0, st>>>(h->img, s->blk[0], s->blk[1], s->blk_words, s->DP, s->R0, s->R1, s->img);
+        TcPackMaps mp = {s->maps, s->maps + (size_t)h->K * h->H[0]};
+        k_tc_pack<<<grid, 256, 0, st>>>(h->img, s->blk[0], s->blk[1], s->blk_words, s->DP, mp, s->img + s->img_words);
         h->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return rabi_fail(h, "k_tc_pack launch failed: %s", cudaGetErrorString(e));
@@ -769,7 +793,7 @@ int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
     const long long nt = (npairs + 127) / 128;
     if (nt > 0x7fffffff) return 2;
     a.ntiles = (int)nt;
-    a.img = s->img;
+    a.img = s->img + s->img_words;
     a.blk[0] = s->blk[0];
     a.blk[1] = s->blk[1];
     a.blk_words = s->blk_words;
@@ -784,7 +808,7 @@ int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
     const int T = NT * 128;
     const size_t smem = ((size_t)s->blk_words + (size_t)T * a.VS) * 4;
     if (mode == TC_GRAD || mode == TC_FKL) {
-        const size_t need = (size_t)2 * h->K * 2 * TC_WL * (size_t)h->sm_count * TC_MAXTILES * 128;
+        const size_t need = (size_t)2 * h->K * 2 * TC_MAXP * (size_t)h->sm_count * TC_MAXTILES * 128;
         if (need > s->bits_words) {
             if (s->bits) {
                 RABI_CU_OK(h, cudaDeviceSynchronize());
@@ -812,6 +836,7 @@ void rabi_tc_destroy(rabi_maf* h) {
     TcState* s = static_cast<TcState*>(h->tc);
     if (!s) return;
     if (s->img) cudaFree(s->img);
+    if (s->maps) cudaFree(s->maps);
     if (s->bits) cudaFree(s->bits);
     delete s;
     h->tc = nullptr;

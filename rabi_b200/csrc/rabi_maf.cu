@@ -1402,8 +1402,9 @@ static int pgd_step_impl(rabi_maf* h, const float* x, float* delta, const float*
     int rc;
     // every kernel family adds the S samples' parts of d/dA_p into gA (float reductions in global memory)
     CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
-    if (!env_int("RABI_FORCE_DEEP", 0) && (long long)S * B >= env_int("RABI_TC_GRAD_MIN_PAIRS", 1)) {
-        // tensor-core path (maf_tc.cu): two-hidden-layer conditioners up to 104 units wide
+    if (!env_int("RABI_FORCE_DEEP", 0) && (long long)S * B >= env_int("RABI_TC_GRAD_MIN_PAIRS", 1025)) {
+        // tensor-core path (maf_tc.cu): two-hidden-layer conditioners up to 120 (padded) units wide; launches of up to 1024
+        // pairs stay on the warp-per-pair kernel (measured: 512 pairs 183 us there, 212 us here; 1500 pairs 320 vs 216 us)
         TcCall tc = {forward_kl ? A_q : A_p, forward_kl ? A_p : A_q, z, kl ? diff : nullptr, nullptr, gA, S, B, inv_B / (float)S};
         rc = rabi_tc_launch(h, tc, forward_kl ? TC_FKL : TC_GRAD, st);
         if (rc == 1) return 1;

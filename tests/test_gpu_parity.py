@@ -498,6 +498,7 @@ def test_warp_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
         for fkl in (False, True):
             outs = []
             for env in ({"RABI_WARP_MAX_PAIRS": "0"}, {}, {"RABI_WARP_STAGE": "0"}):
+                env = dict(env, RABI_TC="0")   # the FMA kernels among themselves; the tensor-core path has its own test below
                 os.environ.update(env)
                 try:
                     gx, kl = eng.rkl_input_grad(xd + 0.05, zs[0], zs[1], q.A, z, 1.0 / xd.shape[0], forward_kl=fkl)
@@ -531,7 +532,9 @@ def test_two_lanes_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
         for S in (5, 1):
             z = torch.randn(S, xd.shape[0], shape["D"], generator=g).to(dev)
             outs = []
-            for env in ({"RABI_FAST2": "0"}, {"RABI_FAST2": "2"}, {"RABI_DISABLE_FAST": "1"}):  # k_fast, k_fast2 (forced), generic
+            # k_fast, k_fast2 (forced), generic, and the tensor-core kernel k_tc (forced for every launch size)
+            for env in ({"RABI_FAST2": "0", "RABI_TC": "0"}, {"RABI_FAST2": "2", "RABI_TC": "0"},
+                        {"RABI_DISABLE_FAST": "1", "RABI_TC": "0"}, {"RABI_TC": "1", "RABI_TC_GRAD_MIN_PAIRS": "1"}):
                 env = dict(env, RABI_WARP_MAX_PAIRS="0")
                 os.environ.update(env)
                 try:
