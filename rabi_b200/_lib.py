@@ -25,6 +25,7 @@ _COMMON = ["rabi_internal.h", "maf_image.h", "maf_tc.h"]
 SOURCES = {
     "rabi_maf.cu": _COMMON + ["maf_pairs.cuh", "maf_fast.cuh", "maf_fast2.cuh", "maf_deep.cuh", "maf_warp.cuh"],
     "maf_tc.cu": _COMMON,
+    "maf_tcd.cu": _COMMON,
 }
 
 EXPORTS = [

@@ -762,6 +762,7 @@ int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
     const long long npairs = (long long)c.S * c.B;
     if (npairs <= 0) return 0;
     if (!rabi_env_int("RABI_TC", 1)) return 2;
+    if (h->L == 3) return rabi_tcd_launch(h, c, mode, st);
     TcState* s = static_cast<TcState*>(h->tc);
     if (!s) h->tc = s = new TcState();
     if (!s->built && tc_build(h, s)) return 1;
@@ -833,6 +834,7 @@ int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
 }
 
 void rabi_tc_destroy(rabi_maf* h) {
+    rabi_tcd_destroy(h);
     TcState* s = static_cast<TcState*>(h->tc);
     if (!s) return;
     if (s->img) cudaFree(s->img);

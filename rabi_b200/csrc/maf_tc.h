@@ -21,5 +21,8 @@ struct TcCall {
 // returns 0 = launched, 1 = error (message on the handle), 2 = shape / launch not eligible for this path
 int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st);
 void rabi_tc_destroy(rabi_maf* h);
+// three hidden layers up to 200 units wide, D <= 32 (maf_tcd.cu); reached through rabi_tc_launch
+int rabi_tcd_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st);
+void rabi_tcd_destroy(rabi_maf* h);
 
 }  // namespace rabi

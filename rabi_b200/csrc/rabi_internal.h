@@ -37,6 +37,7 @@ struct rabi_maf {
     int sm_count = 148;
     int max_smem_optin = 0;
     void* tc = nullptr;        // tensor-core path state (maf_tc.cu), owned by rabi_tc_*
+    void* tcd = nullptr;       // three-hidden-layer tensor-core path state (maf_tcd.cu), owned by rabi_tcd_*
     unsigned long long weights_version = 0;   // bumped by rabi_maf_set_weights / finalize: derived images re-pack lazily
 };
 

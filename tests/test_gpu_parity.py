@@ -546,3 +546,47 @@ def test_two_lanes_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
             for gx, kl in outs[1:]:
                 assert float((kl - outs[0][1]).abs().max()) < 1e-5 * lp_scale
                 assert_trajectories_match(gx, outs[0][0], 1e-4)
+
+
+@pytest.mark.parametrize("shape", [dict(dx=20, D=31, hidden=[64, 64, 64], B=45), dict(dx=12, D=9, hidden=[40, 36, 44], B=130),
+                                   dict(dx=100, D=31, hidden=[200, 200, 200], B=300), dict(dx=16, D=5, hidden=[72, 200, 33], B=1031)])
+def test_three_layer_tensor_core_kernel_equals_fma_paths(shape, dev):
+    """maf_tcd.cu (three hidden layers up to 200 wide on tcgen05.mma, all per-pair activations in tensor memory) against
+    the global-scratch deep path (RABI_TC=0) in every mode: metric, reverse- / forward-KL attack gradient, log_prob,
+    rsample + own log-density; pyloric shapes, ragged tiles, unequal widths, several tiles per CTA round."""
+    import os
+
+    ref, model, x = _fresh(shape, dev, seed=11)
+    xd = x.to(dev)
+    eng = model.engine()
+    g = torch.Generator().manual_seed(4)
+    D = shape["D"]
+    with torch.no_grad():
+        q = model(xd)
+        _, zs, _ = model.condition_inputs(xd)
+        for S in (3, 1):
+            z = torch.randn(S, xd.shape[0], D, generator=g).to(dev)
+            outs = []
+            for env in ({"RABI_TC": "0"}, {"RABI_TC": "1", "RABI_TC_GRAD_MIN_PAIRS": "1"}):
+                env = dict(env, RABI_WARP_MAX_PAIRS="0")
+                os.environ.update(env)
+                try:
+                    Ap = model(xd + 0.05).A
+                    kl = eng.rkl(Ap, q.A, z)
+                    gx, klm = eng.rkl_input_grad(xd + 0.05, zs[0], zs[1], q.A, z, 1.0 / xd.shape[0])
+                    gxf, klf = eng.rkl_input_grad(xd + 0.05, zs[0], zs[1], q.A, z, 1.0 / xd.shape[0], forward_kl=True)
+                    th, lq = eng.rsample(q.A, z)
+                    lp = eng.log_prob(Ap, th)
+                finally:
+                    for k in env:
+                        os.environ.pop(k, None)
+                outs.append((kl, gx, klm, gxf, klf, th, lq, lp))
+            a, b = outs
+            lp_scale = max(1.0, float(a[6].abs().max()))
+            assert rel_err(b[5], a[5]) < 1e-5, "rsample"
+            assert float((b[6] - a[6]).abs().max()) < 1e-5 * lp_scale, "own log-density"
+            assert float((b[7] - a[7]).abs().max()) < 1e-5 * lp_scale, "log_prob"
+            assert float((b[0] - a[0]).abs().max()) < 1e-5 * lp_scale, "metric"
+            assert float((b[2] - a[2]).abs().max()) < 1e-5 * lp_scale and float((b[4] - a[4]).abs().max()) < 1e-5 * lp_scale
+            assert_trajectories_match(b[1], a[1], 1e-4)
+            assert_trajectories_match(b[3], a[3], 1e-4)
