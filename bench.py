@@ -101,6 +101,16 @@ def algorithmic_flops(model, w):
     return dict(attack_pair=att, eval_pair=ev, pair_kernel_attack=pair_kernel_att, X=X / w["K"], R=R / w["K"])
 
 
+def bench_config(wname, w, world, flops):
+    """The ``config`` object of the bench line; the reference arm prints the SAME object (same workload, same sizes)."""
+    return {"workload": wname, "rows_per_gpu": w["rows"], "chunk": w["chunk"], "nb_iter": w["nb_iter"],
+            "S_att": w["S_att"], "S_eval": w["S_eval"], "dx": w["dx"], "D": w["D"], "hidden": w["hidden"], "K": w["K"],
+            "pairs_per_step": w["rows"] * pairs_per_row(w) * world,
+            "parallelism": f"rows sharded over {world} GPU(s), no data-path collective",
+            "l2": "per-step inputs (fresh base noise, 160 MB) exceed the 126 MB L2",
+            "flop_per_attack_pair": flops["attack_pair"], "flop_per_eval_pair": flops["eval_pair"]}
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -171,8 +181,8 @@ def cpu_reference_sample(w, model_state, threads, it_sample=10, seed=0):
     t_chunk = t_att / it_sample * w["nb_iter"] + t_eval
     pairs = w["chunk"] * pairs_per_row(w)
     sample = (f"oracle (PyTorch restatement of the reference path) on one {w['chunk']}-row chunk: {it_sample} of "
-              f"{w['nb_iter']} PGD iterations ({t_att:.2f} s) + S={w['S_eval']} metric ({t_eval:.2f} s), extrapolated "
-              f"linearly to {w['nb_iter']} iterations")
+              f"{w['nb_iter']} PGD iterations ({t_att:.2f} s) + S={w['S_eval']} metric ({t_eval:.2f} s)"
+              + ("" if it_sample == w["nb_iter"] else f", extrapolated linearly to {w['nb_iter']} iterations"))
     return pairs / t_chunk, sample, t_att + t_eval
 
 
@@ -200,22 +210,34 @@ def run_reference_arm(args, w, wname):
     model = make_weights(w)
     model.embedding_net = torch.nn.Sequential(ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])), model.embedding_net)
     threads = os.cpu_count() or 1
+    flops = algorithmic_flops(model, w)
+    # One timed step = ONE WHOLE chunk of the workload through the reference path: all nb_iter PGD iterations + the S_eval
+    # metric (lotka_volterra: ~7 s of CPU work) -- a measurement, not an extrapolation.  The warm-up steps only have to spin
+    # up the thread pool and the allocator, so they use 3 iterations.  Conditioners whose whole chunk takes minutes (pyloric
+    # shapes: ~80 s) time a bounded number of iterations per step and say so.
+    full = len(w["hidden"]) == 2
+    it_timed = w["nb_iter"] if full else 20
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
-        v, sample, dt = cpu_reference_sample(w, model.state_dict(), threads, it_sample=3, seed=i)
-        if i >= args.warmup:
+        timed_step = i >= args.warmup
+        v, sample, dt = cpu_reference_sample(w, model.state_dict(), threads, it_sample=it_timed if timed_step else 3, seed=i)
+        if timed_step:
             vals.append(v)
             secs.append(dt)
-    value = sum(vals) / len(vals)
+    pairs_chunk = w["chunk"] * pairs_per_row(w)
+    value = pairs_chunk * len(secs) / sum(secs) if full else sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wname, **{k: w[k] for k in ("dx", "D", "hidden", "K", "chunk", "nb_iter", "S_att", "S_eval")}},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": bench_config(wname, w, 1, flops),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "pairs_per_timed_step": pairs_chunk if full else w["chunk"] * (it_timed * w["S_att"] + w["S_eval"]),
+                         "extrapolated": not full},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference (pyro/advertorch/sbi) cannot be installed here; this arm times the oracle port of its "
-                "CPU path on all host threads",
+                "CPU path on all host threads; a timed step is one whole chunk of the config's rows (the CPU walks the "
+                "rows chunk by chunk at the same cost per chunk), value = pairs of the timed chunks / their wall time",
     }
     emit(json.dumps(line))
 
@@ -353,34 +375,53 @@ def emit(text):
         os.write(_RESULT_FD, (text + "\n").encode())
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="rabi_b200", choices=["rabi_b200", "reference"])
-    ap.add_argument("--workload", default="lotka_volterra_l2pgd_rkl", choices=list(WORKLOADS))
-    ap.add_argument("--rows", type=int, default=None, help="observations per GPU (default: the workload's)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--next-rows", action="store_true",
-                    help="measure the SURVEY 8f rows (fKL eval, coverage / NLL metrics, defenses) instead of the bench line")
-    args = ap.parse_args()
-    # stdout carries exactly ONE JSON line: whatever libraries print while the bench runs (e.g. NCCL's version banner under
-    # torchrun) is sent to stderr, and the result lines below are written to the saved descriptor
-    global _RESULT_FD
-    sys.stdout.flush()
-    _RESULT_FD = os.dup(1)
-    os.dup2(2, 1)
-    if args.next_rows:
-        return run_next_rows(args)
-    w = dict(WORKLOADS[args.workload])
-    if args.rows:
-        w["rows"] = args.rows
-    if args.impl == "reference":
-        return run_reference_arm(args, w, args.workload)
-    if args.warmup < 3:
-        args.warmup = 3
+def tensor_fraction(model, w):
+    """Share of the per-pair kernel's masked MACs that run as tcgen05.mma products: the hidden -> hidden products (and, on
+    the three-layer path, the hidden -> output product); layer 0 (K = D) and the own-degree blocks stay FMA code."""
+    tc = tot = 0
+    for k in range(w["K"]):
+        layers = getattr(model, f"t{k}").nn.layers
+        C = model.context_dim
+        tot += int(layers[0].mask[:, C:].sum()) + sum(int(l.mask.sum()) for l in layers[1:])
+        tc += sum(int(l.mask.sum()) for l in layers[1:-1])
+        if len(w["hidden"]) == 3:
+            tc += int(layers[-1].mask.sum())
+    return tc / max(tot, 1)
 
+
+def gpu_eager_sample(w, model_state, dev, it_sample=5):
+    """The oracle (op-for-op restatement of the reference's Pyro / advertorch path) run EAGERLY on the same B200 -- what
+    ``device: cuda`` gave the reference's authors: one chunk, ``it_sample`` PGD iterations + the S_eval metric, extrapolated."""
+    from oracle import rbi_oracle as O
+
+    ref = O.OracleMAF(w["dx"], w["D"], hidden_dims=w["hidden"], num_transforms=w["K"], shuffle=False,
+                      embedding_net=torch.nn.Sequential(O.ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])),
+                                                        make_embedding(w) or torch.nn.Identity()),
+                      log_scale_min_clip=-7, log_scale_max_clip=5, stable=False)
+    ref.load_state_dict(dict(model_state), strict=True)
+    ref = ref.to(dev).eval()
+    x = make_rows(w, 0, w["chunk"]).to(dev)
+    eps = float(0.5 * x.std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+    loss = O.ReverseKLLoss(mc_samples=w["S_att"])
+    O.l2pgd_perturb(ref, x, loss, eps, 1, eps / 10, cmin, cmax)   # warm-up (cuBLAS handles, allocator)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    xa = O.l2pgd_perturb(ref, x, loss, eps, it_sample, eps / 10, cmin, cmax)
+    torch.cuda.synchronize()
+    t_att = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.rkl_rob_metric(ref, x, xa, w["S_eval"])
+    torch.cuda.synchronize()
+    t_eval = time.perf_counter() - t0
+    t_chunk = t_att / it_sample * w["nb_iter"] + t_eval
+    return {"value": w["chunk"] * pairs_per_row(w) / t_chunk, "unit": UNIT, "kind": "port",
+            "sample": f"oracle in eager PyTorch on cuda:{dev.index}: one {w['chunk']}-row chunk, {it_sample} of {w['nb_iter']} PGD "
+                      f"iterations ({t_att:.2f} s) + S={w['S_eval']} metric ({t_eval:.2f} s), extrapolated linearly"}
+
+
+def measure(wname, w, args, steps, warmup, dev, world, rank, local, scaling, with_baselines):
+    """One bench record for workload ``wname`` (rows PER GPU already set in ``w``)."""
     import torch.distributed as dist
 
     from rabi_b200 import _lib
@@ -389,22 +430,11 @@ def main():
     from rabi_b200.metric import ReverseKLRobMetric
     from rabi_b200.models import ZScoreLayer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl rabi_b200) needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.build()
-
     model = make_weights(w)
     model.embedding_net = torch.nn.Sequential(ZScoreLayer(torch.zeros(w["dx"]), torch.ones(w["dx"])), model.embedding_net)
     state_cpu = {k: v.clone() for k, v in model.state_dict().items()}
     flops = algorithmic_flops(model, w)
+    tfrac = tensor_fraction(model, w)
     model = model.to(dev).eval()
     x_host = make_rows(w, rank, w["rows"]).pin_memory()
     x_dev = x_host.to(dev)
@@ -447,11 +477,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         ev1.record()
         barrier()
@@ -463,24 +493,27 @@ def main():
         return ms
 
     fma_peak = float(_lib.lib().rabi_fma_peak_tflops(local, 5))
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     barrier()
     launches0 = eng.launches
-    eng.profile(True)
-    with ClockSampler(local) as clocks:
-        ms = timed(step_device, args.steps)
-    kern_ms, kern_n = eng.profile_read()
-    eng.profile(False)
+    with ClockSampler(local) as clocks:   # `value` and `e2e` are both timed with the per-launch event records OFF
+        ms = timed(step_device, steps)
     launches = eng.launches - launches0
     step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
+    # separate pass for the dominant kernel's average launch duration (CUDA events around every launch on its stream)
+    n_prof = min(steps, 3)
+    eng.profile(True)
+    ms_prof = timed(step_device, n_prof)
+    kern_ms, kern_n = eng.profile_read()
+    eng.profile(False)
 
     pairs_step = w["rows"] * pairs_per_row(w) * world
-    value = pairs_step * args.steps / (ms * 1e-3)
-    e2e = pairs_step * args.steps / (ms_e2e * 1e-3)
+    value = pairs_step * steps / (ms * 1e-3)
+    e2e = pairs_step * steps / (ms_e2e * 1e-3)
 
-    # roofline of the dominant kernel: per-pair rKL forward+backward (one launch per PGD iteration)
+    # roofline of the dominant kernel: per-pair rKL forward + reverse (one launch per PGD iteration)
     pairs_launch = w["rows"] * w["S_att"]
     achieved = pairs_launch * flops["pair_kernel_attack"] / (kern_ms / max(kern_n, 1) * 1e-3) / 1e12 if kern_n else None
     peaks = {}
@@ -488,54 +521,122 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    traffic = None
-    on_chip = len(w["hidden"]) == 2 and w["D"] <= 12  # k_fast holds the per-pair state on chip; deeper / wider: kd_*
-    if args.workload == "lotka_volterra_l2pgd_rkl":
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "k_fast_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            pass
-    kernel_name = ("k_fast<GRAD> (per-pair rKL forward + reverse, one launch per PGD iteration)" if on_chip else
-                   f"kd_seq_fwd/kd_full_fwd/kd_full_bwd/kd_seq_bwd ({4 * w['K']} launches per PGD iteration, timed as a group)")
+    three = len(w["hidden"]) == 3
+    kernel_name = "k_tcd<GRAD>" if three else "k_tc<GRAD>"
+    traffic = traffic_src = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this kernel
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel_name]
+        if t["pairs_per_launch"] == pairs_launch:
+            traffic, traffic_src = t["dram_bytes_per_launch"], f"ncu capture at commit {t['commit']} ({t['file']})"
+    except Exception:
+        pass
+    # ceiling: the tensor-eligible share of the MACs at the 3xTF32 rate of the tensor pipe, the rest at the fp32 FMA rate
+    bf16 = peaks.get("bf16_tflops_sustained") or 1386.3
+    tc_peak = bf16 / 2.0 / 3.0      # TF32 runs at half the bf16 rate; one fp32-accurate product = 3 TF32 MMAs
+    ceiling = 1.0 / (tfrac / tc_peak + (1.0 - tfrac) / fma_peak) if fma_peak > 0 else None
     roofline = {
-        "bound": "fp32_fma", "kernel": kernel_name,
-        "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s",
-        "frac": (achieved / fma_peak) if (achieved and fma_peak > 0) else None, "traffic": traffic,
+        "bound": "tensor", "kernel": f"{kernel_name} (per-pair rKL forward + reverse on tcgen05.mma kind::tf32 (3xTF32) + FMA, "
+                                     "one launch per PGD iteration)",
+        "achieved": achieved, "peak": ceiling, "unit": "TFLOP/s",
+        "frac": (achieved / ceiling) if (achieved and ceiling) else None, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": int(4 * (w["rows"] * w["S_att"] * w["D"] + 3 * w["K"] * w["hidden"][0] * w["rows"])),
-        "peak_source": "rabi_fma_peak_tflops (register-only FFMA microbenchmark run in this process; "
-                       "MEASURED_PEAKS.json has no fp32 entry)",
+        "peak_source": f"{tfrac:.3f} of the kernel's algorithmic MACs are tensor-core products: ceiling = 1 / (share / (bf16_tflops_sustained "
+                       f"{bf16} [MEASURED_PEAKS.json] / 2 [TF32] / 3 [3xTF32]) + (1 - share) / fp32 FMA peak {fma_peak:.1f} "
+                       "[rabi_fma_peak_tflops, register-only FFMA microbenchmark run in this process])",
+        "tensor_share_of_macs": tfrac, "fp32_fma_peak": fma_peak,
+        "frac_of_fp32_fma_peak": (achieved / fma_peak) if (achieved and fma_peak > 0) else None,
         "flop_per_launch": pairs_launch * flops["pair_kernel_attack"],
         "kernel_ms_avg": kern_ms / max(kern_n, 1), "kernel_launches_timed": kern_n,
-        "kernel_share_of_step": kern_ms / ms if ms else None,
+        "kernel_share_of_step": kern_ms / ms_prof if ms_prof else None,
         "whole_step_tflops": (w["rows"] * (w["nb_iter"] * w["S_att"] * flops["attack_pair"] + w["S_eval"] * flops["eval_pair"])
-                              * args.steps / (ms * 1e-3) / 1e12),
+                              * steps / (ms * 1e-3) / 1e12),
         "hbm_gbs_measured_peak": peaks.get("hbm_gbs"),
     }
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        v, sample, _ = cpu_reference_sample(w, state_cpu, os.cpu_count() or 1, it_sample=10)
+    cpu = gpu_eager = None
+    if rank == 0 and world == 1 and with_baselines:
+        v, sample, _ = cpu_reference_sample(w, state_cpu, os.cpu_count() or 1, it_sample=30 if not three else 10)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        try:
+            gpu_eager = gpu_eager_sample(w, state_cpu, dev)
+        except Exception as e:  # the comparator must never take the bench line down
+            gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "rows_per_gpu": w["rows"], "chunk": w["chunk"], "nb_iter": w["nb_iter"],
-                   "S_att": w["S_att"], "S_eval": w["S_eval"], "dx": w["dx"], "D": w["D"], "hidden": w["hidden"], "K": w["K"],
-                   "pairs_per_step": pairs_step, "parallelism": f"rows sharded over {world} GPU(s), no data-path collective",
-                   "l2": "per-step inputs (fresh base noise, 160 MB) exceed the 126 MB L2",
-                   "flop_per_attack_pair": flops["attack_pair"], "flop_per_eval_pair": flops["eval_pair"]},
+        "config": bench_config(wname, w, world, flops),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
-                "d2h_bytes_per_step": int(loss_host.numel() * 4 + xadv_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": int(loss_host.numel() * 4 + xadv_host.numel() * 4), "ms_per_step": ms_e2e / steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": gpu_eager,
     }
-    emit(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="rabi_b200", choices=["rabi_b200", "reference"])
+    ap.add_argument("--workload", default="lotka_volterra_l2pgd_rkl", choices=list(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=None, help="observations per GPU (default: the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's rows on EVERY GPU; strong: the workload's rows in total, split over the GPUs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true",
+                    help="skip the second record (BASELINE config 5: pyloric ctx-space) carried under 'also' in the same JSON line")
+    ap.add_argument("--next-rows", action="store_true",
+                    help="measure the SURVEY 8f rows (fKL eval, coverage / NLL metrics, defenses) instead of the bench line")
+    args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: whatever libraries print while the bench runs (e.g. NCCL's version banner under
+    # torchrun) is sent to stderr, and the result lines below are written to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+    if args.next_rows:
+        return run_next_rows(args)
+    w = dict(WORKLOADS[args.workload])
+    if args.rows:
+        w["rows"] = args.rows
+    if args.impl == "reference":
+        return run_reference_arm(args, w, args.workload)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+
+    from rabi_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl rabi_b200) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.build()
+    if args.scaling == "strong":
+        w["rows"] = w["rows"] // world
+    line = measure(args.workload, w, args, args.steps, args.warmup, dev, world, rank, local, args.scaling,
+                   with_baselines=not args.no_cpu_baseline)
+    if args.workload == "lotka_volterra_l2pgd_rkl" and not args.no_config5:
+        # BASELINE config 5 (pyloric shapes, ctx-space, 100 000 observations over 8 GPUs = 12 500 per GPU) in front of the driver:
+        # a second, shorter measurement in the same run, carried under "also" (stdout keeps exactly one JSON line)
+        w5 = dict(WORKLOADS["pyloric_ctx_l2pgd_rkl"])
+        if args.scaling == "strong":
+            w5["rows"] = (8 * w5["rows"]) // world
+        rec = measure("pyloric_ctx_l2pgd_rkl", w5, args, 2, 1, dev, world, rank, local, args.scaling,
+                      with_baselines=not args.no_cpu_baseline)
+        line["also"] = {"pyloric_ctx_l2pgd_rkl": rec}
+    if rank == 0:
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

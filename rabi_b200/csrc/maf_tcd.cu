@@ -36,20 +36,28 @@
 
 namespace rabi {
 
-constexpr int TD_R0 = 0, TD_R1 = 200, TD_R2 = 400, TD_ST = 464;   // staging buffer b: hi at TD_ST + 16 b, lo 8 columns further
+constexpr int TD_R0 = 0, TD_R1 = 200, TD_R2 = 400, TD_ST = 464;   // staging buffer b (of TD_NB): hi at TD_ST + 16 b, lo 8 columns further
 constexpr int TD_MAXH = 200;
 constexpr int TD_NSLOT = 6;
 constexpr int TD_SLOT = 13312;     // bytes per ring slot (>= 2 halves x 2 k-chunks x 200 rows x 16 B), multiple of 128
 constexpr int TD_MAXP = 64;        // pieces per layer
-constexpr int TD_THREADS = 160;
+constexpr int TD_THREADS = 192;    // warps 0-3: the tile, warp 4: weight producer, warp 5: MMA issuer
+constexpr int TD_NB = 3;           // staging buffers of 8 inputs (hi, lo)
 
-struct TdPiece { int r0, nr, j, flags; };   // real units [r0, r0 + nr), nr <= 8, of degree j; flags bit 0: last piece of its group
-struct TdPush { int off16, bytes, dcol, N; };   // strip at image + 16 * off16; accumulator columns [dcol, dcol + N)
+// piece flags
+constexpr int TD_F_FWD = 1;   // the piece pushes into the next layer / the outputs (forward stream)
+constexpr int TD_F_REV = 2;   // the piece pushes its cotangents into the previous layer (reverse stream)
+constexpr int TD_F_DGN = 4;   // its product with the SAME degree group of the NEXT layer is an FMA block (zeroed in the strips)
+constexpr int TD_F_DGP = 8;   // the same for the group of the PREVIOUS layer
+struct TdPiece { int r0, nr, j, flags; };   // real units [r0, r0 + nr), nr <= 8, of degree j
+struct TdPush { int off16, bytes, dcol, N; };   // strip at image + 16 * off16; accumulator columns [dcol & 0xffff, .. + N); bit 16: overwrite
 
 struct TdBlk {   // word offsets inside the resident per-transform block
     int w0t, b1, b2, bo, wot;       // [H0][DP], [H1], [H2], [2 DP] (m, s interleaved), [H2][2 DP]
+    int dg01, dg12;                 // [D][8][8] own-degree blocks of W1 / W2 (rows: next layer's group, columns: this layer's)
     int perm, permy;
     int np, pstart, pieces;         // np[3]; pstart[3][D + 1]; pieces[3][TD_MAXP]
+    int dgi;                        // [2][D][4] (row0, rows, col0, cols) of the blocks above; rows = 0: no block
     int words;
 };
 
@@ -68,7 +76,7 @@ struct TdArgs {
     TdBlk blk;
     const char* strips;    // packed strips
     const TdPush* push;    // push tables
-    int ps_off[RABI_MAXK][4], ps_cnt[RABI_MAXK][4];   // per transform: streams FS, FF, BF, BS
+    int ps_off[RABI_MAXK][2], ps_cnt[RABI_MAXK][2];   // per transform: forward and reverse push streams
     float* vec;            // [(4K+2) D][stride]
     uint32_t* bits;        // [2K][3][TD_MAXP][stride]
     int stride;            // grid * 128
@@ -94,6 +102,24 @@ __device__ __forceinline__ void td_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 }
 __device__ __forceinline__ void td_commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(td_smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void td_mbar_init(uint64_t* mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(td_smem_u32(mbar)), "r"(count) : "memory");
+}
+// wait of the producer / issuer threads: they share a scheduler with a compute warp, so they back off between polls
+__device__ __forceinline__ void td_mbar_wait_bg(uint64_t* mbar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(td_smem_u32(mbar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(32);
+        if (++spins > 40000000u) {   // ~2 s: never hang the GPU
+            printf("rabi_b200 k_tcd: background mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
 }
 __device__ __forceinline__ void td_mbar_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t done = 0;
@@ -144,17 +170,20 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
     const int* Wi = reinterpret_cast<const int*>(Wb);
     float2* ms = reinterpret_cast<float2*>(Wb + a.blk.words);                           // [DP][128] (mbar, sbar) per position
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(8) uint64_t bar_blk, bar_push[2], bar_full[TD_NSLOT], bar_empty[TD_NSLOT];
+    __shared__ __align__(8) uint64_t bar_blk, bar_staged[TD_NB], bar_done[TD_NB], bar_full[TD_NSLOT], bar_empty[TD_NSLOT];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int K = g.K, D = g.D, H0 = g.H[0], H2 = g.H[2];
+    const int K = g.K, D = g.D, H0 = g.H[0];
     const float HALF_LOG_2PI = 0.91893853320467274178f;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(td_smem_u32(&bar_blk)) : "memory");
-        for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(td_smem_u32(&bar_push[i])) : "memory");
+        td_mbar_init(&bar_blk, 1);
+        for (int i = 0; i < TD_NB; ++i) {
+            td_mbar_init(&bar_staged[i], 128);
+            td_mbar_init(&bar_done[i], 1);
+        }
         for (int i = 0; i < TD_NSLOT; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(td_smem_u32(&bar_full[i])) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(td_smem_u32(&bar_empty[i])) : "memory");
+            td_mbar_init(&bar_full[i], 1);
+            td_mbar_init(&bar_empty[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -179,16 +208,50 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                 for (int ph = ph0; ph < nphase; ++ph) {
                     const int kind = ph / K, idx = ph - kind * K;
                     const int k = (kind == 0 || kind == 2) ? idx : K - 1 - idx;
-                    const TdPush* tbl = a.push + a.ps_off[k][kind];
-                    const int n = a.ps_cnt[k][kind];
+                    const TdPush* tbl = a.push + a.ps_off[k][kind >> 1];
+                    const int n = a.ps_cnt[k][kind >> 1];
                     for (int i = 0; i < n; ++i, ++e) {
                         const unsigned slot = e % TD_NSLOT, par = (e / TD_NSLOT) & 1u;
-                        td_mbar_wait(&bar_empty[slot], par ^ 1u);
+                        td_mbar_wait_bg(&bar_empty[slot], par ^ 1u);
                         const int off16 = __ldg(&tbl[i].off16), bytes = __ldg(&tbl[i].bytes);
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(td_smem_u32(&bar_full[slot])), "r"((uint32_t)bytes) : "memory");
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                      :: "r"(td_smem_u32(ring + slot * TD_SLOT)), "l"(a.strips + (size_t)off16 * 16), "r"((uint32_t)bytes),
                                         "r"(td_smem_u32(&bar_full[slot])) : "memory");
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer: one thread turns every staged group into a 3xTF32 push =====================
+        if (tid == 160) {
+            const uint32_t tcol = tmem_base_s;
+            unsigned e = 0;
+            for (int round = 0; round < rounds; ++round) {
+                if (round * (int)gridDim.x + (int)blockIdx.x >= a.ntiles) break;
+                for (int ph = ph0; ph < nphase; ++ph) {
+                    const int kind = ph / K, idx = ph - kind * K;
+                    const int k = (kind == 0 || kind == 2) ? idx : K - 1 - idx;
+                    const TdPush* tbl = a.push + a.ps_off[k][kind >> 1];
+                    const int n = a.ps_cnt[k][kind >> 1];
+                    for (int i = 0; i < n; ++i, ++e) {
+                        const unsigned slot = e % TD_NSLOT, sb = e % TD_NB;
+                        const int N = __ldg(&tbl[i].N), dcol = __ldg(&tbl[i].dcol);
+                        const uint32_t acc = (dcol >> 16) ? 0u : 1u;   // bit 16: first push into its region (overwrite)
+                        td_mbar_wait_bg(&bar_staged[sb], (e / TD_NB) & 1u);
+                        td_mbar_wait_bg(&bar_full[slot], (e / TD_NSLOT) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t idesc = td_make_idesc(128, N);
+                        const uint32_t lbo = (uint32_t)N * 16u;
+                        const uint32_t sbase = td_smem_u32(ring + slot * TD_SLOT);
+                        const uint64_t dhi = td_make_desc(sbase, lbo, 128u), dlo = td_make_desc(sbase + 2u * lbo, lbo, 128u);
+                        const uint32_t ah = tcol + TD_ST + 16 * sb, al = ah + 8;
+                        const uint32_t dst = tcol + (uint32_t)(dcol & 0xFFFF);
+                        td_mma_ts(dst, ah, dhi, idesc, acc);
+                        td_mma_ts(dst, al, dhi, idesc, 1u);
+                        td_mma_ts(dst, ah, dlo, idesc, 1u);
+                        td_commit(&bar_done[sb]);
+                        td_commit(&bar_empty[slot]);
                     }
                 }
             }
@@ -202,58 +265,36 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
         const size_t VS = (size_t)a.stride;
         float2* msp = ms + tid;
         const int oV = 0, oU = (K + 1) * D, oSHP = (2 * K + 1) * D, oSHQ = (3 * K + 1) * D, oG = (4 * K + 1) * D;
-        unsigned e = 0;                // running push counter (ring position), identical in every thread and in the producer
-        uint32_t pph[2] = {0u, 0u};    // parity of the two staging-buffer barriers
-        bool pend[2] = {false, false};
-        int nb = 0;                    // staging buffer of the next push
-        uint32_t bph = 0;              // parity of the block barrier
+        unsigned e = 0;        // pushes staged so far (identical in every thread, the producer and the issuer)
+        unsigned waited = 0;   // pushes [0, waited) are known to be complete
+        uint32_t bph = 0;      // parity of the block barrier
         int resident = -1;
 
-        auto wait_buf = [&](int b) {
-            if (pend[b]) {
-                td_mbar_wait(&bar_push[b], pph[b]);
-                pph[b] ^= 1u;
-                pend[b] = false;
+        // pushes complete in issue order; every thread observes every phase of the bar_done barriers in order
+        auto wait_upto = [&](unsigned n) {
+            if (waited < n) {
+                do {
+                    td_mbar_wait(&bar_done[waited % TD_NB], (waited / TD_NB) & 1u);
+                    ++waited;
+                } while (waited < n);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
         };
-        auto wait_all = [&]() {
-            wait_buf(0);
-            wait_buf(1);
-        };
-        // stage 8 values (hi, lo) into the free staging buffer and issue the push described by `pu` without waiting
-        auto stage_push = [&](const float (&v)[8], const TdPush* pu, bool first) {
-            const int b = nb;
-            nb ^= 1;
-            wait_buf(b);
+        // stage 8 values as TF32 (hi, lo) halves into the next staging buffer and hand the push to the issuer
+        auto stage_push = [&](const float (&v)[8]) {
+            const unsigned sb = e % TD_NB;
+            if (e >= TD_NB) wait_upto(e - TD_NB + 1);   // the push that used this buffer before
             float hi[8], lo[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 hi[q] = td_hi(v[q]);
                 lo[q] = v[q] - hi[q];
             }
-            td_st8(trow + TD_ST + 16 * b, hi);
-            td_st8(trow + TD_ST + 16 * b + 8, lo);
+            td_st8(trow + TD_ST + 16 * sb, hi);
+            td_st8(trow + TD_ST + 16 * sb + 8, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 0) {
-                const unsigned slot = e % TD_NSLOT, par = (e / TD_NSLOT) & 1u;
-                const int N = __ldg(&pu->N), dcol = __ldg(&pu->dcol);
-                td_mbar_wait(&bar_full[slot], par);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t idesc = td_make_idesc(128, N);
-                const uint32_t lbo = (uint32_t)N * 16u;
-                const uint32_t sbase = td_smem_u32(ring + slot * TD_SLOT);
-                const uint64_t dhi = td_make_desc(sbase, lbo, 128u), dlo = td_make_desc(sbase + 2u * lbo, lbo, 128u);
-                const uint32_t ah = tcol + TD_ST + 16 * b, al = ah + 8;
-                td_mma_ts(tcol + (uint32_t)dcol, ah, dhi, idesc, first ? 0u : 1u);
-                td_mma_ts(tcol + (uint32_t)dcol, al, dhi, idesc, 1u);
-                td_mma_ts(tcol + (uint32_t)dcol, ah, dlo, idesc, 1u);
-                td_commit(&bar_push[b]);
-                td_commit(&bar_empty[slot]);
-            }
-            pend[b] = true;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(td_smem_u32(&bar_staged[sb])) : "memory");
             ++e;
         };
 
@@ -278,9 +319,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                 const int kind = ph / K, idx = ph - kind * K;
                 const int k = (kind == 0 || kind == 2) ? idx : K - 1 - idx;
                 const bool seq = (kind == 0 || kind == 3);
-                if (resident != k) {   // resident block of transform k (all pushes of the previous phase were waited for)
-                    wait_all();
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (resident != k) {   // resident block of transform k
+                    asm volatile("bar.sync 1, 128;" ::: "memory");   // every thread is done with the previous block
                     if (tid == 0) {
                         const uint32_t bytes = (uint32_t)a.blk.words * 4u;
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(td_smem_u32(&bar_blk)), "r"(bytes) : "memory");
@@ -301,23 +341,24 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                 const float* b2 = Wb + bk.b2;
                 const float* bo = Wb + bk.bo;
                 const float* WoT = Wb + bk.wot;
+                const float* dg01 = Wb + bk.dg01;                                     // [D][8 out][8 in]
+                const float* dg12 = Wb + bk.dg12;
                 const int* perm = Wi + bk.perm;
                 const int* permy = Wi + bk.permy;
-                const int* np = Wi + bk.np;
                 const int* pstart = Wi + bk.pstart;                                   // [3][D + 1]
                 const TdPiece* pieces = reinterpret_cast<const TdPiece*>(Wi + bk.pieces);   // [3][TD_MAXP]
-                const TdPush* pu = a.push + a.ps_off[k][kind];                         // next push of this phase
                 uint32_t* bits = bitp + (size_t)((seq ? k : K + k) * 3 * TD_MAXP) * VS;  // [layer][piece]
                 const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
+                const int* ps0 = pstart;
+                const int* ps1 = pstart + (D + 1);
+                const int* ps2 = pstart + 2 * (D + 1);
 
                 if (kind < 2) {
-                    // ===================== forward pass of transform k =====================
+                    // ===================== forward pass of transform k (step-structured; seq: y_j produced by step j) =====================
                     const float* Abase = (seq ? a.A_p : a.A_q) + (size_t)k * H0 * a.B + b;
                     float y[DP];
 #pragma unroll
                     for (int jj = 0; jj < DP; ++jj) y[jj] = (!seq && jj < D) ? vecp[(size_t)(src + permy[jj]) * VS] : 0.f;
-                    bool first0 = true, first1 = true, first2 = true;
-                    // layer-0 piece: h = relu(A[u] + W0t[u] . y) over the positions < jlim
                     float an[8];
                     auto load_A = [&](const TdPiece& c) {
                         const float* ap = Abase + (size_t)c.r0 * a.B;
@@ -327,141 +368,175 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                             ap += a.B;
                         }
                     };
-                    auto l0_piece = [&](int pi, int jlim) {
-                        const TdPiece c = pieces[pi];
-                        float pre[8];
+                    unsigned markp0 = e, markp1 = e, markp2 = e;
+                    float hv0[8], hv1[8], hv2[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) pre[i] = an[i];
-                        if (pi + 1 < np[0]) load_A(pieces[pi + 1]);   // in flight during this piece's push
-#pragma unroll
-                        for (int q4 = 0; q4 < DP / 4; ++q4) {
-                            if (4 * q4 < jlim) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)min(c.r0 + i, H0 - 1) * DP + 4 * q4);
-                                    pre[i] = fmaf(w.x, y[4 * q4], pre[i]);
-                                    pre[i] = fmaf(w.y, y[4 * q4 + 1], pre[i]);
-                                    pre[i] = fmaf(w.z, y[4 * q4 + 2], pre[i]);
-                                    pre[i] = fmaf(w.w, y[4 * q4 + 3], pre[i]);
-                                }
-                            }
-                        }
-                        float hv[8];
-                        uint32_t cm = 0u;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const bool on = i < c.nr && pre[i] > 0.f;
-                            hv[i] = on ? pre[i] : 0.f;
-                            cm |= on ? (1u << i) : 0u;
-                        }
-                        if (GRADM) bits[(size_t)pi * VS] = cm;
-                        stage_push(hv, pu++, first0);
-                        first0 = false;
-                    };
-                    // hidden piece of layer l (1 or 2): h = relu(acc + bias), read from region `rsrc`; returns the values
-                    auto mid_piece = [&](int l, int pi, uint32_t rsrc, const float* bias, float (&hv)[8]) {
-                        const TdPiece c = pieces[l * TD_MAXP + pi];
-                        float acc[8];
-                        td_ld8(trow + rsrc + (uint32_t)c.r0, acc);
-                        uint32_t cm = 0u;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float val = acc[i] + bias[min(c.r0 + i, TD_MAXH - 1)];
-                            const bool on = i < c.nr && val > 0.f;
-                            hv[i] = on ? val : 0.f;
-                            cm |= on ? (1u << i) : 0u;
-                        }
-                        if (GRADM) bits[(size_t)(l * TD_MAXP + pi) * VS] = cm;
-                        return c;
-                    };
+                    for (int i = 0; i < 8; ++i) hv0[i] = hv1[i] = hv2[i] = 0.f;
                     load_A(pieces[0]);
-                    if (seq) {
-                        float zn = vecp[(size_t)(oV + k * D + perm[0]) * VS];
-                        for (int j = 0; j < D; ++j) {
-                            const float zj = zn;
-                            if (j + 1 < D) zn = vecp[(size_t)(oV + k * D + perm[j + 1]) * VS];
-                            for (int pi = pstart[j]; pi < pstart[j + 1]; ++pi) l0_piece(pi, j);
-                            wait_all();
-                            for (int pi = pstart[(D + 1) + j]; pi < pstart[(D + 1) + j + 1]; ++pi) {
-                                float hv[8];
-                                mid_piece(1, pi, TD_R0, b1, hv);
-                                stage_push(hv, pu++, first1);
-                                first1 = false;
+                    float zn = seq ? vecp[(size_t)(oV + k * D + perm[0]) * VS] : 0.f;
+                    for (int j = 0; j < D; ++j) {
+                        const float zj = zn;
+                        if (seq && j + 1 < D) zn = vecp[(size_t)(oV + k * D + perm[j + 1]) * VS];
+                        // ---- layer 0, group j: h = relu(A[u] + W0t[u] . y) (only positions < j have non-zero weights)
+                        for (int pi = ps0[j]; pi < ps0[j + 1]; ++pi) {
+                            const TdPiece c = pieces[pi];
+                            float pre[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) pre[i] = an[i];
+                            if (pi + 1 < ps0[D]) load_A(pieces[pi + 1]);
+#pragma unroll
+                            for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                if (4 * q4 < j) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 w = *reinterpret_cast<const float4*>(W0t + (size_t)(c.r0 + i) * DP + 4 * q4);
+                                        pre[i] = fmaf(w.x, y[4 * q4], pre[i]);
+                                        pre[i] = fmaf(w.y, y[4 * q4 + 1], pre[i]);
+                                        pre[i] = fmaf(w.z, y[4 * q4 + 2], pre[i]);
+                                        pre[i] = fmaf(w.w, y[4 * q4 + 3], pre[i]);
+                                    }
+                                }
                             }
-                            wait_all();
-                            // last hidden layer: the own group's part of (m_j, s_j) by FMA, the later positions by an un-waited push
-                            float2 msj = make_float2(bo[2 * j], bo[2 * j + 1]);
-                            if (j > 0) {   // contributions of the groups < j (their pushes are complete after wait_all)
-                                float m0, s0;
-                                td_ld2(trow + TD_R2 + 2 * j, m0, s0);
-                                msj.x += m0;
-                                msj.y += s0;
+                            uint32_t cm = 0u;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const bool on = i < c.nr && pre[i] > 0.f;
+                                hv0[i] = on ? pre[i] : 0.f;
+                                cm |= on ? (1u << i) : 0u;
                             }
-                            for (int pi = pstart[2 * (D + 1) + j]; pi < pstart[2 * (D + 1) + j + 1]; ++pi) {
-                                float hv[8];
-                                const TdPiece c = mid_piece(2, pi, TD_R1, b2, hv);
+                            if (GRADM) bits[(size_t)pi * VS] = cm;
+                            if (c.flags & TD_F_FWD) stage_push(hv0);
+                        }
+                        const unsigned mark0 = e;
+                        // ---- layer 1, group j: accumulated pushes of the groups < j (+ own group: FMA block or waited push)
+                        for (int pi = ps1[j]; pi < ps1[j + 1]; ++pi) {
+                            const TdPiece c = pieces[TD_MAXP + pi];
+                            float acc[8];
+                            if (c.flags & TD_F_DGP) {
+                                wait_upto(markp0);
+                                if (j > 0) {
+                                    td_ld8(trow + TD_R0 + (uint32_t)c.r0, acc);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+                                }
+                                const float4* dq = reinterpret_cast<const float4*>(dg01 + (size_t)j * 64);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float2 wj = *reinterpret_cast<const float2*>(WoT + (size_t)min(c.r0 + i, H2 - 1) * 2 * DP + 2 * j);
-                                    msj = td_ffma2(wj, make_float2(hv[i], hv[i]), msj);
+                                    const float4 w0 = dq[2 * i], w1 = dq[2 * i + 1];
+                                    acc[i] = fmaf(w0.x, hv0[0], acc[i]);
+                                    acc[i] = fmaf(w0.y, hv0[1], acc[i]);
+                                    acc[i] = fmaf(w0.z, hv0[2], acc[i]);
+                                    acc[i] = fmaf(w0.w, hv0[3], acc[i]);
+                                    acc[i] = fmaf(w1.x, hv0[4], acc[i]);
+                                    acc[i] = fmaf(w1.y, hv0[5], acc[i]);
+                                    acc[i] = fmaf(w1.z, hv0[6], acc[i]);
+                                    acc[i] = fmaf(w1.w, hv0[7], acc[i]);
                                 }
-                                if (j + 1 < D) {
-                                    stage_push(hv, pu++, first2);
-                                    first2 = false;
-                                }
+                            } else {
+                                wait_upto(mark0);
+                                td_ld8(trow + TD_R0 + (uint32_t)c.r0, acc);
                             }
-                            const float sh = fminf(fmaxf(msj.y, g.lo), g.hi);
+                            uint32_t cm = 0u;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float val = acc[i] + b1[c.r0 + i];
+                                const bool on = i < c.nr && val > 0.f;
+                                hv1[i] = on ? val : 0.f;
+                                cm |= on ? (1u << i) : 0u;
+                            }
+                            if (GRADM) bits[(size_t)(TD_MAXP + pi) * VS] = cm;
+                            if (c.flags & TD_F_FWD) stage_push(hv1);
+                        }
+                        const unsigned mark1 = e;
+                        // ---- layer 2, group j; its part of (m_j, s_j) by FMA, the later positions by a push
+                        float2 msj = make_float2(bo[2 * j], bo[2 * j + 1]);
+                        for (int pi = ps2[j]; pi < ps2[j + 1]; ++pi) {
+                            const TdPiece c = pieces[2 * TD_MAXP + pi];
+                            float acc[8];
+                            if (c.flags & TD_F_DGP) {
+                                wait_upto(markp1);
+                                if (j > 0) {
+                                    td_ld8(trow + TD_R1 + (uint32_t)c.r0, acc);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+                                }
+                                const float4* dq = reinterpret_cast<const float4*>(dg12 + (size_t)j * 64);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 w0 = dq[2 * i], w1 = dq[2 * i + 1];
+                                    acc[i] = fmaf(w0.x, hv1[0], acc[i]);
+                                    acc[i] = fmaf(w0.y, hv1[1], acc[i]);
+                                    acc[i] = fmaf(w0.z, hv1[2], acc[i]);
+                                    acc[i] = fmaf(w0.w, hv1[3], acc[i]);
+                                    acc[i] = fmaf(w1.x, hv1[4], acc[i]);
+                                    acc[i] = fmaf(w1.y, hv1[5], acc[i]);
+                                    acc[i] = fmaf(w1.z, hv1[6], acc[i]);
+                                    acc[i] = fmaf(w1.w, hv1[7], acc[i]);
+                                }
+                            } else {
+                                wait_upto(mark1);
+                                td_ld8(trow + TD_R1 + (uint32_t)c.r0, acc);
+                            }
+                            uint32_t cm = 0u;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float val = acc[i] + b2[c.r0 + i];
+                                const bool on = i < c.nr && val > 0.f;
+                                hv2[i] = on ? val : 0.f;
+                                cm |= on ? (1u << i) : 0u;
+                            }
+                            if (GRADM) bits[(size_t)(2 * TD_MAXP + pi) * VS] = cm;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 wj = *reinterpret_cast<const float2*>(WoT + (size_t)(c.r0 + i) * 2 * DP + 2 * j);
+                                msj = td_ffma2(wj, make_float2(hv2[i], hv2[i]), msj);
+                            }
+                            if (c.flags & TD_F_FWD) stage_push(hv2);
+                        }
+                        const unsigned mark2 = e;
+                        // ---- position j: contributions of the groups < j come from the accumulator
+                        if (j > 0) {
+                            wait_upto(markp2);
+                            float m0, s0;
+                            td_ld2(trow + TD_R2 + 2 * j, m0, s0);
+                            msj.x += m0;
+                            msj.y += s0;
+                        }
+                        const float sh = fminf(fmaxf(msj.y, g.lo), g.hi);
+                        if (seq) {
                             const float yj = (zj - msj.x) * expf(-sh);
 #pragma unroll
                             for (int jj = 0; jj < DP; ++jj) y[jj] = jj == j ? yj : y[jj];
                             logp += sh;
                             vecp[(size_t)(oSHP + k * D + j) * VS] = sh;
                             vecp[(size_t)(oV + (k + 1) * D + permy[j]) * VS] = yj;
-                        }
-                    } else {
-                        for (int pi = 0; pi < np[0]; ++pi) l0_piece(pi, D);
-                        wait_all();
-                        for (int pi = 0; pi < np[1]; ++pi) {
-                            float hv[8];
-                            mid_piece(1, pi, TD_R0, b1, hv);
-                            stage_push(hv, pu++, first1);
-                            first1 = false;
-                        }
-                        wait_all();
-                        for (int pi = 0; pi < np[2]; ++pi) {
-                            float hv[8];
-                            mid_piece(2, pi, TD_R1, b2, hv);
-                            stage_push(hv, pu++, first2);
-                            first2 = false;
-                        }
-                        wait_all();
-                        // u_k = exp(clamp(s)) * u_{k+1} + m
-                        for (int jj = 0; jj < D; ++jj) {
-                            float m0, s0;
-                            td_ld2(trow + TD_R2 + 2 * jj, m0, s0);
-                            m0 += bo[2 * jj];
-                            s0 += bo[2 * jj + 1];
-                            const float sh = fminf(fmaxf(s0, g.lo), g.hi);
+                        } else {   // u_k = exp(clamp(s)) * u_{k+1} + m
                             float yj = 0.f;
 #pragma unroll
-                            for (int q = 0; q < DP; ++q) yj = q == jj ? y[q] : yj;
-                            vecp[(size_t)(oSHQ + k * D + jj) * VS] = sh;
+                            for (int q = 0; q < DP; ++q) yj = q == j ? y[q] : yj;
+                            vecp[(size_t)(oSHQ + k * D + j) * VS] = sh;
                             logq += sh;
-                            vecp[(size_t)(oU + k * D + perm[jj]) * VS] = fmaf(expf(sh), yj, m0);
+                            vecp[(size_t)(oU + k * D + perm[j]) * VS] = fmaf(expf(sh), yj, msj.x);
                         }
-                        if (k == 0) {  // end of the density chain: base log-density, KL term, reverse-mode seed
-                            float ssq = 0.f;
-                            for (int d = 0; d < D; ++d) {
-                                const float u = vecp[(size_t)(oU + d) * VS];
-                                ssq = fmaf(u, u, ssq);
-                                if (GRADM) vecp[(size_t)(oG + d) * VS] = a.w * u;  // d(-w log q)/d u_0
-                            }
-                            logq += -0.5f * ssq - (float)D * HALF_LOG_2PI;
-                            if (a.diff && live) a.diff[pidx] = MODE == TC_LOGPROB ? logq : logp - logq;
+                        markp0 = mark0;
+                        markp1 = mark1;
+                        markp2 = mark2;
+                    }
+                    wait_upto(e);   // the next pass overwrites the accumulators
+                    if (!seq && k == 0) {  // end of the density chain: base log-density, KL term, reverse-mode seed
+                        float ssq = 0.f;
+                        for (int d = 0; d < D; ++d) {
+                            const float u = vecp[(size_t)(oU + d) * VS];
+                            ssq = fmaf(u, u, ssq);
+                            if (GRADM) vecp[(size_t)(oG + d) * VS] = a.w * u;  // d(-w log q)/d u_0
                         }
+                        logq += -0.5f * ssq - (float)D * HALF_LOG_2PI;
+                        if (a.diff && live) a.diff[pidx] = MODE == TC_LOGPROB ? logq : logp - logq;
                     }
                 } else {
-                    // ===================== reverse pass of transform k =====================
+                    // ===================== reverse pass of transform k (steps in descending order) =====================
                     const float w = a.w;
                     float yb[DP];
                     if (seq) {
@@ -483,67 +558,17 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                     }
                     float* gAbase = a.gA + (size_t)k * H0 * a.B + b;
                     const bool emit = (seq || MODE == TC_FKL) && live;
-                    bool firstA = true, firstB = true;
-                    // cotangents of the last hidden layer's piece: g = relu'(.) * sum_{jj >= jlo} WoT[v][jj] . (mbar, sbar)_jj
-                    auto g3_piece = [&](int pi, int jlo) {
-                        const TdPiece c = pieces[2 * TD_MAXP + pi];
-                        const uint32_t cm = bits[(size_t)(2 * TD_MAXP + pi) * VS];
-                        float2 acc[8];
+                    unsigned markp2 = e, markp1 = e;
+                    float gs2[8], gs1[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] = make_float2(0.f, 0.f);
-                        for (int jj = jlo; jj < D; ++jj) {
-                            const float2 mv = msp[jj * 128];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float2 wj = *reinterpret_cast<const float2*>(WoT + (size_t)min(c.r0 + i, H2 - 1) * 2 * DP + 2 * jj);
-                                acc[i] = td_ffma2(wj, mv, acc[i]);
-                            }
-                        }
-                        float gs[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) gs[i] = ((cm >> i) & 1u) ? acc[i].x + acc[i].y : 0.f;
-                        stage_push(gs, pu++, firstA);
-                        firstA = false;
-                    };
-                    auto g2_piece = [&](int pi) {   // cotangents of hidden layer 1 (read from R0), pushed into R1
-                        const TdPiece c = pieces[TD_MAXP + pi];
-                        const uint32_t cm = bits[(size_t)(TD_MAXP + pi) * VS];
-                        float acc[8], gs[8];
-                        td_ld8(trow + TD_R0 + (uint32_t)c.r0, acc);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) gs[i] = ((cm >> i) & 1u) ? acc[i] : 0.f;
-                        stage_push(gs, pu++, firstB);
-                        firstB = false;
-                    };
-                    auto g1_piece = [&](int pi, int jlim) {   // layer-0 cotangents (read from R1): d/dA, and d/dy of the positions < jlim
-                        const TdPiece c = pieces[pi];
-                        const uint32_t cm = bits[(size_t)pi * VS];
-                        float acc[8], gv[8];
-                        td_ld8(trow + TD_R1 + (uint32_t)c.r0, acc);
-                        float* gAp = gAbase + (size_t)c.r0 * a.B;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const bool on = (cm >> i) & 1u;
-                            gv[i] = on ? acc[i] : 0.f;
-                            if (emit && on) atomicAdd(gAp + (size_t)i * a.B, gv[i]);
-                        }
-#pragma unroll
-                        for (int q4 = 0; q4 < DP / 4; ++q4) {
-                            if (4 * q4 < jlim) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 w4 = *reinterpret_cast<const float4*>(W0t + (size_t)min(c.r0 + i, H0 - 1) * DP + 4 * q4);
-                                    yb[4 * q4] = fmaf(w4.x, gv[i], yb[4 * q4]);
-                                    yb[4 * q4 + 1] = fmaf(w4.y, gv[i], yb[4 * q4 + 1]);
-                                    yb[4 * q4 + 2] = fmaf(w4.z, gv[i], yb[4 * q4 + 2]);
-                                    yb[4 * q4 + 3] = fmaf(w4.w, gv[i], yb[4 * q4 + 3]);
-                                }
-                            }
-                        }
-                    };
+                    for (int i = 0; i < 8; ++i) gs2[i] = gs1[i] = 0.f;
+                    float yvn = 0.f, shn = 0.f;
                     if (seq) {
-                        float yvn = vecp[(size_t)(oV + (k + 1) * D + permy[D - 1]) * VS], shn = vecp[(size_t)(oSHP + k * D + D - 1) * VS];
-                        for (int j = D - 1; j >= 0; --j) {
+                        yvn = vecp[(size_t)(oV + (k + 1) * D + permy[D - 1]) * VS];
+                        shn = vecp[(size_t)(oSHP + k * D + D - 1) * VS];
+                    }
+                    for (int j = D - 1; j >= 0; --j) {
+                        if (seq) {
                             const float yvj = yvn, shj = shn;
                             if (j > 0) {
                                 yvn = vecp[(size_t)(oV + (k + 1) * D + permy[j - 1]) * VS];
@@ -555,18 +580,118 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                             const float zbj = ybj * expf(-shj);
                             msp[j * 128] = make_float2(-zbj, fmaf(-ybj, yvj, w));
                             vecp[(size_t)(oG + perm[j]) * VS] = zbj;   // the old oG values are all in yb already
-                            for (int pi = pstart[2 * (D + 1) + j + 1] - 1; pi >= pstart[2 * (D + 1) + j]; --pi) g3_piece(pi, j);
-                            wait_all();
-                            for (int pi = pstart[(D + 1) + j + 1] - 1; pi >= pstart[(D + 1) + j]; --pi) g2_piece(pi);
-                            wait_all();
-                            for (int pi = pstart[j]; pi < pstart[j + 1]; ++pi) g1_piece(pi, j);
                         }
-                    } else {
-                        for (int pi = np[2] - 1; pi >= 0; --pi) g3_piece(pi, pieces[2 * TD_MAXP + pi].j);
-                        wait_all();
-                        for (int pi = np[1] - 1; pi >= 0; --pi) g2_piece(pi);
-                        wait_all();
-                        for (int pi = 0; pi < np[0]; ++pi) g1_piece(pi, pieces[pi].j);
+                        // ---- layer 2, group j: g = relu'(.) * sum_{jj >= j} WoT[v][jj] . (mbar, sbar)_jj
+                        for (int pi = ps2[j + 1] - 1; pi >= ps2[j]; --pi) {
+                            const TdPiece c = pieces[2 * TD_MAXP + pi];
+                            const uint32_t cm = bits[(size_t)(2 * TD_MAXP + pi) * VS];
+                            float2 acc[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[i] = make_float2(0.f, 0.f);
+                            for (int jj = j; jj < D; ++jj) {
+                                const float2 mv = msp[jj * 128];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float2 wj = *reinterpret_cast<const float2*>(WoT + (size_t)(c.r0 + i) * 2 * DP + 2 * jj);
+                                    acc[i] = td_ffma2(wj, mv, acc[i]);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) gs2[i] = ((cm >> i) & 1u) ? acc[i].x + acc[i].y : 0.f;
+                            if (c.flags & TD_F_REV) stage_push(gs2);
+                        }
+                        const unsigned mark2 = e;
+                        // ---- layer 1, group j: cotangents pushed by the layer-2 groups > j (+ own group: FMA block or waited push)
+                        for (int pi = ps1[j + 1] - 1; pi >= ps1[j]; --pi) {
+                            const TdPiece c = pieces[TD_MAXP + pi];
+                            const uint32_t cm = bits[(size_t)(TD_MAXP + pi) * VS];
+                            float acc[8];
+                            if (c.flags & TD_F_DGN) {
+                                wait_upto(markp2);
+                                if (j < D - 1) {
+                                    td_ld8(trow + TD_R0 + (uint32_t)c.r0, acc);
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                                }
+                                const float4* dq = reinterpret_cast<const float4*>(dg12 + (size_t)j * 64);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 w0 = dq[2 * i], w1 = dq[2 * i + 1];
+                                    acc[0] = fmaf(w0.x, gs2[i], acc[0]);
+                                    acc[1] = fmaf(w0.y, gs2[i], acc[1]);
+                                    acc[2] = fmaf(w0.z, gs2[i], acc[2]);
+                                    acc[3] = fmaf(w0.w, gs2[i], acc[3]);
+                                    acc[4] = fmaf(w1.x, gs2[i], acc[4]);
+                                    acc[5] = fmaf(w1.y, gs2[i], acc[5]);
+                                    acc[6] = fmaf(w1.z, gs2[i], acc[6]);
+                                    acc[7] = fmaf(w1.w, gs2[i], acc[7]);
+                                }
+                            } else {
+                                wait_upto(mark2);
+                                td_ld8(trow + TD_R0 + (uint32_t)c.r0, acc);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) gs1[i] = ((cm >> i) & 1u) ? acc[i] : 0.f;
+                            if (c.flags & TD_F_REV) stage_push(gs1);
+                        }
+                        const unsigned mark1 = e;
+                        // ---- layer 0, group j: d/dA, and d/dy of the positions < j
+                        for (int pi = ps0[j]; pi < ps0[j + 1]; ++pi) {
+                            const TdPiece c = pieces[pi];
+                            const uint32_t cm = bits[(size_t)pi * VS];
+                            float acc[8], gv[8];
+                            if (c.flags & TD_F_DGN) {
+                                wait_upto(markp1);
+                                if (j < D - 1) {
+                                    td_ld8(trow + TD_R1 + (uint32_t)c.r0, acc);
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                                }
+                                const float4* dq = reinterpret_cast<const float4*>(dg01 + (size_t)j * 64);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 w0 = dq[2 * i], w1 = dq[2 * i + 1];
+                                    acc[0] = fmaf(w0.x, gs1[i], acc[0]);
+                                    acc[1] = fmaf(w0.y, gs1[i], acc[1]);
+                                    acc[2] = fmaf(w0.z, gs1[i], acc[2]);
+                                    acc[3] = fmaf(w0.w, gs1[i], acc[3]);
+                                    acc[4] = fmaf(w1.x, gs1[i], acc[4]);
+                                    acc[5] = fmaf(w1.y, gs1[i], acc[5]);
+                                    acc[6] = fmaf(w1.z, gs1[i], acc[6]);
+                                    acc[7] = fmaf(w1.w, gs1[i], acc[7]);
+                                }
+                            } else {
+                                wait_upto(mark1);
+                                td_ld8(trow + TD_R1 + (uint32_t)c.r0, acc);
+                            }
+                            float* gAp = gAbase + (size_t)c.r0 * a.B;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const bool on = (cm >> i) & 1u;
+                                gv[i] = on ? acc[i] : 0.f;
+                                if (emit && on) atomicAdd(gAp + (size_t)i * a.B, gv[i]);
+                            }
+#pragma unroll
+                            for (int q4 = 0; q4 < DP / 4; ++q4) {
+                                if (4 * q4 < j) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 w4 = *reinterpret_cast<const float4*>(W0t + (size_t)(c.r0 + i) * DP + 4 * q4);
+                                        yb[4 * q4] = fmaf(w4.x, gv[i], yb[4 * q4]);
+                                        yb[4 * q4 + 1] = fmaf(w4.y, gv[i], yb[4 * q4 + 1]);
+                                        yb[4 * q4 + 2] = fmaf(w4.z, gv[i], yb[4 * q4 + 2]);
+                                        yb[4 * q4 + 3] = fmaf(w4.w, gv[i], yb[4 * q4 + 3]);
+                                    }
+                                }
+                            }
+                        }
+                        markp2 = mark2;
+                        markp1 = mark1;
+                    }
+                    wait_upto(e);
+                    if (!seq) {
 #pragma unroll
                         for (int jj = 0; jj < DP; ++jj)
                             if (jj < D) vecp[(size_t)(oG + permy[jj]) * VS] = yb[jj];
@@ -578,7 +703,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                 if (a.diff) a.diff[pidx] = logp;
             }
         }
-        wait_all();
+        wait_upto(e);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -586,8 +711,9 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
 }
 
 // ------------------------------------------------------------------------------------------------- image packing
-struct TdStrip { int dir, l, r0, nr, n0, N, off16, pad; };   // dir 0: forward (K side = layer l units, N side = layer l+1 / outputs)
-                                                             // dir 1: reverse (K side = layer l units, N side = layer l-1 units)
+struct TdStrip { int dir, l, r0, nr, n0, N, off16, zcut; };
+// dir 0: forward (K side = layer l units, N side = layer l+1 units / outputs); columns c < zcut are zeroed (own-degree FMA block)
+// dir 1: reverse (K side = layer l units, N side = layer l-1 units); columns c >= zcut are zeroed
 // one block per strip: [2 k-chunks][N][4] hi, then lo; element (n, kk) = weight between K-side unit r0 + kk and N-side column n0 + n
 __global__ void k_tcd_pack_strips(const MafImg g, int k, const TdStrip* __restrict__ strips, char* __restrict__ img) {
     const TdStrip s = strips[blockIdx.x];
@@ -602,12 +728,12 @@ __global__ void k_tcd_pack_strips(const MafImg g, int k, const TdStrip* __restri
         if (kk < s.nr) {
             const int u = s.r0 + kk, c = s.n0 + n;
             if (s.dir == 0 && s.l < 2) {           // W[l+1] is [v][u]: row = unit of layer l+1 (column c), col = unit of layer l
-                if (c < g.H[s.l + 1]) w = f[t.W[s.l + 1] + (size_t)c * t.ld[s.l + 1] + u];
+                if (c < g.H[s.l + 1] && c >= s.zcut) w = f[t.W[s.l + 1] + (size_t)c * t.ld[s.l + 1] + u];
             } else if (s.dir == 0) {               // output layer: column c = 2 * position + half; Wo rows: position j = mean, D + j = log-scale
                 const int jj = c >> 1, half = c & 1;
-                if (jj < D) w = f[t.Wo + (size_t)(half * D + jj) * t.ldo + u];
+                if (jj < D && c >= s.zcut) w = f[t.Wo + (size_t)(half * D + jj) * t.ldo + u];
             } else {                               // reverse: K side = unit of layer l (row of W[l]), N side = unit of layer l-1
-                if (c < g.H[s.l - 1]) w = f[t.W[s.l] + (size_t)u * t.ld[s.l] + c];
+                if (c < g.H[s.l - 1] && c < s.zcut) w = f[t.W[s.l] + (size_t)u * t.ld[s.l] + c];
             }
         }
         const float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
@@ -615,10 +741,11 @@ __global__ void k_tcd_pack_strips(const MafImg g, int k, const TdStrip* __restri
         lo[o] = w - h;
     }
 }
-// float part of the resident block of transform k (integer tables come from the host template)
+// float part of the resident block of transform k (integer tables come from the host template, already copied into `out`)
 __global__ void k_tcd_pack_block(const MafImg g, int k, TdBlk bk, int DP, float* __restrict__ out) {
     const TImg t = g.t[k];
     const float* f = g.f;
+    const int D = g.D;
     const int H0 = g.H[0], H1 = g.H[1], H2 = g.H[2];
     const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     for (int o = t0; o < H0 * DP; o += stride) {
@@ -631,6 +758,14 @@ __global__ void k_tcd_pack_block(const MafImg g, int k, TdBlk bk, int DP, float*
     for (int o = t0; o < H2 * 2 * DP; o += stride) {
         const int v = o / (2 * DP), c = o % (2 * DP);
         out[bk.wot + o] = c < 2 * t.ldt ? f[t.WoT + (size_t)v * 2 * t.ldt + c] : 0.f;
+    }
+    const int* dgi = reinterpret_cast<const int*>(out) + bk.dgi;
+    for (int o = t0; o < 2 * D * 64; o += stride) {
+        const int lp = o / (D * 64), j = (o >> 6) % D, i = (o >> 3) & 7, q = o & 7;
+        const int* tab = dgi + (lp * D + j) * 4;
+        float w = 0.f;
+        if (i < tab[1] && q < tab[3]) w = f[t.W[lp + 1] + (size_t)(tab[0] + i) * t.ld[lp + 1] + tab[2] + q];
+        out[(lp ? bk.dg12 : bk.dg01) + (o - lp * D * 64)] = w;
     }
 }
 
@@ -645,7 +780,7 @@ struct TdState {
     TdStrip* strip_tbl = nullptr;   // device copy, per transform contiguous
     std::vector<int> strip_off, strip_cnt;
     TdPush* push = nullptr;
-    int ps_off[RABI_MAXK][4], ps_cnt[RABI_MAXK][4];
+    int ps_off[RABI_MAXK][2], ps_cnt[RABI_MAXK][2];
     unsigned long long packed_version = ~0ull;
     float* vec = nullptr;
     uint32_t* bits = nullptr;
@@ -675,7 +810,7 @@ static int td_build(rabi_maf* h, TdState* s) {
     s->built = true;
     s->eligible = false;
     const int K = h->K, D = h->D;
-    if (h->L != 3 || D > 32 || 2 * D > 64) return 0;
+    if (h->L != 3 || D > 32 || D < 2) return 0;
     for (int l = 0; l < 3; ++l)
         if (h->H[l] > TD_MAXH) return 0;
     const std::vector<int>& M = h->meta_host;
@@ -683,6 +818,7 @@ static int td_build(rabi_maf* h, TdState* s) {
     const int DP = td_r4(D);
     s->DP = DP;
     const int H0 = h->H[0], H1 = h->H[1], H2 = h->H[2];
+    const bool use_diag = rabi_env_int("RABI_TCD_DIAG", 1) != 0;
     // resident block layout
     {
         TdBlk& b = s->blk;
@@ -692,16 +828,20 @@ static int td_build(rabi_maf* h, TdState* s) {
             o += (n + 3) & ~3;
             return at;
         };
-        b.w0t = take(H0 * DP);
-        b.b1 = take(TD_MAXH);
-        b.b2 = take(TD_MAXH);
+        // 8 zero rows of slack behind every per-unit array: a piece always touches 8 unit slots
+        b.w0t = take((H0 + 8) * DP);
+        b.b1 = take(TD_MAXH + 8);
+        b.b2 = take(TD_MAXH + 8);
         b.bo = take(2 * DP);
-        b.wot = take(H2 * 2 * DP);
+        b.wot = take((H2 + 8) * 2 * DP);
+        b.dg01 = take(D * 64);
+        b.dg12 = take(D * 64);
         b.perm = take(DP);
         b.permy = take(DP);
         b.np = take(4);
         b.pstart = take(3 * (D + 1));
         b.pieces = take(3 * TD_MAXP * 4);
+        b.dgi = take(2 * D * 4);
         b.words = (o + 31) & ~31;
     }
     std::vector<float> blocks((size_t)K * s->blk.words, 0.f);
@@ -732,20 +872,32 @@ static int td_build(rabi_maf* h, TdState* s) {
                     c.r0 = grp[l][j] + o;
                     c.nr = std::min(8, len - o);
                     c.j = j;
-                    c.flags = (o + 8 >= len) ? 1 : 0;
+                    c.flags = 0;
                     pc[l].push_back(c);
                 }
             }
             ps[l][D] = (int)pc[l].size();
             if ((int)pc[l].size() > TD_MAXP) return 0;
-            w[s->blk.np + l] = (int)pc[l].size();
-            for (int j = 0; j <= D; ++j) w[s->blk.pstart + l * (D + 1) + j] = ps[l][j];
-            memcpy(w + s->blk.pieces + l * TD_MAXP * 4, pc[l].data(), pc[l].size() * sizeof(TdPiece));
         }
-        // strips: forward (layer l piece -> layer l+1 / outputs), reverse (layer l piece -> layer l-1), l = 2, 1
+        // own-degree blocks: when group j is a single piece in layer l and in layer l + 1, their product is an FMA block on
+        // the values the thread still holds, and the strips leave it out -- no push has to complete inside a step
+        bool dg[2][32];
+        for (int lp = 0; lp < 2; ++lp)
+            for (int j = 0; j < D; ++j) {
+                dg[lp][j] = use_diag && ps[lp][j + 1] - ps[lp][j] == 1 && ps[lp + 1][j + 1] - ps[lp + 1][j] == 1;
+                int* tab = w + s->blk.dgi + (lp * D + j) * 4;
+                tab[0] = grp[lp + 1][j];
+                tab[1] = dg[lp][j] ? grp[lp + 1][j + 1] - grp[lp + 1][j] : 0;
+                tab[2] = grp[lp][j];
+                tab[3] = dg[lp][j] ? grp[lp][j + 1] - grp[lp][j] : 0;
+                if (dg[lp][j]) {
+                    pc[lp][ps[lp][j]].flags |= TD_F_DGN;
+                    pc[lp + 1][ps[lp + 1][j]].flags |= TD_F_DGP;
+                }
+            }
+        // strips + push streams.  Forward stream: per step j the pieces of layer 0, 1, 2; reverse: j descending, layer 2, 1.
         s->strip_off[k] = (int)strips.size();
-        std::vector<int> fidx[3], ridx[3];
-        auto add_strip = [&](int dir, int l, const TdPiece& c, int n0, int N) {
+        auto add_strip = [&](int dir, int l, const TdPiece& c, int n0, int N, int zcut) {
             TdStrip st;
             st.dir = dir;
             st.l = l;
@@ -754,67 +906,70 @@ static int td_build(rabi_maf* h, TdState* s) {
             st.n0 = n0;
             st.N = N;
             st.off16 = (int)(img_bytes / 16);
-            st.pad = 0;
+            st.zcut = zcut;
             img_bytes += (size_t)2 * 2 * N * 16;
             img_bytes = (img_bytes + 127) & ~(size_t)127;
             strips.push_back(st);
             return (int)strips.size() - 1;
         };
-        const uint32_t region[3] = {TD_R0, TD_R1, TD_R2};
-        for (int l = 0; l < 3; ++l)
-            for (const TdPiece& c : pc[l]) {
-                int n0, N;
-                if (l < 2) {
-                    n0 = grp[l + 1][c.j] & ~7;
-                    N = td_r8(Hl[l + 1]) - n0;
-                } else {
-                    n0 = (2 * c.j) & ~7;
-                    N = td_r8(2 * D) - n0;
-                }
-                fidx[l].push_back(add_strip(0, l, c, n0, N));
-            }
-        for (int l = 2; l >= 1; --l)
-            for (const TdPiece& c : pc[l]) ridx[l].push_back(add_strip(1, l, c, 0, std::min(td_r8(Hl[l - 1]), td_r8(grp[l - 1][c.j + 1]))));
-        s->strip_cnt[k] = (int)strips.size() - s->strip_off[k];
-        auto emit = [&](int si, uint32_t reg) {
+        const int region[3] = {TD_R0, TD_R1, TD_R2};
+        int bad = 0;
+        auto emit = [&](int si, int reg, bool first) {
             const TdStrip& st = strips[si];
             TdPush p;
             p.off16 = st.off16;
             p.bytes = 2 * 2 * st.N * 16;
-            p.dcol = (int)reg + st.n0;
+            p.dcol = (reg + st.n0) | (first ? (1 << 16) : 0);
             p.N = st.N;
-            if (p.bytes > TD_SLOT) return 1;
+            if (p.bytes > TD_SLOT || st.N < 8 || st.N > 256) bad = 1;
             pushes.push_back(p);
-            return 0;
         };
-        int bad = 0;
-        // FS: sequential forward
         s->ps_off[k][0] = (int)pushes.size();
-        for (int j = 0; j < D; ++j) {
-            for (int pi = ps[0][j]; pi < ps[0][j + 1]; ++pi) bad |= emit(fidx[0][pi], region[0]);
-            for (int pi = ps[1][j]; pi < ps[1][j + 1]; ++pi) bad |= emit(fidx[1][pi], region[1]);
-            if (j + 1 < D)
-                for (int pi = ps[2][j]; pi < ps[2][j + 1]; ++pi) bad |= emit(fidx[2][pi], region[2]);
-        }
+        bool firstF[3] = {true, true, true};
+        for (int j = 0; j < D; ++j)
+            for (int l = 0; l < 3; ++l)
+                for (int pi = ps[l][j]; pi < ps[l][j + 1]; ++pi) {
+                    TdPiece& c = pc[l][pi];
+                    int n0, N, zcut, real_end;
+                    if (l < 2) {
+                        zcut = dg[l][j] ? grp[l + 1][j + 1] : 0;
+                        n0 = (dg[l][j] ? grp[l + 1][j + 1] : grp[l + 1][j]) & ~7;
+                        N = td_r8(Hl[l + 1]) - n0;
+                        real_end = Hl[l + 1];
+                    } else {   // own position by FMA
+                        zcut = 2 * (j + 1);
+                        n0 = zcut & ~7;
+                        N = td_r8(2 * D) - n0;
+                        real_end = 2 * D;
+                    }
+                    if (N <= 0 || std::max(zcut, n0) >= real_end) continue;   // nothing left to push into
+                    c.flags |= TD_F_FWD;
+                    emit(add_strip(0, l, c, n0, N, zcut), region[l], firstF[l]);
+                    firstF[l] = false;
+                }
         s->ps_cnt[k][0] = (int)pushes.size() - s->ps_off[k][0];
-        // FF: full forward
         s->ps_off[k][1] = (int)pushes.size();
-        for (int l = 0; l < 3; ++l)
-            for (size_t pi = 0; pi < pc[l].size(); ++pi) bad |= emit(fidx[l][pi], region[l]);
+        bool firstR[3] = {true, true, true};
+        for (int j = D - 1; j >= 0; --j)
+            for (int l = 2; l >= 1; --l)
+                for (int pi = ps[l][j + 1] - 1; pi >= ps[l][j]; --pi) {
+                    TdPiece& c = pc[l][pi];
+                    const bool d = dg[l - 1][j];
+                    const int zcut = d ? grp[l - 1][j] : (1 << 30);
+                    const int N = td_r8(d ? grp[l - 1][j] : grp[l - 1][j + 1]);
+                    if (N <= 0) continue;
+                    c.flags |= TD_F_REV;
+                    emit(add_strip(1, l, c, 0, N, zcut), l == 2 ? TD_R0 : TD_R1, firstR[l]);
+                    firstR[l] = false;
+                }
         s->ps_cnt[k][1] = (int)pushes.size() - s->ps_off[k][1];
-        // BF: full reverse (descending pieces: the first push covers every column)
-        s->ps_off[k][2] = (int)pushes.size();
-        for (int l = 2; l >= 1; --l)
-            for (int pi = (int)pc[l].size() - 1; pi >= 0; --pi) bad |= emit(ridx[l][pi], l == 2 ? TD_R0 : TD_R1);
-        s->ps_cnt[k][2] = (int)pushes.size() - s->ps_off[k][2];
-        // BS: sequential reverse
-        s->ps_off[k][3] = (int)pushes.size();
-        for (int j = D - 1; j >= 0; --j) {
-            for (int pi = ps[2][j + 1] - 1; pi >= ps[2][j]; --pi) bad |= emit(ridx[2][pi], TD_R0);
-            for (int pi = ps[1][j + 1] - 1; pi >= ps[1][j]; --pi) bad |= emit(ridx[1][pi], TD_R1);
-        }
-        s->ps_cnt[k][3] = (int)pushes.size() - s->ps_off[k][3];
+        s->strip_cnt[k] = (int)strips.size() - s->strip_off[k];
         if (bad) return 0;
+        for (int l = 0; l < 3; ++l) {
+            w[s->blk.np + l] = (int)pc[l].size();
+            for (int j = 0; j <= D; ++j) w[s->blk.pstart + l * (D + 1) + j] = ps[l][j];
+            memcpy(w + s->blk.pieces + l * TD_MAXP * 4, pc[l].data(), pc[l].size() * sizeof(TdPiece));
+        }
     }
     td_free(s);
     s->blocks_words = blocks.size();

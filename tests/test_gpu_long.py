@@ -1,0 +1,129 @@
+"""Long-horizon L2-PGD parity at the BENCHED configuration (run on the B200 with ``-m gpu``).
+
+Fixtures ``tests/golden/long_*.pt`` hold the UNMODIFIED reference's x + delta_t at checkpoints of one real chunk
+(lotka_volterra shapes: 1000 rows, 200 iterations, S = 5; pyloric shapes: 200 rows, 50 iterations) and its final S = 256
+reverse KL (oracle/gen_golden_long.py; inputs and base noise are regenerated from seeds and checked against stored checksums).
+
+Two statements are tested:
+ 1. SINGLE STEP: from the reference's own state delta_t, one product PGD step reproduces the reference's delta_{t+1} to 1e-5
+    relative in EVERY row -- except rows for which an fp64 run of the oracle shows a ReLU pre-activation within a few fp32
+    ulps of zero in exactly that gradient evaluation (tests/util.py::relu_margins).  There a correct fp32 implementation with
+    another summation order may land on the other side of the kink; such a row is exempt only with that proof.
+ 2. FREE RUNNING: the product's own 200-step (50-step) trajectory against the reference's, per checkpoint: the per-row
+    divergence is printed; rows never exposed to a proven near-kink event must... (see the assertions), and the attack result
+    (S = 256 reverse KL of the final perturbation) agrees in distribution.
+"""
+import pytest
+import torch
+
+from tests.util import TAU, build_oracle, build_product, load_golden, relu_margins, row_rel_err
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-5   # one PGD step from the same state
+TRAJ_TOL = 1e-4   # north_star: PGD perturbations within 1e-4 relative
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module", params=["long_lotka_volterra", "long_pyloric"])
+def long_case(request, dev):
+    from oracle.gen_golden_long import S_ATT, S_EVAL, make_inputs, step_noise
+
+    g = load_golden(request.param)
+    cfg = g["cfg"]
+    mean, std, x, d0, eps, cmin, cmax = make_inputs(cfg)
+    assert float(x.double().sum()) == g["x_checksum"] and float(d0.double().sum()) == g["delta0_checksum"], \
+        "the CPU generator no longer reproduces the fixture's inputs: regenerate tests/golden/long_*.pt"
+    B, D, nb = cfg["B"], cfg["D"], cfg["nb_iter"]
+    zs = [step_noise(t, S_ATT, B, D) for t in range(nb)]
+    assert [float(z.double().sum()) for z in zs] == g["noise_checksums"], "base noise differs from the fixture's"
+    z_eval = step_noise(-1, S_EVAL, B, D)
+    assert float(z_eval.double().sum()) == g["z_eval_checksum"]
+    return dict(name=request.param, g=g, cfg=cfg, x=x, d0=d0, zs=zs, z_eval=z_eval, model=build_product(g, dev),
+                oracle=build_oracle(g))
+
+
+def _attack(c, nb_iter):
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+
+    p = c["g"]["pgd"]
+    return L2PGDAttack(c["model"], loss_fn=ReverseKLLoss(mc_samples=p["S"]), eps=p["eps"], nb_iter=nb_iter,
+                       eps_iter=p["eps_iter"], clip_min=p["clip_min"], clip_max=p["clip_max"])
+
+
+def test_single_step_from_reference_states_with_flip_proofs(long_case, dev):
+    from rabi_b200 import noise
+
+    c = long_case
+    g, x, keep = c["g"], c["x"], c["cfg"]["keep"]
+    cps = sorted(g["x_adv"])
+    pairs = [t for t in cps if t + 1 in g["x_adv"]]
+    assert pairs
+    xd = x.to(dev)
+    n_exempt = n_rows = 0
+    for t in pairs:
+        delta_t = torch.zeros_like(x)
+        delta_t[:keep] = g["x_adv"][t] - x[:keep]          # rows >= keep are filler (rows are independent; B fixes 1/B)
+        with noise.injected([c["zs"][t]]):
+            xa = _attack(c, 1).perturb(xd, delta_init=delta_t.to(dev))
+        err = row_rel_err(xa.cpu()[:keep] - x[:keep], g["x_adv"][t + 1] - x[:keep])
+        margin = relu_margins(c["oracle"], g["x_adv"][t], x[:keep], c["zs"][t][:, :keep])
+        prone = margin < TAU
+        dev_rows = err > STEP_TOL
+        unproven = dev_rows & ~prone
+        print(f"\n[{c['name']}] step {t}->{t + 1}: rows {keep}, median err {float(err.median()):.2e}, "
+              f"max err on rows without a near-kink {float(err[~prone].max()):.2e}, deviating rows {int(dev_rows.sum())} "
+              f"(all with margin < {TAU:g}: {not bool(unproven.any())}; smallest margin among them "
+              f"{float(margin[dev_rows].max()) if dev_rows.any() else float('nan'):.2e}), near-kink rows {int(prone.sum())}")
+        assert not bool(unproven.any()), \
+            f"rows {unproven.nonzero().flatten().tolist()} deviate by {err[unproven].tolist()} with margins {margin[unproven].tolist()}"
+        n_exempt += int(dev_rows.sum())
+        n_rows += keep
+    # the exemption is a proven fraction, with no floor
+    assert n_exempt <= 0.02 * n_rows, (n_exempt, n_rows)
+
+
+def test_free_running_trajectory_divergence_per_checkpoint(long_case, dev):
+    from rabi_b200 import noise
+    from rabi_b200.loss import ReverseKLLoss
+
+    c = long_case
+    g, x, keep, nb = c["g"], c["x"], c["cfg"]["keep"], c["cfg"]["nb_iter"]
+    cps = [t for t in sorted(g["x_adv"]) if t > 0]
+    xd = x.to(dev)
+    delta = c["d0"].to(dev)
+    t_now = 0
+    prone_ever = torch.zeros(keep, dtype=torch.bool)
+    rows = []
+    for t in cps:
+        # near-kink exposure of the REFERENCE trajectory is only known at the stored states; the product's own states are
+        # used for the steps in between (they agree to ~1e-6 until the first flip)
+        with noise.injected(c["zs"][t_now:t]):
+            xa = _attack(c, t - t_now).perturb(xd, delta_init=delta)
+        delta = xa - xd
+        t_now = t
+        err = row_rel_err(delta.cpu()[:keep], g["x_adv"][t] - x[:keep])
+        rows.append((t, float(err.median()), float(err.quantile(0.9)), float(err.max()), float((err > TRAJ_TOL).float().mean())))
+    print(f"\n[{c['name']}] free-running divergence vs the reference, per checkpoint (rows: {keep})")
+    print("  step   median      p90         max         frac > 1e-4")
+    for r in rows:
+        print(f"  {r[0]:4d}   {r[1]:.2e}   {r[2]:.2e}   {r[3]:.2e}   {r[4]:.3f}")
+    # attack result: S_eval = 256 reverse KL of the product's own final perturbation vs the reference's
+    with torch.no_grad(), noise.injected([c["z_eval"]]):
+        kl = ReverseKLLoss(mc_samples=g["pgd"]["S_eval"], reduction=None)(c["model"](xa), c["model"](xd)).cpu()[:keep]
+    ref = g["rkl_eval"]
+    rel_mean = abs(float(kl.mean()) - float(ref.mean())) / abs(float(ref.mean()))
+    row_dev = ((kl - ref).abs() / ref.abs().clamp_min(1e-3))
+    print(f"  final rKL (S=256): mean {float(kl.mean()):.6f} vs reference {float(ref.mean()):.6f} (rel {rel_mean:.2e}); "
+          f"per-row rel. deviation median {float(row_dev.median()):.2e}, p90 {float(row_dev.quantile(0.9)):.2e}")
+    assert float((xa - xd).norm(dim=-1).max()) <= g["pgd"]["eps"] * (1 + 1e-5)
+    # the first steps must agree everywhere except at proven near-kink rows (covered by the single-step test): typical error tiny
+    assert rows[0][1] < 1e-6 and rows[0][4] <= 0.01, rows[0]
+    assert all(r[1] < TRAJ_TOL for r in rows), "median row must stay within 1e-4 over the whole trajectory"
+    assert rel_mean < 2e-3

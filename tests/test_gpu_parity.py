@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from tests.util import (CASES, RTOL, assert_trajectories_match, build_oracle, build_product, load_golden,
-                        rel_err)
+                        pgd_near_kink_rows, rel_err, relu_margins)
+from tests.util import TAU, assert_kl_close
 
 pytestmark = pytest.mark.gpu
 
@@ -53,9 +54,7 @@ def test_reverse_kl_matches_reference(case, dev, S):
     with torch.no_grad(), noise.injected([g[f"z_rkl{S}"]]):
         kl = ReverseKLLoss(mc_samples=S, reduction=None)(model(g["x_tilde"].to(dev)), model(g["x"].to(dev)))
     ref = g[f"rkl{S}"]
-    # KL is a difference of O(10) log-densities: tolerance relative to the log-density scale
-    scale = max(float(g["rsample_log_prob"].abs().max()), float(ref.abs().max()))
-    assert float((kl.cpu() - ref).abs().max()) < RTOL * scale
+    assert_kl_close(kl, ref, g["rsample_log_prob"].abs().max(), f"{name}: rKL S={S}")
 
 
 def test_forward_kl_matches_reference(case, dev):
@@ -65,8 +64,7 @@ def test_forward_kl_matches_reference(case, dev):
     name, g, model = case
     with torch.no_grad(), noise.injected([g["z_fkl5"]]):
         kl = ForwardKLLoss(mc_samples=5, reduction=None)(model(g["x_tilde"].to(dev)), model(g["x"].to(dev)))
-    scale = max(float(g["rsample_log_prob"].abs().max()), float(g["fkl5"].abs().max()))
-    assert float((kl.cpu() - g["fkl5"]).abs().max()) < RTOL * scale
+    assert_kl_close(kl, g["fkl5"], g["rsample_log_prob"].abs().max(), f"{name}: fKL S=5")
 
 
 def test_reverse_kl_input_gradient_matches_reference(case, dev):
@@ -80,7 +78,7 @@ def test_reverse_kl_input_gradient_matches_reference(case, dev):
         zs = zs or (None, None)
         gx, kl = eng.rkl_input_grad(xt, zs[0], zs[1], q.A, g["z_rkl_grad"].to(dev), 1.0 / x.shape[0])
     assert rel_err(gx, g["rkl_grad_x"]) < RTOL
-    assert abs(float(kl.mean()) - float(g["rkl_mean"])) < RTOL * float(g["rsample_log_prob"].abs().max())
+    assert_kl_close(kl.mean(), g["rkl_mean"], g["rsample_log_prob"].abs().max(), f"{name}: mean rKL of the attack loss")
 
 
 @pytest.mark.parametrize("n_it", [1, 5, 20])
@@ -98,7 +96,10 @@ def test_l2pgd_matches_reference(case, dev, n_it):
         xa = atk.perturb(x, delta_init=p["delta0"].to(dev))
     ref = p[f"x_adv_{n_it}"]
     # compare the perturbations (x~ - x), relative to their size
-    assert_trajectories_match(xa.cpu() - g["x"], ref - g["x"], RTOL if n_it <= 5 else 5 * RTOL)
+    # a row may leave the tolerance only with the fp64 proof of a near-kink event on its trajectory
+    prone = pgd_near_kink_rows(build_oracle(g), g["x"], p["delta0"], list(p[f"z_{n_it}"]), p)
+    e = assert_trajectories_match(xa.cpu() - g["x"], ref - g["x"], RTOL, prone=prone)
+    print(f"\n[{name}] x~ after {n_it} PGD steps: max row rel. err {float(e.max()):.2e}, near-kink rows {int(prone.sum())}/{e.numel()}")
     assert float((xa.cpu() - g["x"]).norm(dim=-1).max()) <= p["eps"] * (1 + 1e-5)
     assert float(xa.min()) >= p["clip_min"] - 1e-6 and float(xa.max()) <= p["clip_max"] + 1e-6
 
@@ -157,12 +158,13 @@ def test_full_shape_pipeline_vs_oracle(shape, dev):
                       clip_min=cmin, clip_max=cmax)
     with noise.injected(zs):
         xa = atk.perturb(x.to(dev), delta_init=d0.to(dev))
-    assert_trajectories_match(xa.cpu() - x, xa_ref - x, 2 * RTOL)
+    prone = pgd_near_kink_rows(ref, x, d0, zs, dict(eps=eps, eps_iter=eps / 10, clip_min=cmin, clip_max=cmax, S=S))
+    assert_trajectories_match(xa.cpu() - x, xa_ref - x, RTOL, prone=prone)
     with torch.no_grad(), noise.injected([z_eval]):
         kl = ReverseKLLoss(mc_samples=S_eval, reduction=None)(model(xa_ref.to(dev)), model(x.to(dev)))
     with torch.no_grad():
         lp_scale = float(ref(x).log_prob(ref(x).sample()).abs().max())
-    assert float((kl.cpu() - kl_ref).abs().max()) < RTOL * max(lp_scale, float(kl_ref.abs().max()))
+    assert_kl_close(kl, kl_ref, lp_scale, f"{shape}: rKL metric S={S_eval} at full shape")
 
 
 def test_size_independent_properties_at_config2_scale(dev):
@@ -233,7 +235,8 @@ def test_forward_kl_attack_vs_oracle(shape, dev):
                       clip_min=cmin, clip_max=cmax)
     with noise.injected(zs):
         xa = atk.perturb(x.to(dev), delta_init=d0.to(dev))
-    assert_trajectories_match(xa.cpu() - x, xa_ref - x, 2 * RTOL)
+    prone = pgd_near_kink_rows(ref, x, d0, zs, dict(eps=eps, eps_iter=eps / 10, clip_min=cmin, clip_max=cmax, S=S), forward_kl=True)
+    assert_trajectories_match(xa.cpu() - x, xa_ref - x, RTOL, prone=prone)
 
 
 def test_edge_cases_empty_ragged_and_large_sample_counts(dev):
@@ -353,7 +356,8 @@ def test_l2pgd_through_a_nonidentity_embedding_vs_oracle(dev):
                       clip_min=cmin, clip_max=cmax)
     with noise.injected(zs):
         xa = atk.perturb(x.to(dev), delta_init=d0.to(dev))
-    assert_trajectories_match(xa.cpu() - x, xa_ref - x, 2 * RTOL)
+    prone = pgd_near_kink_rows(ref, x, d0, zs, dict(eps=eps, eps_iter=eps / 10, clip_min=cmin, clip_max=cmax, S=S))
+    assert_trajectories_match(xa.cpu() - x, xa_ref - x, RTOL, prone=prone)
     with torch.no_grad(), O.injected_base_noise([zs[0]]):
         kl_ref = O.ReverseKLLoss(mc_samples=S, reduction=None)(ref(xa_ref), ref(x))
     with torch.no_grad(), noise.injected([zs[0]]):
@@ -383,8 +387,7 @@ def test_deep_path_matches_reference_fixtures(case, dev, force_deep):
     launches0 = model.engine().launches
     with torch.no_grad(), noise.injected([g["z_rkl64"]]):
         kl = ReverseKLLoss(mc_samples=64, reduction=None)(model(xt), model(x))
-    scale = max(float(g["rsample_log_prob"].abs().max()), float(g["rkl64"].abs().max()))
-    assert float((kl.cpu() - g["rkl64"]).abs().max()) < RTOL * scale
+    assert_kl_close(kl, g["rkl64"], g["rsample_log_prob"].abs().max(), f"{name} (deep path): rKL S=64")
     eng = model.engine()
     with torch.no_grad():
         q = model(x)
@@ -392,13 +395,14 @@ def test_deep_path_matches_reference_fixtures(case, dev, force_deep):
         zs = zs or (None, None)
         gx, klm = eng.rkl_input_grad(xt, zs[0], zs[1], q.A, g["z_rkl_grad"].to(dev), 1.0 / x.shape[0])
     assert rel_err(gx, g["rkl_grad_x"]) < RTOL
-    assert abs(float(klm.mean()) - float(g["rkl_mean"])) < RTOL * float(g["rsample_log_prob"].abs().max())
+    assert_kl_close(klm.mean(), g["rkl_mean"], g["rsample_log_prob"].abs().max(), f"{name} (deep path): mean rKL")
     p = g["pgd"]
     atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=p["S"]), eps=p["eps"], nb_iter=5, eps_iter=p["eps_iter"],
                       clip_min=p["clip_min"], clip_max=p["clip_max"])
     with noise.injected(list(p["z_5"])):
         xa = atk.perturb(x, delta_init=p["delta0"].to(dev))
-    assert_trajectories_match(xa.cpu() - g["x"], p["x_adv_5"] - g["x"], RTOL)
+    prone = pgd_near_kink_rows(build_oracle(g), g["x"], p["delta0"], list(p["z_5"]), p)
+    assert_trajectories_match(xa.cpu() - g["x"], p["x_adv_5"] - g["x"], RTOL, prone=prone)
     assert model.engine().launches > launches0
     # the single-chain modes: density of given theta, sampling (+ free log-density)
     with torch.no_grad():
@@ -438,7 +442,7 @@ def test_deep_path_equals_generic_kernel_across_batches(dev):
     (kl_d, gx_d, klm_d), (kl_g, gx_g, klm_g) = outs
     assert float((kl_d - kl_g).abs().max()) < 1e-5 * max(1.0, float(kl_g.abs().max()) * 10)
     assert float((klm_d - klm_g).abs().max()) < 1e-5 * max(1.0, float(klm_g.abs().max()) * 10)
-    assert_trajectories_match(gx_d, gx_g, 1e-4)
+    assert_trajectories_match(gx_d, gx_g, 1e-4, prone=relu_margins(ref, x + 0.05, x, z.cpu()) < TAU)
 
 
 def test_size_independent_properties_at_config5_scale(dev):
@@ -506,9 +510,10 @@ def test_warp_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
                     for k in env:
                         os.environ.pop(k, None)
                 outs.append((gx, kl))
+            prone = (relu_margins(ref, x, x + 0.05, z.cpu()) if fkl else relu_margins(ref, x + 0.05, x, z.cpu())) < TAU
             for gx, kl in outs[1:]:
                 assert float((kl - outs[0][1]).abs().max()) < 1e-5 * lp_scale
-                assert_trajectories_match(gx, outs[0][0], 1e-4)
+                assert_trajectories_match(gx, outs[0][0], 1e-4, prone=prone)
 
 
 @pytest.mark.parametrize("shape", [dict(dx=100, D=4, hidden=[100, 100], B=301), dict(dx=100, D=4, hidden=[100, 100], B=2000),
@@ -543,9 +548,10 @@ def test_two_lanes_per_pair_kernel_equals_thread_per_pair_kernels(shape, dev):
                     for k in env:
                         os.environ.pop(k, None)
                 outs.append((gx, kl))
+            prone = relu_margins(ref, x + 0.05, x, z.cpu()) < TAU
             for gx, kl in outs[1:]:
                 assert float((kl - outs[0][1]).abs().max()) < 1e-5 * lp_scale
-                assert_trajectories_match(gx, outs[0][0], 1e-4)
+                assert_trajectories_match(gx, outs[0][0], 1e-4, prone=prone)
 
 
 @pytest.mark.parametrize("shape", [dict(dx=20, D=31, hidden=[64, 64, 64], B=45), dict(dx=12, D=9, hidden=[40, 36, 44], B=130),
@@ -588,5 +594,5 @@ def test_three_layer_tensor_core_kernel_equals_fma_paths(shape, dev):
             assert float((b[7] - a[7]).abs().max()) < 1e-5 * lp_scale, "log_prob"
             assert float((b[0] - a[0]).abs().max()) < 1e-5 * lp_scale, "metric"
             assert float((b[2] - a[2]).abs().max()) < 1e-5 * lp_scale and float((b[4] - a[4]).abs().max()) < 1e-5 * lp_scale
-            assert_trajectories_match(b[1], a[1], 1e-4)
-            assert_trajectories_match(b[3], a[3], 1e-4)
+            assert_trajectories_match(b[1], a[1], 1e-4, prone=relu_margins(ref, x + 0.05, x, z.cpu()) < TAU)
+            assert_trajectories_match(b[3], a[3], 1e-4, prone=relu_margins(ref, x, x + 0.05, z.cpu()) < TAU)
