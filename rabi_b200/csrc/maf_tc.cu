@@ -82,9 +82,22 @@ struct TcArgs {
     const float* img;    // [K][2][blk_words]
     TcBlk blk[2];
     int blk_words;
+    int region_words;    // shared-memory words in front of the per-pair region (>= the largest block; RUN: also the context weights)
     uint32_t* bits;      // [2K][2][TC_MAXP][bits_stride] relu masks, one word per piece
     int bits_stride;
     int VS;
+    // ---- persistent attack (template RUN): a CTA owns blocks of R observation rows with all their S samples for all
+    // nb_iter L2-PGD iterations; projection, gradient back-projection and the PGD update run inside the kernel
+    const float* x;       // [B][C]
+    float* delta;         // [B][C] in: delta_0, out: delta_nb_iter
+    const float* zmean;   // [C] or null
+    const float* zstd;
+    int nb_iter, R, RP, nblocks;   // R rows per block (multiple of 4), RP = shared-memory row stride (round8(R) + 4)
+    float eps, eps_iter, cmin, cmax, floor_;
+    long long zstride;    // floats between the base noise of consecutive iterations (S * B * D)
+    int vec_words;        // words of the per-pair region (the tail's tiles live there between the flow phases)
+    int xs_off;           // word offset of Xs inside it; the partial gradient tiles of the thread groups lie in front
+    long long* dbg;       // optional [16] cycle counters of CTA 0 (RABI_TC_RUN_DBG=1): where an iteration's time goes
 };
 
 // ------------------------------------------------------------------------------------------------- device helpers
@@ -154,13 +167,14 @@ __device__ __forceinline__ void tc_stage4(uint32_t trow, int q, const float (&v)
 }
 
 // ------------------------------------------------------------------------------------------------- the kernel
-template <int MODE, int DP>
+template <int MODE, int DP, bool RUN>
 __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, const TcArgs a) {
     extern __shared__ __align__(128) float sm[];
     constexpr bool GRADM = MODE == TC_GRAD || MODE == TC_FKL;
+    static_assert(!RUN || GRADM, "the persistent attack exists for the two attack losses only");
     float* Wb = sm;                                   // the resident (transform, orientation) block
     const int* Wi = reinterpret_cast<const int*>(sm);
-    float* vec = sm + a.blk_words;                    // [threads][VS]
+    float* vec = sm + a.region_words;                 // [threads][VS]
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t mbar[TC_MAXTILES + 1];   // one per tile (MMA completion) + the block loader
     const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2, lane128 = tid & 127;
@@ -237,19 +251,154 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
 
-    const int rounds = (a.ntiles + (int)gridDim.x * NT - 1) / ((int)gridDim.x * NT);
-    for (int round = 0; round < rounds; ++round) {
-        const int tile = (round * NT + wg) * (int)gridDim.x + (int)blockIdx.x;
-        const bool tile_live = tile < a.ntiles;
-        const long long p = (long long)tile * 128 + lane128;
-        const bool live = tile_live && p < a.npairs;
-        const long long pidx = live ? p : 0;
-        const int b = (int)(pidx % a.B);
+    // generic smem <- global bulk copies into the block region (same mbarrier protocol as ensure_block)
+    auto bulk_expect = [&](uint32_t bytes) {
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc_smem_u32(&mbar[TC_MAXTILES])), "r"(bytes) : "memory");
+    };
+    auto bulk_piece = [&](uint32_t dst_off, const void* srcp, uint32_t bytes) {
+        if (tid == 0) {
+            const char* src = reinterpret_cast<const char*>(srcp);
+            for (uint32_t off = 0; off < bytes; off += 32768u) {
+                const uint32_t n = min(bytes - off, 32768u);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(tc_smem_u32(sm) + dst_off + off), "l"(src + off), "r"(n), "r"(tc_smem_u32(&mbar[TC_MAXTILES])) : "memory");
+            }
+        }
+    };
+    auto bulk_wait = [&]() {
+        tc_mbar_wait(&mbar[TC_MAXTILES], wphase);
+        wphase ^= 1u;
+    };
+    // RUN: geometry of the in-kernel projection products (8 rows x 8 outputs per thread, packed FMAs, operands in shared memory)
+    const int C = g.C;
+    const int RP = RUN ? a.RP : 0;                   // row stride of the staged tiles: RT + 4, so that column walks spread over 8 banks
+    const int RT = RP - 4;                           // rows covered by the 8-row tiles (rows >= nr are zero)
+    float* Xs = vec + a.xs_off;                      // [C][RP]    z-scored x + delta of the block's rows, transposed (behind the gradient tiles)
+    float* Xn = Xs;
+    float* Gs = vec;                                 // [K H0][RP] cotangents d/dA of the block's rows; then up to G partial
+                                                     //            gradient tiles [G][C][RP] of the thread groups
+    float* pertA = const_cast<float*>(MODE == TC_GRAD ? a.A_p : a.A_q);   // the projection that follows delta
+    const int nwarps = (int)(blockDim.x >> 5), lane = tid & 31;
+    auto load_ctx_weights = [&]() {                  // W0cT [C][ldKH] of all transforms -> weight region
+        const uint32_t wbytes = (uint32_t)C * (uint32_t)g.ldKH * 4u;
+        bulk_expect(wbytes);
+        bulk_piece(0u, g.f + g.W0cT, wbytes);
+    };
+
+    long long tmark = 0;
+    auto mark = [&](int slot) {
+        if (RUN && a.dbg && blockIdx.x == 0 && tid == 0) {
+            const long long now = clock64();
+            if (slot >= 0) a.dbg[slot] += now - tmark;
+            tmark = now;
+        }
+    };
+
+    const int rounds = RUN ? a.nblocks : (a.ntiles + (int)gridDim.x * NT - 1) / ((int)gridDim.x * NT);
+    for (int round = RUN ? (int)blockIdx.x : 0; round < rounds; round += RUN ? (int)gridDim.x : 1) {
+        // ---- which pair this thread owns
+        bool tile_live, live;
+        long long pidx;
+        int b, b0 = 0, nr = 0;
+        if constexpr (RUN) {
+            b0 = round * a.R;
+            nr = min(a.R, a.B - b0);
+            const int lp = wg * 128 + lane128;       // local pair: sample-major over the block's rows
+            const int sidx = lp / nr, rr = lp - sidx * nr;
+            tile_live = wg * 128 < a.S * nr;
+            live = sidx < a.S;
+            b = b0 + (live ? rr : 0);
+            pidx = (long long)(live ? sidx : 0) * a.B + b;
+        } else {
+            const int tile = (round * NT + wg) * (int)gridDim.x + (int)blockIdx.x;
+            tile_live = tile < a.ntiles;
+            const long long p = (long long)tile * 128 + lane128;
+            live = tile_live && p < a.npairs;
+            pidx = live ? p : 0;
+            b = (int)(pidx % a.B);
+        }
+        if constexpr (RUN) {   // Xs <- ((x + delta_0) - mean) / std, rows of the block (lanes walk the context dimension)
+            __syncthreads();
+            resident = -1;
+            load_ctx_weights();
+            for (int r = warp; r < RT; r += nwarps) {
+                const bool in = r < nr;
+                for (int c = lane; c < C; c += 32) {
+                    float v = 0.f;
+                    if (in) {
+                        v = a.x[(size_t)(b0 + r) * C + c] + a.delta[(size_t)(b0 + r) * C + c];
+                        if (a.zmean) v = (v - a.zmean[c]) / a.zstd[c];
+                    }
+                    Xs[c * RP + r] = v;
+                }
+            }
+        }
+      for (int it = 0; it < (RUN ? a.nb_iter : 1); ++it) {
+        if constexpr (RUN) {
+            // ================= projection of the block's rows: A[k,u,b] = b0_k[u] + sum_c W0_k[u,c] ctx[b,c] =================
+            mark(-1);
+            __syncthreads();                          // Xs complete
+            bulk_wait();
+            mark(0);                              // context weights (issued before the update / the first Xs)
+            const int ldw = g.ldKH, ncol = K * g.H0p, NG = (ncol + 7) >> 3, RG = RT >> 3;
+            for (int t = tid; t < NG * RG; t += (int)blockDim.x) {
+                const int rg = t % RG, ug = t / RG;
+                float2 acc[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 2
+                for (int c = 0; c < C; ++c) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(Xs + c * RP + 8 * rg);
+                    const float4 x1 = *reinterpret_cast<const float4*>(Xs + c * RP + 8 * rg + 4);
+                    const float4 w0 = *reinterpret_cast<const float4*>(Wb + c * ldw + 8 * ug);
+                    const float4 w1 = *reinterpret_cast<const float4*>(Wb + c * ldw + 8 * ug + 4);
+                    const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 xx = make_float2(xr[i], xr[i]);
+                        acc[i][0] = tc_ffma2(make_float2(w0.x, w0.y), xx, acc[i][0]);
+                        acc[i][1] = tc_ffma2(make_float2(w0.z, w0.w), xx, acc[i][1]);
+                        acc[i][2] = tc_ffma2(make_float2(w1.x, w1.y), xx, acc[i][2]);
+                        acc[i][3] = tc_ffma2(make_float2(w1.z, w1.w), xx, acc[i][3]);
+                    }
+                }
+                const bool vec4 = (a.B & 3) == 0;     // b0 is a multiple of 4
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = 8 * ug + j;
+                    if (col >= ncol) continue;
+                    const int kk = col / g.H0p, u = col - kk * g.H0p;
+                    if (u >= H0) continue;
+                    const float bias = __ldg(g.f + g.t[kk].b0 + u);
+                    float* out = pertA + ((size_t)kk * H0 + u) * a.B + b0 + 8 * rg;
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = bias + ((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x);
+#pragma unroll
+                    for (int h4 = 0; h4 < 2; ++h4) {
+                        const int r0 = 8 * rg + 4 * h4;
+                        if (vec4 && r0 + 3 < nr) {
+                            __stcg(reinterpret_cast<float4*>(out + 4 * h4), make_float4(o[4 * h4], o[4 * h4 + 1], o[4 * h4 + 2], o[4 * h4 + 3]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (r0 + i < nr) __stcg(out + 4 * h4 + i, o[4 * h4 + i]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();                          // the projection is visible to the block; Xs and the weights are dead
+            mark(1);
+        }
+        const float* zit = a.z + (RUN ? (size_t)it * (size_t)a.zstride : (size_t)0);
         float logp = 0.f, logq = 0.f;
         if (tile_live) {
             float ssq = 0.f;
             for (int d = 0; d < D; ++d) {
-                const float zv = live ? a.z[(size_t)pidx * D + d] : 0.f;
+                const float zv = live ? zit[(size_t)pidx * D + d] : 0.f;
                 vecp[oV + (MODE == TC_LOGPROB ? K * D : 0) + d] = zv;
                 ssq = fmaf(zv, zv, ssq);
             }
@@ -262,8 +411,13 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             const int k = (kind == 0 || kind == 2) ? idx : K - 1 - idx;
             const bool seq = (kind == 0 || kind == 3);
             const int ori = kind < 2 ? 0 : 1;
+            mark(-1);
             ensure_block(k, ori);
-            if (!tile_live) continue;
+            mark(8);
+            if (!tile_live) {
+                mark(9 + kind);
+                continue;
+            }
             const TcBlk& bk = a.blk[ori];
             const float* W0t = Wb + bk.w0t;
             const float* b1 = Wb + bk.b1;
@@ -284,6 +438,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             if (kind < 2) {
                 // ===================== forward pass of transform k =====================
                 const float* Abase = (seq ? a.A_p : a.A_q) + (size_t)k * H0 * a.B + b;
+                const bool rewritten = RUN && (MODE == TC_GRAD ? seq : !seq);   // this projection follows delta: no read-only path
                 float zos[DP], y[DP];
                 float2 oms[DP];
 #pragma unroll
@@ -298,7 +453,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                     const float* ap = Abase + (size_t)c0.r0 * a.B;
 #pragma unroll
                     for (int i = 0; i < TC_KC; ++i) {
-                        an[i] = i < c0.nr ? __ldg(ap) : 0.f;
+                        an[i] = i < c0.nr ? (rewritten ? __ldcg(ap) : __ldg(ap)) : 0.f;
                         ap += a.B;
                     }
                 }
@@ -312,7 +467,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                         const float* ap = Abase + (size_t)cn.r0 * a.B;
 #pragma unroll
                         for (int i = 0; i < TC_KC; ++i) {
-                            an[i] = i < cn.nr ? __ldg(ap) : 0.f;
+                            an[i] = i < cn.nr ? (rewritten ? __ldcg(ap) : __ldg(ap)) : 0.f;
                             ap += a.B;
                         }
                     }
@@ -536,11 +691,197 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                         else vecp[oG + permy[jj]] = yb[jj];
                     }
             }
+            mark(9 + kind);
         }
         if (MODE == TC_RSAMPLE && live) {
             for (int d = 0; d < D; ++d) a.theta_out[(size_t)pidx * D + d] = vecp[oV + K * D + d];
             if (a.diff) a.diff[pidx] = logp;
         }
+        if constexpr (RUN) {
+            // ================= input gradient of the block's rows: gx[b,c] = (1/std[c]) sum_{k,u} W0_k[u,c] gA[k,u,b] =================
+            __threadfence();                          // this thread's reductions into gA are performed before the block reads them
+            __syncthreads();
+            mark(2);
+            resident = -1;
+            const int ldc = g.t[0].ldc, KH = K * H0;  // the K context blocks [H0][ldc] land back to back: row kk * H0 + u
+            {
+                const uint32_t nbytes = (uint32_t)H0 * (uint32_t)ldc * 4u;
+                bulk_expect(nbytes * (uint32_t)K);
+                for (int kk = 0; kk < K; ++kk) bulk_piece(nbytes * (uint32_t)kk, g.f + g.t[kk].W0c, nbytes);
+            }
+            // cotangents of the block's rows -> Gs (24 loads in flight per thread); the slab is zeroed for the next iteration
+            {
+                const int n = KH * RP, T = (int)blockDim.x;
+                for (int base = tid; base < n; base += 24 * T) {
+                    float v[24];
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) {
+                        const int idx = base + i * T;
+                        const int j = idx / RP, r = idx - j * RP;
+                        v[i] = (idx < n && r < nr) ? __ldcg(a.gA + (size_t)j * a.B + b0 + r) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) {
+                        const int idx = base + i * T;
+                        if (idx < n) {
+                            const int j = idx / RP, r = idx - j * RP;
+                            Gs[idx] = v[i];
+                            if (r < nr) __stcg(a.gA + (size_t)j * a.B + b0 + r, 0.f);
+                        }
+                    }
+                }
+            }
+            bulk_wait();
+            __syncthreads();
+            mark(3);
+            // (8 rows x 8 columns) tiles; the thread groups split the K H0 reduction rows among them
+            const int RG = RT >> 3, NGC = (C + 7) >> 3, ntile = RG * NGC;
+            const int G = max(1, min((int)blockDim.x / ntile, KH));
+            const int grp = tid / ntile, tile = tid - grp * ntile;
+            const bool worker = grp < G;
+            const int cg = tile % NGC, rg = tile / NGC;   // lanes walk the columns: broadcast cotangent loads, 2-way tile stores
+            float2 acc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+            if (worker) {
+                const int j0 = (int)((long long)KH * grp / G), j1 = (int)((long long)KH * (grp + 1) / G);
+#pragma unroll 2
+                for (int j = j0; j < j1; ++j) {
+                    const float4 g0 = *reinterpret_cast<const float4*>(Gs + j * RP + 8 * rg);
+                    const float4 g1 = *reinterpret_cast<const float4*>(Gs + j * RP + 8 * rg + 4);
+                    const float4 w0 = *reinterpret_cast<const float4*>(Wb + j * ldc + 8 * cg);
+                    const float4 w1 = *reinterpret_cast<const float4*>(Wb + j * ldc + 8 * cg + 4);
+                    const float gr[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 gg = make_float2(gr[i], gr[i]);
+                        acc[i][0] = tc_ffma2(make_float2(w0.x, w0.y), gg, acc[i][0]);
+                        acc[i][1] = tc_ffma2(make_float2(w0.z, w0.w), gg, acc[i][1]);
+                        acc[i][2] = tc_ffma2(make_float2(w1.x, w1.y), gg, acc[i][2]);
+                        acc[i][3] = tc_ffma2(make_float2(w1.z, w1.w), gg, acc[i][3]);
+                    }
+                }
+            }
+            __syncthreads();                          // Gs and the context blocks are dead
+            mark(4);
+            if (it + 1 < a.nb_iter) load_ctx_weights();   // arrives while the update runs
+            // the groups add their partial sums into the row-major gradient tile Gt[row][CG] in turn (128-bit accesses)
+            const int CG = (C + 7) & ~7;
+            for (int gi = 0; gi < G; ++gi) {
+                if (worker && grp == gi) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4* o = reinterpret_cast<float4*>(vec + (size_t)(8 * rg + i) * CG + 8 * cg);
+                        float4 v0 = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+                        float4 v1 = make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y);
+                        if (gi) {
+                            const float4 p0 = o[0], p1 = o[1];
+                            v0 = make_float4(v0.x + p0.x, v0.y + p0.y, v0.z + p0.z, v0.w + p0.w);
+                            v1 = make_float4(v1.x + p1.x, v1.y + p1.y, v1.z + p1.z, v1.w + p1.w);
+                        }
+                        o[0] = v0;
+                        o[1] = v1;
+                    }
+                }
+                __syncthreads();
+            }
+            mark(5);
+            // ================= advertorch perturb_iterative(ord=2) update, one warp per row; Xs for the next projection =================
+            {
+                constexpr int NE = 4;                  // context entries per lane (C <= 128: checked by the launcher)
+                constexpr int NB = 6;                  // rows per warp handled together: their dependent chains (two warp
+                                                       // reductions, sqrt, divisions) interleave instead of running one after the other
+                float isd[NE], mu[NE];
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int c = lane + 32 * e;
+                    isd[e] = (a.zstd && c < C) ? a.zstd[c] : 1.f;
+                    mu[e] = (a.zmean && c < C) ? a.zmean[c] : 0.f;
+                }
+                for (int rb = warp; rb < RT; rb += NB * nwarps) {
+                    float xv[NB][NE], dv[NB][NE], gv[NB][NE], n2[NB], d2[NB];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        const int r = rb + q * nwarps;
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) {
+                            const int c = lane + 32 * e;
+                            const bool in = r < nr && c < C;
+                            xv[q][e] = in ? a.x[(size_t)(b0 + r) * C + c] : 0.f;
+                            dv[q][e] = in ? a.delta[(size_t)(b0 + r) * C + c] : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        const int r = rb + q * nwarps;
+                        n2[q] = 0.f;
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) {
+                            const int c = lane + 32 * e;
+                            float v = 0.f;
+                            if (r < nr && c < C) {
+                                v = vec[(size_t)r * CG + c];
+                                if (a.zstd) v /= isd[e];
+                            }
+                            gv[q][e] = v;
+                            n2[q] = fmaf(v, v, n2[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1)
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) n2[q] += __shfl_xor_sync(0xffffffffu, n2[q], o);
+                    if (n2[0] == 123.456f) Xn[0] = 1.f;
+                    mark(13);
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        const float inv = 1.f / fmaxf(sqrtf(n2[q]), a.floor_);
+                        d2[q] = 0.f;
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) {
+                            float d = dv[q][e] + (gv[q][e] * inv) * a.eps_iter;
+                            d = fminf(fmaxf(xv[q][e] + d, a.cmin), a.cmax) - xv[q][e];
+                            dv[q][e] = (lane + 32 * e < C) ? d : 0.f;
+                            d2[q] = fmaf(dv[q][e], dv[q][e], d2[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1)
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) d2[q] += __shfl_xor_sync(0xffffffffu, d2[q], o);
+                    if (d2[0] == 123.456f) Xn[0] = 1.f;
+                    mark(14);
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        const int r = rb + q * nwarps;
+                        if (r >= RT) continue;
+                        const float factor = fminf(a.eps / sqrtf(d2[q]), 1.f);
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) {
+                            const int c = lane + 32 * e;
+                            if (c < C) {
+                                float v = 0.f;
+                                if (r < nr) {
+                                    const float d = dv[q][e] * factor;
+                                    a.delta[(size_t)(b0 + r) * C + c] = d;
+                                    v = xv[q][e] + d;
+                                    if (a.zmean) v = (v - mu[e]) / isd[e];
+                                }
+                                Xn[c * RP + r] = v;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if constexpr (RUN) {
+            mark(15);
+            __syncthreads();
+            mark(6);
+        }
+      }   // iterations
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -733,12 +1074,12 @@ static int tc_build(rabi_maf* h, TcState* s) {
     return 0;
 }
 
-template <int MODE, int DP>
+template <int MODE, int DP, bool RUN>
 static int tc_launch_inst(rabi_maf* h, const TcArgs& a, int grid, int T, size_t smem, cudaStream_t st) {
-    RABI_CU_OK(h, cudaFuncSetAttribute(k_tc<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RABI_CU_OK(h, cudaFuncSetAttribute(k_tc<MODE, DP, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool prof = MODE == TC_GRAD || MODE == TC_FKL;
     if (prof && rabi_prof_begin(h, st)) return 1;
-    k_tc<MODE, DP><<<grid, T, smem, st>>>(h->img, a);
+    k_tc<MODE, DP, RUN><<<grid, T, smem, st>>>(h->img, a);
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return rabi_fail(h, "k_tc launch failed: %s", cudaGetErrorString(e));
@@ -747,27 +1088,39 @@ static int tc_launch_inst(rabi_maf* h, const TcArgs& a, int grid, int T, size_t 
 }
 
 template <int DP>
-static int tc_launch_mode(rabi_maf* h, const TcArgs& a, int mode, int grid, int T, size_t smem, cudaStream_t st) {
+static int tc_launch_mode(rabi_maf* h, const TcArgs& a, int mode, bool run, int grid, int T, size_t smem, cudaStream_t st) {
+    if (run) {
+        if (mode == TC_GRAD) return tc_launch_inst<TC_GRAD, DP, true>(h, a, grid, T, smem, st);
+        if (mode == TC_FKL) return tc_launch_inst<TC_FKL, DP, true>(h, a, grid, T, smem, st);
+        return 2;
+    }
     switch (mode) {
-        case TC_FWD: return tc_launch_inst<TC_FWD, DP>(h, a, grid, T, smem, st);
-        case TC_GRAD: return tc_launch_inst<TC_GRAD, DP>(h, a, grid, T, smem, st);
-        case TC_FKL: return tc_launch_inst<TC_FKL, DP>(h, a, grid, T, smem, st);
-        case TC_RSAMPLE: return tc_launch_inst<TC_RSAMPLE, DP>(h, a, grid, T, smem, st);
-        case TC_LOGPROB: return tc_launch_inst<TC_LOGPROB, DP>(h, a, grid, T, smem, st);
+        case TC_FWD: return tc_launch_inst<TC_FWD, DP, false>(h, a, grid, T, smem, st);
+        case TC_GRAD: return tc_launch_inst<TC_GRAD, DP, false>(h, a, grid, T, smem, st);
+        case TC_FKL: return tc_launch_inst<TC_FKL, DP, false>(h, a, grid, T, smem, st);
+        case TC_RSAMPLE: return tc_launch_inst<TC_RSAMPLE, DP, false>(h, a, grid, T, smem, st);
+        case TC_LOGPROB: return tc_launch_inst<TC_LOGPROB, DP, false>(h, a, grid, T, smem, st);
     }
     return 2;
 }
 
-int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
-    const long long npairs = (long long)c.S * c.B;
-    if (npairs <= 0) return 0;
-    if (!rabi_env_int("RABI_TC", 1)) return 2;
-    if (h->L == 3) return rabi_tcd_launch(h, c, mode, st);
+static int tc_dispatch_dp(rabi_maf* h, TcState* s, const TcArgs& a, int mode, bool run, int grid, int T, size_t smem, cudaStream_t st) {
+    switch (s->DP) {
+        case 4: return tc_launch_mode<4>(h, a, mode, run, grid, T, smem, st);
+#ifndef RABI_LEAN
+        case 8: return tc_launch_mode<8>(h, a, mode, run, grid, T, smem, st);
+        case 12: return tc_launch_mode<12>(h, a, mode, run, grid, T, smem, st);
+#endif
+    }
+    return 2;
+}
+
+// state, packed image and the mode-independent arguments; 0 = ready, 1 = error, 2 = not eligible
+static int tc_prepare(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st, TcState** out, TcArgs* ap) {
     TcState* s = static_cast<TcState*>(h->tc);
     if (!s) h->tc = s = new TcState();
     if (!s->built && tc_build(h, s)) return 1;
     if (!s->eligible) return 2;
-    if (npairs < (long long)rabi_env_int("RABI_TC_MIN_PAIRS", 1)) return 2;
     if (s->packed_version != h->weights_version) {
         // padding entries stay zero: start from the template, then write the real units
         RABI_CU_OK(h, cudaMemcpyAsync(s->img + s->img_words, s->img, s->img_words * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -779,7 +1132,7 @@ int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
         if (e != cudaSuccess) return rabi_fail(h, "k_tc_pack launch failed: %s", cudaGetErrorString(e));
         s->packed_version = h->weights_version;
     }
-    TcArgs a;
+    TcArgs& a = *ap;
     memset(&a, 0, sizeof(a));
     a.A_p = c.A_p;
     a.A_q = c.A_q;
@@ -790,24 +1143,13 @@ int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
     a.S = c.S;
     a.B = c.B;
     a.w = c.w;
-    a.npairs = npairs;
-    const long long nt = (npairs + 127) / 128;
-    if (nt > 0x7fffffff) return 2;
-    a.ntiles = (int)nt;
+    a.npairs = (long long)c.S * c.B;
     a.img = s->img + s->img_words;
     a.blk[0] = s->blk[0];
     a.blk[1] = s->blk[1];
     a.blk_words = s->blk_words;
+    a.region_words = s->blk_words;
     a.VS = ((4 * h->K + 2) * h->D) | 1;
-    // tiles per CTA: as many as the per-pair state next to the weight block allows, no more than the launch needs
-    const size_t budget = (size_t)h->max_smem_optin - 1024;
-    int NT = std::min(TC_MAXTILES, std::max(1, rabi_env_int("RABI_TC_TILES", TC_MAXTILES)));
-    while (NT > 1 && ((size_t)s->blk_words + (size_t)NT * 128 * a.VS) * 4 > budget) --NT;
-    if (((size_t)s->blk_words + (size_t)NT * 128 * a.VS) * 4 > budget) return 2;
-    const int grid = (int)std::min<long long>(nt, h->sm_count);
-    while (NT > 1 && (long long)grid * (NT - 1) >= nt) --NT;   // spread the tiles over the SMs first
-    const int T = NT * 128;
-    const size_t smem = ((size_t)s->blk_words + (size_t)T * a.VS) * 4;
     if (mode == TC_GRAD || mode == TC_FKL) {
         const size_t need = (size_t)2 * h->K * 2 * TC_MAXP * (size_t)h->sm_count * TC_MAXTILES * 128;
         if (need > s->bits_words) {
@@ -823,14 +1165,129 @@ int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
         a.bits = s->bits;
         a.bits_stride = h->sm_count * TC_MAXTILES * 128;
     }
-    switch (s->DP) {
-        case 4: return tc_launch_mode<4>(h, a, mode, grid, T, smem, st);
-#ifndef RABI_LEAN
-        case 8: return tc_launch_mode<8>(h, a, mode, grid, T, smem, st);
-        case 12: return tc_launch_mode<12>(h, a, mode, grid, T, smem, st);
-#endif
+    *out = s;
+    return 0;
+}
+
+int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
+    const long long npairs = (long long)c.S * c.B;
+    if (npairs <= 0) return 0;
+    if (!rabi_env_int("RABI_TC", 1)) return 2;
+    if (h->L == 3) return rabi_tcd_launch(h, c, mode, st);
+    if (npairs < (long long)rabi_env_int("RABI_TC_MIN_PAIRS", 1)) return 2;
+    TcState* s = nullptr;
+    TcArgs a;
+    const int rc = tc_prepare(h, c, mode, st, &s, &a);
+    if (rc) return rc;
+    const long long nt = (npairs + 127) / 128;
+    if (nt > 0x7fffffff) return 2;
+    a.ntiles = (int)nt;
+    // tiles per CTA: as many as the per-pair state next to the weight block allows, no more than the launch needs
+    const size_t budget = (size_t)h->max_smem_optin - 1024;
+    int NT = std::min(TC_MAXTILES, std::max(1, rabi_env_int("RABI_TC_TILES", TC_MAXTILES)));
+    while (NT > 1 && ((size_t)s->blk_words + (size_t)NT * 128 * a.VS) * 4 > budget) --NT;
+    if (((size_t)s->blk_words + (size_t)NT * 128 * a.VS) * 4 > budget) return 2;
+    const int grid = (int)std::min<long long>(nt, h->sm_count);
+    while (NT > 1 && (long long)grid * (NT - 1) >= nt) --NT;   // spread the tiles over the SMs first
+    const int T = NT * 128;
+    const size_t smem = ((size_t)s->blk_words + (size_t)T * a.VS) * 4;
+    return tc_dispatch_dp(h, s, a, mode, false, grid, T, smem, st);
+}
+
+// The whole L2-PGD attack in ONE launch (north_star kernel 3: "PGD step, L2 projection and eps-ball clamp in one launch"):
+// rows are independent, so a CTA keeps its row blocks for all nb_iter iterations and runs projection -> 12 flow phases ->
+// gradient back-projection -> advertorch perturb_iterative(ord=2) update on chip / in its own L2-resident slabs.
+// Reference loop body: advertorch perturb_iterative as called at rbi/rbi/attacks/advertorch_attack.py:100-114.
+int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
+    if (r.S <= 0 || r.B <= 0 || r.nb_iter <= 0) return 2;
+    if (!rabi_env_int("RABI_TC", 1) || !rabi_env_int("RABI_TC_RUN", 1)) return 2;
+    if (h->L != 2) return 2;
+    if ((long long)r.S * r.B < (long long)rabi_env_int("RABI_TC_RUN_MIN_PAIRS", 1025)) return 2;
+    TcCall c = {r.A_p, r.A_q, r.z_all, nullptr, nullptr, r.gA, r.S, r.B, r.inv_B / (float)r.S};
+    TcState* s = nullptr;
+    TcArgs a;
+    const int rc = tc_prepare(h, c, mode, st, &s, &a);
+    if (rc) return rc;
+    const MafImg& g = h->img;
+    const int C = h->C, H0 = h->H[0], K = h->K;
+    // the transposed context weights of all transforms (projection) and the K context blocks (back-projection) take turns in
+    // the weight-block region; bulk copies need 16-byte granularity
+    if ((g.ldKH & 3) || (g.W0cT & 3)) return 2;
+    size_t wsum = 0;
+    for (int k = 0; k < K; ++k) {
+        const TImg& t = g.t[k];
+        if ((t.ldc & 3) || (t.W0c & 3)) return 2;
+        wsum += (size_t)H0 * t.ldc;
     }
-    return 2;
+    // (the 8-wide unit / column tiles of the two products may read a few floats past a row end: still inside shared memory,
+    //  and those accumulators are never stored)
+    const size_t region = (std::max(std::max((size_t)s->blk_words, (size_t)C * g.ldKH), wsum) + 31) & ~(size_t)31;
+    a.region_words = (int)region;
+    const size_t budget = (size_t)h->max_smem_optin - 1024;
+    int NT = TC_MAXTILES;
+    while (NT > 1 && (region + (size_t)NT * 128 * a.VS) * 4 > budget) --NT;
+    if ((region + (size_t)NT * 128 * a.VS) * 4 > budget) return 2;
+    // rows per block: all S samples of a row in one CTA; as few rounds of blocks as possible, every CTA the same number of rows.
+    // The per-pair region also holds, in turn, the cotangent tile [K H0][RP] and the gradient tile + Xs (2 C RP).
+    if (C > 128) return 2;                               // the update keeps a row in 4 registers per lane
+    const size_t spare = budget / 4 - region;            // words available behind the weight region
+    auto tail_words = [&](int R_) {
+        const size_t RP_ = (size_t)((R_ + 7) & ~7) + 4;
+        const size_t CG_ = (size_t)((C + 7) & ~7);
+        return std::max((size_t)K * H0 * RP_, RP_ * CG_ + (size_t)C * RP_);   // cotangent tile | gradient tile [RP][CG] + Xs [C][RP]
+    };
+    int Rmax = ((NT * 128) / r.S) & ~3;
+    while (Rmax >= 4 && tail_words(Rmax) > spare) Rmax -= 4;
+    if (Rmax < 4) return 2;
+    const int rounds = (r.B + h->sm_count * Rmax - 1) / (h->sm_count * Rmax);
+    int R = ((r.B + h->sm_count * rounds - 1) / (h->sm_count * rounds) + 3) & ~3;
+    R = std::min(R, Rmax);
+    const int RP = ((R + 7) & ~7) + 4;
+    const int nblocks = (r.B + R - 1) / R;
+    const int gtiles = ((C + 7) / 8) * ((RP - 4) / 8);         // one (8 rows x 8 columns) gradient tile per thread
+    if (gtiles > NT * 128) return 2;
+    while (NT > 1 && (NT - 1) * 128 >= r.S * R && (NT - 1) * 128 >= gtiles) --NT;
+    a.x = r.x;
+    a.delta = r.delta;
+    a.zmean = r.zmean;
+    a.zstd = r.zstd;
+    a.nb_iter = r.nb_iter;
+    a.R = R;
+    a.RP = RP;
+    a.nblocks = nblocks;
+    a.eps = r.eps;
+    a.eps_iter = r.eps_iter;
+    a.cmin = r.cmin;
+    a.cmax = r.cmax;
+    a.floor_ = r.floor_;
+    a.zstride = (long long)r.S * r.B * h->D;
+    const int grid = std::min(nblocks, h->sm_count);
+    const int T = NT * 128;
+    a.vec_words = (int)std::max((size_t)T * a.VS, tail_words(R));
+    a.xs_off = a.vec_words - C * RP;
+    const size_t smem = (region + (size_t)a.vec_words) * 4;
+    if (smem > budget) return 2;
+    if (rabi_env_int("RABI_TC_RUN_DBG", 0)) {   // development aid: cycle counters of CTA 0 per section of an iteration
+        long long* d = nullptr;
+        RABI_CU_OK(h, cudaMalloc(&d, 16 * sizeof(long long)));
+        RABI_CU_OK(h, cudaMemsetAsync(d, 0, 16 * sizeof(long long), st));
+        a.dbg = d;
+        int rc2 = tc_dispatch_dp(h, s, a, mode, true, grid, T, smem, st);
+        long long hc[16];
+        RABI_CU_OK(h, cudaStreamSynchronize(st));
+        RABI_CU_OK(h, cudaMemcpy(hc, d, sizeof(hc), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        static const char* names[7] = {"wait ctx weights", "projection", "flow phases", "stage gA", "gx product", "reduce groups", "update"};
+        fprintf(stderr, "rabi_tc_run: R=%d RP=%d blocks=%d T=%d smem=%zu; cycles per iteration of CTA 0:", R, RP, nblocks, T, smem);
+        for (int i = 0; i < 7; ++i) fprintf(stderr, " %s %.0f;", names[i], (double)hc[i] / r.nb_iter);
+        fprintf(stderr, " | inside the flow phases: block loads %.0f; sampling fwd %.0f; density fwd %.0f; density bwd %.0f; sampling bwd %.0f;",
+                (double)hc[8] / r.nb_iter, (double)hc[9] / r.nb_iter, (double)hc[10] / r.nb_iter, (double)hc[11] / r.nb_iter, (double)hc[12] / r.nb_iter);
+        fprintf(stderr, " | update of warp 0: operands + first reduction %.0f; second reduction %.0f; stores %.0f; wait for the other warps %.0f",
+                (double)hc[13] / r.nb_iter, (double)hc[14] / r.nb_iter, (double)hc[15] / r.nb_iter, (double)hc[6] / r.nb_iter);
+        fprintf(stderr, "\n");
+        return rc2;
+    }
+    return tc_dispatch_dp(h, s, a, mode, true, grid, T, smem, st);
 }
 
 void rabi_tc_destroy(rabi_maf* h) {

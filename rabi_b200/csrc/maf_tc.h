@@ -18,6 +18,22 @@ struct TcCall {
     float w;            // weight of one pair in the loss (inv_B / S)
 };
 
+// The whole L2-PGD attack (nb_iter iterations) as one persistent launch (two-hidden-layer conditioners, identity / z-score
+// embedding): projection, flow passes, gradient back-projection and the perturb_iterative(ord=2) update inside the kernel.
+struct TcRunCall {
+    const float* A_p;     // reverse KL: [K,H0,B] slab the kernel rewrites every iteration; forward KL: the fixed target's projection
+    const float* A_q;     // reverse KL: projection of the clean x (fixed); forward KL: the slab that follows delta
+    const float* z_all;   // [nb_iter,S,B,D]
+    float* gA;            // [K,H0,B], zeroed by the caller; left zeroed
+    const float* x;       // [B,C]
+    float* delta;         // [B,C] in / out
+    const float* zmean;   // [C] or null (with zstd)
+    const float* zstd;
+    int nb_iter, S, B;
+    float eps, eps_iter, cmin, cmax, inv_B, floor_;
+};
+int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st);
+
 // returns 0 = launched, 1 = error (message on the handle), 2 = shape / launch not eligible for this path
 int rabi_tc_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st);
 void rabi_tc_destroy(rabi_maf* h);

@@ -1552,6 +1552,38 @@ extern "C" int rabi_fkl_input_grad(rabi_maf_t* h, const float* x_dev, const floa
     return 0;
 }
 
+// The whole attack as ONE persistent launch where the tensor-core path supports it (maf_tc.cu: rabi_tc_run); 2 = not eligible,
+// the caller then runs the per-iteration launch groups.  Workspace as in pgd_step_impl: [A_p][gA][gx][diff].
+static int pgd_run_fused(rabi_maf* h, const float* x, float* delta, const float* zm, const float* zs, const float* A_fixed,
+                         const float* z_all, int nb_iter, int S, int B, float eps, float eps_iter, float cmin, float cmax,
+                         float inv_B, float floor_, cudaStream_t st, int forward_kl) {
+    if ((zm == nullptr) != (zs == nullptr)) return fail(h, "zs_mean and zs_std must both be given or both be NULL");
+    if (env_int("RABI_FORCE_DEEP", 0)) return 2;
+    const size_t nA = (size_t)h->K * h->H[0] * B;
+    float* A_pert = (float*)h->ws;
+    float* gA = A_pert + nA;
+    CU_OK(h, cudaMemsetAsync(gA, 0, nA * sizeof(float), st));
+    rabi::TcRunCall r = {};
+    r.A_p = forward_kl ? A_fixed : A_pert;
+    r.A_q = forward_kl ? A_pert : A_fixed;
+    r.z_all = z_all;
+    r.gA = gA;
+    r.x = x;
+    r.delta = delta;
+    r.zmean = zm;
+    r.zstd = zs;
+    r.nb_iter = nb_iter;
+    r.S = S;
+    r.B = B;
+    r.eps = eps;
+    r.eps_iter = eps_iter;
+    r.cmin = cmin;
+    r.cmax = cmax;
+    r.inv_B = inv_B;
+    r.floor_ = floor_;
+    return rabi::rabi_tc_run(h, r, forward_kl ? rabi::TC_FKL : rabi::TC_GRAD, st);
+}
+
 extern "C" int rabi_fkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* zs_mean_dev,
                                 const float* zs_std_dev, const float* A_t_dev, const float* z_all_dev, int nb_iter, int S,
                                 int B, float eps, float eps_iter, float clip_min, float clip_max, float inv_B,
@@ -1568,7 +1600,10 @@ extern "C" int rabi_fkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_
         A_t = own;
     }
     const size_t zstride = (size_t)S * B * h->D;
-    for (int it = 0; it < nb_iter; ++it)
+    int fused = pgd_run_fused(h, x_dev, delta_dev, zs_mean_dev, zs_std_dev, A_t, z_all_dev, nb_iter, S, B, eps, eps_iter, clip_min,
+                              clip_max, inv_B, norm_floor, st, 1);
+    if (fused == 1) return 1;
+    for (int it = 0; fused == 2 && it < nb_iter; ++it)
         if (pgd_step_impl(h, x_dev, delta_dev, zs_mean_dev, zs_std_dev, A_t, z_all_dev + (size_t)it * zstride, S, B, eps,
                           eps_iter, clip_min, clip_max, inv_B, norm_floor, nullptr, st, 1))
             return 1;
@@ -1597,7 +1632,10 @@ extern "C" int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_
         A_q = own;
     }
     const size_t zstride = (size_t)S * B * h->D;
-    for (int it = 0; it < nb_iter; ++it)
+    int fused = pgd_run_fused(h, x_dev, delta_dev, zs_mean_dev, zs_std_dev, A_q, z_all_dev, nb_iter, S, B, eps, eps_iter, clip_min,
+                              clip_max, inv_B, norm_floor, st, 0);
+    if (fused == 1) return 1;
+    for (int it = 0; fused == 2 && it < nb_iter; ++it)
         if (pgd_step_impl(h, x_dev, delta_dev, zs_mean_dev, zs_std_dev, A_q, z_all_dev + (size_t)it * zstride, S, B, eps,
                           eps_iter, clip_min, clip_max, inv_B, norm_floor, nullptr, st))
             return 1;

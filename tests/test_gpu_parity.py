@@ -596,3 +596,64 @@ def test_three_layer_tensor_core_kernel_equals_fma_paths(shape, dev):
             assert float((b[2] - a[2]).abs().max()) < 1e-5 * lp_scale and float((b[4] - a[4]).abs().max()) < 1e-5 * lp_scale
             assert_trajectories_match(b[1], a[1], 1e-4, prone=relu_margins(ref, x + 0.05, x, z.cpu()) < TAU)
             assert_trajectories_match(b[3], a[3], 1e-4, prone=relu_margins(ref, x, x + 0.05, z.cpu()) < TAU)
+
+
+@pytest.mark.parametrize("shape", [dict(dx=100, D=4, hidden=[100, 100], B=301, S=5), dict(dx=10, D=10, hidden=[100, 100], B=530, S=3),
+                                   dict(dx=12, D=3, hidden=[64, 48], B=1300, S=1), dict(dx=100, D=4, hidden=[100, 100], B=12007, S=5),
+                                   dict(dx=37, D=2, hidden=[20, 36], B=77, S=7)])
+def test_persistent_attack_equals_per_iteration_launches(shape, dev):
+    """rabi_tc_run (maf_tc.cu: the whole L2-PGD attack as ONE persistent launch -- projection, flow passes, gradient
+    back-projection and the perturb_iterative(ord=2) update inside the kernel, a CTA owning its row blocks for all iterations)
+    against (a) the per-iteration launch groups of the same library and (b) the oracle, for the reverse- and the forward-KL
+    loss: ragged row counts, S = 1, context width != hidden width, D = 10, more than one round of row blocks per CTA."""
+    import os
+
+    from oracle import rbi_oracle as O
+
+    ref, model, x = _fresh(shape, dev, seed=21)
+    xd = x.to(dev)
+    eng = model.engine()
+    S, B, D, n_it = shape["S"], shape["B"], shape["D"], 6
+    g = torch.Generator().manual_seed(5)
+    z_all = torch.randn(n_it, S, B, D, generator=g)
+    d0 = 0.01 * torch.randn(B, shape["dx"], generator=g)
+    eps = float(0.5 * x.std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+    with torch.no_grad():
+        _, zs, _ = model.condition_inputs(xd)
+    launches = {}
+    for fkl in (False, True):
+        outs = []
+        for env in ({"RABI_TC_RUN": "0"}, {"RABI_TC_RUN_MIN_PAIRS": "1"}):
+            os.environ.update(env)
+            try:
+                delta = d0.to(dev).clone()
+                n0 = eng.launches
+                with torch.no_grad():
+                    xa = eng.pgd_run(xd, delta, zs[0], zs[1], None, z_all.to(dev), eps, eps / 4, cmin, cmax, 1.0 / B, forward_kl=fkl)
+                launches[tuple(env)] = eng.launches - n0
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+            outs.append((xa.cpu(), delta.cpu()))
+        nb = min(B, 400)   # the oracle walks a bounded number of rows (rows are independent; 1/B is explicit)
+        loss = (O.ForwardKLLoss if fkl else O.ReverseKLLoss)(mc_samples=S)
+        p = dict(eps=eps, eps_iter=eps / 4, clip_min=cmin, clip_max=cmax, S=S)
+        prone = pgd_near_kink_rows(ref, x[:nb], d0[:nb], [z[:, :nb] for z in z_all], p, forward_kl=fkl)
+        # (b) vs the oracle on the first rows: advertorch divides the loss by the batch it sees, the engine by B: same direction,
+        # the 1e-6 norm floor is far away at these sizes
+        with O.injected_base_noise([z[:, :nb] for z in z_all]):
+            xa_ref = O.l2pgd_perturb(ref, x[:nb], loss, eps, n_it, eps / 4, cmin, cmax, delta0=d0[:nb])
+        for q in ref.parameters():
+            q.grad = None
+        e = assert_trajectories_match(outs[1][0][:nb] - x[:nb], xa_ref - x[:nb], RTOL, prone=prone)
+        # (a) vs the per-iteration path: every row, same tolerance; rows proven near a kink (first rows) or, beyond them, a
+        # bounded fraction may sit on the other side of a ReLU kink
+        assert_trajectories_match(outs[1][1][:nb], outs[0][1][:nb], RTOL, prone=prone)
+        if B > nb:
+            assert_trajectories_match(outs[1][1][nb:], outs[0][1][nb:], RTOL, max_flip_frac=0.02)
+        assert float((outs[1][0] - x).norm(dim=-1).max()) <= eps * (1 + 1e-5)
+        print(f"\n[persistent attack {shape}, {'fKL' if fkl else 'rKL'}] max row rel. err vs oracle {float(e.max()):.2e} "
+              f"(near-kink rows {int(prone.sum())}/{nb})")
+    # one launch for the whole attack (+ the projection of the clean x, the final clamp and, on first use, the image pack)
+    assert launches[("RABI_TC_RUN_MIN_PAIRS",)] <= 4 < launches[("RABI_TC_RUN",)], launches
