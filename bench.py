@@ -105,7 +105,7 @@ def bench_config(wname, w, world, flops):
     """The ``config`` object of the bench line; the reference arm prints the SAME object (same workload, same sizes)."""
     return {"workload": wname, "rows_per_gpu": w["rows"], "chunk": w["chunk"], "nb_iter": w["nb_iter"],
             "S_att": w["S_att"], "S_eval": w["S_eval"], "dx": w["dx"], "D": w["D"], "hidden": w["hidden"], "K": w["K"],
-            "pairs_per_step": w["rows"] * pairs_per_row(w) * world,
+            "pairs_per_step": w["rows"] * pairs_per_row(w) * world * max(1, int(w.get("eps_sweep", 1))), "eps_values_batched": max(1, int(w.get("eps_sweep", 1))),
             "parallelism": f"rows sharded over {world} GPU(s), no data-path collective",
             "l2": "per-step inputs (fresh base noise, 160 MB) exceed the 126 MB L2",
             "flop_per_attack_pair": flops["attack_pair"], "flop_per_eval_pair": flops["eval_pair"]}
@@ -447,28 +447,37 @@ def measure(wname, w, args, steps, warmup, dev, world, rank, local, scaling, wit
                                 batch_size=w["chunk"], reduction=None)
     eng = model.engine()
 
-    def step_device():
+    n_eps = max(1, int(getattr(args, "eps_sweep", 1)))
+    sweep = [0.1, 0.2, 0.3, 0.5, 1.0, 2.0][:n_eps] if n_eps > 1 else None   # config/experiment/eval_l2_pyloric.yaml:13-16
+
+    def run(xd):
+        """one pass of the hot path over this rank's rows: attack + metric (at every radius of the sweep, batched, if asked)"""
         metric._cached_x = metric._cached_xs_tilde = metric._cached_losses = None
-        losses = metric._eval(x_dev)
+        if sweep is None:
+            return metric._eval(xd)
+        return torch.stack([v for v in metric.eval_sweep(xd, sweep).values()]).reshape(-1)
+
+    def step_device():
+        losses = run(x_dev)
         if world > 1:  # the path's one exchange step: gather the per-observation losses for the quantile summary
             out = [torch.empty_like(losses) for _ in range(world)]
             dist.all_gather(out, losses)
             losses = torch.cat(out)
         return losses
 
-    loss_host = torch.empty(w["rows"] * world, dtype=torch.float32).pin_memory()
+    loss_host = torch.empty(w["rows"] * world * n_eps, dtype=torch.float32).pin_memory()
     xadv_host = torch.empty_like(x_host).pin_memory()
 
     def step_e2e():
-        metric._cached_x = metric._cached_xs_tilde = metric._cached_losses = None
         xd = x_host.to(dev, non_blocking=True)
-        losses = metric._eval(xd)
+        losses = run(xd)
         if world > 1:
             out = [torch.empty_like(losses) for _ in range(world)]
             dist.all_gather(out, losses)
             losses = torch.cat(out)
         loss_host.copy_(losses, non_blocking=True)
-        xadv_host.copy_(metric._cached_xs_tilde, non_blocking=True)
+        if sweep is None:
+            xadv_host.copy_(metric._cached_xs_tilde, non_blocking=True)
         torch.cuda.synchronize()
         return loss_host
 
@@ -509,13 +518,19 @@ def measure(wname, w, args, steps, warmup, dev, world, rank, local, scaling, wit
     kern_ms, kern_n = eng.profile_read()
     eng.profile(False)
 
-    pairs_step = w["rows"] * pairs_per_row(w) * world
+    pairs_step = w["rows"] * pairs_per_row(w) * world * n_eps
     value = pairs_step * steps / (ms * 1e-3)
     e2e = pairs_step * steps / (ms_e2e * 1e-3)
 
     # roofline of the dominant kernel: per-pair rKL forward + reverse (one launch per PGD iteration)
-    pairs_launch = w["rows"] * w["S_att"]
-    achieved = pairs_launch * flops["pair_kernel_attack"] / (kern_ms / max(kern_n, 1) * 1e-3) / 1e12 if kern_n else None
+    pairs_launch = w["rows"] * w["S_att"] * n_eps
+    # the persistent attack kernel covers all nb_iter iterations (and the context projection / back-projection products,
+    # 2 x 2 K X FLOP per row and iteration) in ONE launch; the per-iteration path launches the per-pair kernel nb_iter times
+    iters_per_launch = max(1, round(w["nb_iter"] * n_prof / max(kern_n, 1)))
+    flop_launch = pairs_launch * flops["pair_kernel_attack"] * iters_per_launch
+    if iters_per_launch > 1:
+        flop_launch += iters_per_launch * w["rows"] * n_eps * 4.0 * w["K"] * flops["X"]
+    achieved = flop_launch / (kern_ms / max(kern_n, 1) * 1e-3) / 1e12 if kern_n else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -526,7 +541,7 @@ def measure(wname, w, args, steps, warmup, dev, world, rank, local, scaling, wit
     traffic = traffic_src = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this kernel
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel_name]
-        if t["pairs_per_launch"] == pairs_launch:
+        if t["pairs_per_launch"] == pairs_launch and t.get("pgd_iterations_per_launch", 1) == iters_per_launch:
             traffic, traffic_src = t["dram_bytes_per_launch"], f"ncu capture at commit {t['commit']} ({t['file']})"
     except Exception:
         pass
@@ -535,17 +550,21 @@ def measure(wname, w, args, steps, warmup, dev, world, rank, local, scaling, wit
     tc_peak = bf16 / 2.0 / 3.0      # TF32 runs at half the bf16 rate; one fp32-accurate product = 3 TF32 MMAs
     ceiling = 1.0 / (tfrac / tc_peak + (1.0 - tfrac) / fma_peak) if fma_peak > 0 else None
     roofline = {
-        "bound": "tensor", "kernel": f"{kernel_name} (per-pair rKL forward + reverse on tcgen05.mma kind::tf32 (3xTF32) + FMA, "
-                                     "one launch per PGD iteration)",
+        "bound": "tensor", "kernel": f"{kernel_name} (per-pair rKL forward + reverse on tcgen05.mma kind::tf32 (3xTF32) + FMA, " + (
+            "one launch per PGD iteration)" if iters_per_launch == 1 else
+            f"persistent: ONE launch for all {iters_per_launch} PGD iterations incl. projection, back-projection and update)"),
         "achieved": achieved, "peak": ceiling, "unit": "TFLOP/s",
         "frac": (achieved / ceiling) if (achieved and ceiling) else None, "traffic": traffic, "traffic_source": traffic_src,
-        "algorithmic_bytes_per_launch": int(4 * (w["rows"] * w["S_att"] * w["D"] + 3 * w["K"] * w["hidden"][0] * w["rows"])),
+        # per launch: base noise of every iteration; per-iteration path: + A_p, A_q in, gA out; persistent kernel: A_q + x, delta once
+        "algorithmic_bytes_per_launch": int(4 * n_eps * (iters_per_launch * w["rows"] * w["S_att"] * w["D"] + (
+            3 * w["K"] * w["hidden"][0] * w["rows"] if iters_per_launch == 1 else
+            w["K"] * w["hidden"][0] * w["rows"] + 3 * w["rows"] * w["dx"]))),
         "peak_source": f"{tfrac:.3f} of the kernel's algorithmic MACs are tensor-core products: ceiling = 1 / (share / (bf16_tflops_sustained "
                        f"{bf16} [MEASURED_PEAKS.json] / 2 [TF32] / 3 [3xTF32]) + (1 - share) / fp32 FMA peak {fma_peak:.1f} "
                        "[rabi_fma_peak_tflops, register-only FFMA microbenchmark run in this process])",
         "tensor_share_of_macs": tfrac, "fp32_fma_peak": fma_peak,
         "frac_of_fp32_fma_peak": (achieved / fma_peak) if (achieved and fma_peak > 0) else None,
-        "flop_per_launch": pairs_launch * flops["pair_kernel_attack"],
+        "flop_per_launch": flop_launch, "pgd_iterations_per_launch": iters_per_launch,
         "kernel_ms_avg": kern_ms / max(kern_n, 1), "kernel_launches_timed": kern_n,
         "kernel_share_of_step": kern_ms / ms_prof if ms_prof else None,
         "whole_step_tflops": (w["rows"] * (w["nb_iter"] * w["S_att"] * flops["attack_pair"] + w["S_eval"] * flops["eval_pair"])
@@ -585,6 +604,8 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="observations per GPU (default: the workload's)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's rows on EVERY GPU; strong: the workload's rows in total, split over the GPUs")
+    ap.add_argument("--eps-sweep", type=int, default=1,
+                    help="attack every row at this many radii of the reference's eps sweep in ONE batched call (rows x eps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true",
                     help="skip the second record (BASELINE config 5: pyloric ctx-space) carried under 'also' in the same JSON line")
@@ -624,6 +645,7 @@ def main():
     _lib.build()
     if args.scaling == "strong":
         w["rows"] = w["rows"] // world
+    w["eps_sweep"] = args.eps_sweep
     line = measure(args.workload, w, args, args.steps, args.warmup, dev, world, rank, local, args.scaling,
                    with_baselines=not args.no_cpu_baseline)
     if args.workload == "lotka_volterra_l2pgd_rkl" and not args.no_config5:

@@ -117,6 +117,13 @@ int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const 
 int rabi_pgd_update(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* grad_dev, int B, int dx, float eps,
                     float eps_iter, float clip_min, float clip_max, float norm_floor, rabi_stream_t s);
 
+/* Per-row attack radii for batched eps-sweeps (config/experiment/eval_l2_pyloric.yaml:13-16 sweeps eps over 6 values;
+ * run_rob_eval.py:115-140 derives eps_abs and eps_iter per value): rows x eps values are independent, so one call can attack
+ * the rows at all radii at once.  While set, every rabi_*_pgd_step / rabi_*_pgd_run / rabi_pgd_update on this handle uses
+ * eps_rows_dev[b] / eps_iter_rows_dev[b] ([B] device arrays owned by the caller) instead of its scalar eps / eps_iter
+ * arguments.  Pass NULL, NULL to return to the scalars. */
+int rabi_pgd_set_row_scales(rabi_maf_t* h, const float* eps_rows_dev, const float* eps_iter_rows_dev);
+
 /* Forward-KL attack loss (ForwardKLLoss, rbi/rbi/loss/eval_loss.py:108-126 -- the default attack_loss_fn of
  * config/eval_rob/attack/l2pgd.yaml): loss = inv_B * sum_b KL(target_b || q(.|x_b + delta_b)); samples are drawn from the
  * fixed target (projection A_t_dev; NULL in the run = the clean x), the gradient flows through the density pass only.

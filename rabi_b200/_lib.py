@@ -34,7 +34,7 @@ EXPORTS = [
     "rabi_maf_ctx_project_bwd", "rabi_maf_log_prob_fwd", "rabi_maf_rsample_fwd", "rabi_rkl_fwd",
     "rabi_rkl_input_grad", "rabi_rkl_pgd_step", "rabi_rkl_pgd_run", "rabi_launch_count",
     "rabi_profile", "rabi_profile_read", "rabi_fma_peak_tflops", "rabi_sgemm", "rabi_sgemm_launch_count",
-    "rabi_fkl_input_grad", "rabi_fkl_pgd_run", "rabi_pgd_update",
+    "rabi_fkl_input_grad", "rabi_fkl_pgd_run", "rabi_pgd_update", "rabi_pgd_set_row_scales",
 ]
 
 
@@ -133,6 +133,8 @@ def lib() -> ctypes.CDLL:
     L.rabi_fkl_input_grad.restype = L.rabi_fkl_pgd_run.restype = c_int
     L.rabi_pgd_update.argtypes = [vp, vp, vp, vp, c_int, c_int, c_float, c_float, c_float, c_float, c_float, vp]
     L.rabi_pgd_update.restype = c_int
+    L.rabi_pgd_set_row_scales.argtypes = [vp, vp, vp]
+    L.rabi_pgd_set_row_scales.restype = c_int
     L.rabi_sgemm.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, vp, c_int, vp, c_int, vp, c_int, c_float, vp]
     L.rabi_sgemm.restype = c_int
     L.rabi_sgemm_launch_count.argtypes = []

@@ -60,9 +60,14 @@ def rand_init_delta_l2(x: Tensor, eps: float, clip_min: float, clip_max: float) 
     """advertorch ``rand_init_delta`` (ord=2) followed by the box clamp of ``PGDAttack.perturb``."""
     delta = torch.empty_like(x).uniform_(clip_min, clip_max) - x
     norm = delta.abs().pow(2).sum(dim=1).pow(0.5)
-    delta = delta * torch.min(eps / norm, torch.ones_like(norm))[:, None]
+    delta = delta * torch.min(eps / norm, torch.ones_like(norm))[:, None]   # eps: float or a [B] tensor (eps-sweep)
     delta = torch.clamp(x + delta, clip_min, clip_max) - x
     return torch.clamp(x + delta, clip_min, clip_max) - x
+
+
+def _scalar(v) -> float:
+    """eps / eps_iter as the scalar argument of the C ABI (ignored by the kernels while per-row scales are set)."""
+    return float(v.max()) if isinstance(v, Tensor) else float(v)
 
 
 class L2PGDAttack(Attack):
@@ -105,10 +110,14 @@ class L2PGDAttack(Attack):
         eng = model.engine()
         x = x.float().contiguous()
         B, dx = x.shape
+        per_row = isinstance(self.eps, Tensor) and self.eps.dim() == 1   # batched eps-sweep: one radius per row
+        if per_row and self.eps.shape[0] != B:
+            raise ValueError(f"per-row eps has {self.eps.shape[0]} entries for {B} rows")
+        eps0 = self.eps.to(x) if per_row else float(self.eps)
         if delta_init is not None:
             delta = delta_init.detach().to(x).clone().contiguous()
         elif self.rand_init:
-            delta = rand_init_delta_l2(x, float(self.eps), float(self.clip_min), float(self.clip_max)).contiguous()
+            delta = rand_init_delta_l2(x, eps0, float(self.clip_min), float(self.clip_max)).contiguous()
         else:
             delta = torch.zeros_like(x)
         S = int(self.loss_fn.mc_samples)
@@ -122,13 +131,42 @@ class L2PGDAttack(Attack):
         if self.targeted:
             inv_B = -inv_B  # perturb_iterative(minimize=True): descend on the loss
         from .models import _split_embedding
-        if _split_embedding(model.embedding_net)[1] is not None:
-            return self._run_embedded(model, eng, x, delta, y, z_all, inv_B).detach()
-        _, zs, _ = model.condition_inputs(x)
-        zs = zs if zs is not None else (None, None)
-        # A_q: the target's projection (== projection of the clean x when untargeted)
-        x_adv = self._run(eng, x, delta, zs, y, z_all, inv_B)
-        return x_adv.detach()
+        if per_row:
+            step = self.eps_iter.to(x) if isinstance(self.eps_iter, Tensor) else torch.full_like(eps0, float(self.eps_iter))
+            eng.set_row_scales(eps0, step)
+        try:
+            if _split_embedding(model.embedding_net)[1] is not None:
+                return self._run_embedded(model, eng, x, delta, y, z_all, inv_B).detach()
+            _, zs, _ = model.condition_inputs(x)
+            zs = zs if zs is not None else (None, None)
+            # A_q: the target's projection (== projection of the clean x when untargeted)
+            x_adv = self._run(eng, x, delta, zs, y, z_all, inv_B)
+            return x_adv.detach()
+        finally:
+            if per_row:
+                eng.set_row_scales()
+
+    def perturb_sweep(self, x: Tensor, eps_values, eps_iter_values=None, delta_init: Optional[Tensor] = None,
+                      chunk_size: Optional[int] = None) -> Tensor:
+        """The attack at SEVERAL radii in one call: x [B, dx] -> x_adv [n_eps, B, dx].
+
+        The reference sweeps eps with one process per value (config/experiment/eval_l2_pyloric.yaml:13-16, hydra multirun);
+        rows x radii are independent, so they are stacked into one batch of n_eps * B rows with a per-row radius / step size
+        (eps_iter "auto" per value as run_rob_eval.py:137-140 when ``eps_iter_values`` is None).  ``chunk_size`` defaults to B, so
+        every row sees the 1/B loss scaling of its own single-eps run."""
+        eps_values = [float(e) for e in eps_values]
+        n, B = len(eps_values), x.shape[0]
+        if eps_iter_values is None:
+            eps_iter_values = [min(e / max(self.nb_iter, 1) * 20, e) for e in eps_values]
+        eps_rows = torch.tensor(eps_values, device=x.device, dtype=torch.float32).repeat_interleave(B)
+        step_rows = torch.tensor([float(e) for e in eps_iter_values], device=x.device, dtype=torch.float32).repeat_interleave(B)
+        saved = (self.eps, self.eps_iter)
+        self.eps, self.eps_iter = eps_rows, step_rows
+        try:
+            out = self.perturb(x.repeat(n, 1), delta_init=delta_init, chunk_size=chunk_size or B)
+        finally:
+            self.eps, self.eps_iter = saved
+        return out.reshape(n, B, -1)
 
     def _run_embedded(self, model, eng, x, delta, y, z_all, inv_B):
         """x-space PGD through a non-identity embedding net (e.g. pyloric's CNN): every iteration the embedding runs in
@@ -143,11 +181,11 @@ class L2PGDAttack(Attack):
             gh, _ = eng.rkl_input_grad(h.detach().float().contiguous(), None, None, y.A, z_all[it], inv_B,
                                        want_kl=False, forward_kl=fkl)
             (gx,) = torch.autograd.grad(h, xd, gh)
-            eng.pgd_update(x, delta, gx.contiguous(), self.eps, self.eps_iter, self.clip_min, self.clip_max)
+            eng.pgd_update(x, delta, gx.contiguous(), _scalar(self.eps), _scalar(self.eps_iter), self.clip_min, self.clip_max)
         return torch.clamp(x + delta, self.clip_min, self.clip_max)
 
     def _run(self, eng, x, delta, zs, y, z_all, inv_B):
-        return eng.pgd_run(x, delta, zs[0], zs[1], y.A, z_all, self.eps, self.eps_iter, self.clip_min, self.clip_max,
+        return eng.pgd_run(x, delta, zs[0], zs[1], y.A, z_all, _scalar(self.eps), _scalar(self.eps_iter), self.clip_min, self.clip_max,
                            inv_B, forward_kl=type(self.loss_fn) is ForwardKLLoss)
 
 

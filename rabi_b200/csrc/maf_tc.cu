@@ -94,6 +94,8 @@ struct TcArgs {
     const float* zstd;
     int nb_iter, R, RP, nblocks;   // R rows per block (multiple of 4), RP = shared-memory row stride (round8(R) + 4)
     float eps, eps_iter, cmin, cmax, floor_;
+    const float* eps_rows;      // optional per-row radius / step size
+    const float* eps_iter_rows;
     long long zstride;    // floats between the base noise of consecutive iterations (S * B * D)
     int vec_words;        // words of the per-pair region (the tail's tiles live there between the flow phases)
     int xs_off;           // word offset of Xs inside it; the partial gradient tiles of the thread groups lie in front
@@ -838,10 +840,12 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
 #pragma unroll
                     for (int q = 0; q < NB; ++q) {
                         const float inv = 1.f / fmaxf(sqrtf(n2[q]), a.floor_);
+                        const int rq = rb + q * nwarps;
+                        const float step = (a.eps_iter_rows && rq < nr) ? a.eps_iter_rows[b0 + rq] : a.eps_iter;
                         d2[q] = 0.f;
 #pragma unroll
                         for (int e = 0; e < NE; ++e) {
-                            float d = dv[q][e] + (gv[q][e] * inv) * a.eps_iter;
+                            float d = dv[q][e] + (gv[q][e] * inv) * step;
                             d = fminf(fmaxf(xv[q][e] + d, a.cmin), a.cmax) - xv[q][e];
                             dv[q][e] = (lane + 32 * e < C) ? d : 0.f;
                             d2[q] = fmaf(dv[q][e], dv[q][e], d2[q]);
@@ -857,7 +861,8 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                     for (int q = 0; q < NB; ++q) {
                         const int r = rb + q * nwarps;
                         if (r >= RT) continue;
-                        const float factor = fminf(a.eps / sqrtf(d2[q]), 1.f);
+                        const float radius = (a.eps_rows && r < nr) ? a.eps_rows[b0 + r] : a.eps;
+                        const float factor = fminf(radius / sqrtf(d2[q]), 1.f);
 #pragma unroll
                         for (int e = 0; e < NE; ++e) {
                             const int c = lane + 32 * e;
@@ -1260,6 +1265,8 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
     a.cmin = r.cmin;
     a.cmax = r.cmax;
     a.floor_ = r.floor_;
+    a.eps_rows = r.eps_rows;
+    a.eps_iter_rows = r.eps_iter_rows;
     a.zstride = (long long)r.S * r.B * h->D;
     const int grid = std::min(nblocks, h->sm_count);
     const int T = NT * 128;

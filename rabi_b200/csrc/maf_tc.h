@@ -31,6 +31,8 @@ struct TcRunCall {
     const float* zstd;
     int nb_iter, S, B;
     float eps, eps_iter, cmin, cmax, inv_B, floor_;
+    const float* eps_rows;       // optional [B] per-row radius / step size (batched eps-sweep); else the scalars
+    const float* eps_iter_rows;
 };
 int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st);
 

@@ -38,6 +38,8 @@ struct rabi_maf {
     int max_smem_optin = 0;
     void* tc = nullptr;        // tensor-core path state (maf_tc.cu), owned by rabi_tc_*
     void* tcd = nullptr;       // three-hidden-layer tensor-core path state (maf_tcd.cu), owned by rabi_tcd_*
+    const float* row_eps = nullptr;        // optional per-row attack radii / step sizes (rabi_pgd_set_row_scales)
+    const float* row_eps_iter = nullptr;
     unsigned long long weights_version = 0;   // bumped by rabi_maf_set_weights / finalize: derived images re-pack lazily
 };
 

@@ -645,9 +645,14 @@ __global__ void k_mean_over_s(const float* __restrict__ in, int S, int B, float*
 
 // advertorch perturb_iterative(ord=2) update, one warp per row.
 __global__ void k_pgd_update(const float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ grad,
-                             int B, int dx, float eps, float eps_iter, float cmin, float cmax, float floor_) {
+                             int B, int dx, float eps, float eps_iter, float cmin, float cmax, float floor_,
+                             const float* __restrict__ eps_rows, const float* __restrict__ eps_iter_rows) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
+    if (eps_rows) {   // batched eps-sweep: every row carries its own radius and step size
+        eps = eps_rows[warp];
+        eps_iter = eps_iter_rows[warp];
+    }
     const float* gr = grad + (size_t)warp * dx;
     const float* xr = x + (size_t)warp * dx;
     float* dr = delta + (size_t)warp * dx;
@@ -1486,7 +1491,7 @@ grad_done:
     }
     int threads = 128, rows_per_block = threads / 32;
     k_pgd_update<<<(B + rows_per_block - 1) / rows_per_block, threads, 0, st>>>(x, delta, gx, B, h->C, eps, eps_iter,
-                                                                                   cmin, cmax, floor_);
+                                                                                   cmin, cmax, floor_, h->row_eps, h->row_eps_iter);
     LAUNCH_CHECK(h);
     if (kl) {
         k_mean_over_s<<<(B + 127) / 128, 128, 0, st>>>(diff, S, B, kl);
@@ -1510,6 +1515,15 @@ extern "C" int rabi_rkl_pgd_step(rabi_maf_t* h, const float* x_dev, float* delta
                          clip_max, inv_B, norm_floor, kl_dev, (cudaStream_t)s);
 }
 
+extern "C" int rabi_pgd_set_row_scales(rabi_maf_t* h, const float* eps_rows_dev, const float* eps_iter_rows_dev) {
+    if (!h) return 1;
+    if ((eps_rows_dev == nullptr) != (eps_iter_rows_dev == nullptr))
+        return fail(h, "rabi_pgd_set_row_scales: pass both arrays or NULL, NULL");
+    h->row_eps = eps_rows_dev;
+    h->row_eps_iter = eps_iter_rows_dev;
+    return 0;
+}
+
 extern "C" int rabi_pgd_update(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* grad_dev, int B, int dx,
                                float eps, float eps_iter, float clip_min, float clip_max, float norm_floor,
                                rabi_stream_t s) {
@@ -1517,7 +1531,7 @@ extern "C" int rabi_pgd_update(rabi_maf_t* h, const float* x_dev, float* delta_d
     if (B <= 0 || dx <= 0) return 0;
     int threads = 128, rows_per_block = threads / 32;
     k_pgd_update<<<(B + rows_per_block - 1) / rows_per_block, threads, 0, (cudaStream_t)s>>>(
-        x_dev, delta_dev, grad_dev, B, dx, eps, eps_iter, clip_min, clip_max, norm_floor);
+        x_dev, delta_dev, grad_dev, B, dx, eps, eps_iter, clip_min, clip_max, norm_floor, h->row_eps, h->row_eps_iter);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -1581,6 +1595,8 @@ static int pgd_run_fused(rabi_maf* h, const float* x, float* delta, const float*
     r.cmax = cmax;
     r.inv_B = inv_B;
     r.floor_ = floor_;
+    r.eps_rows = h->row_eps;
+    r.eps_iter_rows = h->row_eps_iter;
     return rabi::rabi_tc_run(h, r, forward_kl ? rabi::TC_FKL : rabi::TC_GRAD, st);
 }
 

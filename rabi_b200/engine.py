@@ -181,6 +181,15 @@ class MafEngine:
                                                    S, B, float(inv_B), _ptr(gx), _ptr(kl), self._stream()))
         return gx, kl
 
+    def set_row_scales(self, eps_rows=None, eps_iter_rows=None):
+        """Per-row attack radius / step size for batched eps-sweeps ([B] fp32 device tensors the caller keeps alive until it
+        clears them with ``set_row_scales()``); while set they replace the scalar eps / eps_iter of every PGD call."""
+        if (eps_rows is None) != (eps_iter_rows is None):
+            raise ValueError("pass both per-row arrays or neither")
+        self._row_scales = (None if eps_rows is None else (_f32c(eps_rows), _f32c(eps_iter_rows)))
+        a, b = self._row_scales if self._row_scales else (None, None)
+        self._check(self.L.rabi_pgd_set_row_scales(self.h, _ptr(a), _ptr(b)))
+
     def pgd_update(self, x, delta, grad, eps, eps_iter, clip_min, clip_max, norm_floor=1e-6):
         """In-place L2 step / box clamp / projection of ``delta`` given d loss / d delta."""
         B, dx = x.shape

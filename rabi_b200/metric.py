@@ -160,6 +160,27 @@ class RobustnessMetric(Metric):
         self._cached_losses = losses if self._cached_losses is None else torch.cat([self._cached_losses, losses])
         return losses
 
+    def eval_sweep(self, x: Tensor, eps_values, eps_relative_to_std: bool = True) -> dict:
+        """The metric at several attack radii from ONE batched attack (rows x radii are independent): what the reference
+        obtains from one ``run_rob_eval`` process per eps (config/experiment/eval_l2_pyloric.yaml:13-16).  eps is relative to
+        ``x.std(1).mean()`` as in run_rob_eval.py:115-121, eps_iter "auto" per value (:137-140); the attack keeps its other
+        settings.  Returns {eps: reduced value}; untargeted L2PGDAttack only."""
+        if self.targeted or not isinstance(self.attack, L2PGDAttack):
+            raise NotImplementedError("eval_sweep batches the untargeted L2-PGD attack")
+        x = x.to(self.device)
+        scale = float(x.std(1).mean()) if eps_relative_to_std else 1.0
+        eps_abs = [float(e) * scale for e in eps_values]
+        B = x.shape[0]
+        chunk = self.batch_size if (self.batch_size is not None and self.batch_size < B) else B
+        best = None
+        for _ in range(self.attack_attemps):
+            xs_t = self.attack.perturb_sweep(x, eps_abs, chunk_size=chunk)              # [n_eps, B, dx]
+            with torch.no_grad():
+                loss = self.loss_fn(self.model(xs_t.reshape(-1, x.shape[1])), self._get_goal(x.repeat(len(eps_abs), 1), None))
+                loss = torch.stack([self._ensure_loss_constraint(l) for l in loss.reshape(len(eps_abs), B)])
+            best = loss if best is None else (torch.maximum(best, loss) if self.descending else torch.minimum(best, loss))
+        return {float(e): self._reduce(best[i]) for i, e in enumerate(eps_values)}
+
     def generate_adversarial_examples(self, x: Tensor, target: Optional[Any] = None,
                                       num_examples: int = 100) -> Tuple[Tensor, Tensor]:
         if self._cached_x is None or self._cached_x.shape != x.shape or \

@@ -657,3 +657,46 @@ def test_persistent_attack_equals_per_iteration_launches(shape, dev):
               f"(near-kink rows {int(prone.sum())}/{nb})")
     # one launch for the whole attack (+ the projection of the clean x, the final clamp and, on first use, the image pack)
     assert launches[("RABI_TC_RUN_MIN_PAIRS",)] <= 4 < launches[("RABI_TC_RUN",)], launches
+
+
+@pytest.mark.parametrize("shape", ["lotka_volterra", "pyloric"])
+def test_batched_eps_sweep_equals_one_attack_per_eps(shape, dev):
+    """rows x attack radii in ONE call (rabi_pgd_set_row_scales: per-row eps / eps_iter; L2PGDAttack.perturb_sweep,
+    RobustnessMetric.eval_sweep) against one attack per eps -- what the reference runs as one process per value of
+    config/experiment/eval_l2_pyloric.yaml:13-16 -- on the same starting points and base noise."""
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+    from rabi_b200.metric import ReverseKLRobMetric
+
+    sh = dict(SHAPES[shape], B=300)
+    ref, model, x = _fresh(sh, dev, seed=31)
+    xd = x.to(dev)
+    B, D, S, n_it = sh["B"], sh["D"], 5, 6
+    std = float(x.std(1).mean())
+    eps_rel = [0.1, 0.5, 2.0]
+    cmin, cmax = float(x.min()), float(x.max())
+    g = torch.Generator().manual_seed(9)
+    zs = [torch.randn(n_it, S, B, D, generator=g) for _ in eps_rel]
+    d0 = [0.02 * (i + 1) * torch.randn(B, sh["dx"], generator=g) for i in range(len(eps_rel))]
+    singles = []
+    for i, e in enumerate(eps_rel):
+        eps = e * std
+        atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=S), eps=eps, nb_iter=n_it, eps_iter=min(eps / n_it * 20, eps),
+                          clip_min=cmin, clip_max=cmax)
+        with noise.injected(list(zs[i])):
+            singles.append(atk.perturb(xd, delta_init=d0[i].to(dev)).cpu())
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=S), eps=1.0, nb_iter=n_it, eps_iter=0.1, clip_min=cmin, clip_max=cmax)
+    with noise.injected([torch.cat([z[t] for z in zs], dim=1) for t in range(n_it)]):
+        sweep = atk.perturb_sweep(xd, [e * std for e in eps_rel], delta_init=torch.cat(d0).to(dev)).cpu()
+    assert sweep.shape == (len(eps_rel), B, sh["dx"]) and (atk.eps, atk.eps_iter) == (1.0, 0.1)
+    for i, e in enumerate(eps_rel):
+        err = assert_trajectories_match(sweep[i] - x, singles[i] - x, RTOL, max_flip_frac=0.02)
+        assert float((sweep[i] - x).norm(dim=-1).max()) <= e * std * (1 + 1e-5)
+        print(f"\n[eps-sweep {shape}] eps = {e} x std: max row rel. err vs the single-eps attack {float(err.max()):.2e}")
+    # the metric over the sweep: one value per eps, increasing with the radius
+    met = ReverseKLRobMetric(model, atk, mc_samples=32, attack_attemps=1, device=dev, batch_size=None, reduction="mean")
+    torch.manual_seed(3)
+    vals = met.eval_sweep(xd, eps_rel)
+    v = [float(vals[e]) for e in eps_rel]
+    assert all(torch.isfinite(torch.tensor(v))) and v[0] < v[1] < v[2], v
