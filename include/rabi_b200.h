@@ -117,6 +117,20 @@ int rabi_rkl_pgd_run(rabi_maf_t* h, const float* x_dev, float* delta_dev, const 
 int rabi_pgd_update(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* grad_dev, int B, int dx, float eps,
                     float eps_iter, float clip_min, float clip_max, float norm_floor, rabi_stream_t s);
 
+/* Training side (replaces the backward pass torch autograd builds for NLLLoss, rbi/rbi/loss/train_loss.py:16-29, through
+ * TransformedDistribution.log_prob, rbi/rbi/models/base.py:417-446): for theta_dev [S,B,D] (unconstrained space) and the rows'
+ * context ctx_dev [B,C] (after the z-score / embedding) with projection A_dev [K,H0,B] (rabi_maf_ctx_project), writes
+ * logq_dev [S,B] (optional) and, for the loss L with dL/dlogq = gout_dev [S,B]:
+ *   g_theta_dev [S,B,D] = dL/dtheta (optional), g_A_dev [K,H0,B] = dL/dA summed over the S samples of a row (optional; chain it
+ *   to x with rabi_maf_ctx_project_bwd), and the weight / bias gradients in the REFERENCE layout: g_weight_dev[k*(L+1)+l] is
+ *   [out_l, in_l] like t{k}.nn.layers.{l}.weight (masked entries get exact zeros, as autograd of weight*mask gives),
+ *   g_bias_dev[k*(L+1)+l] is [out_l].  g_weight_dev == NULL: no weight gradients.  All buffers are overwritten.
+ * Two-hidden-layer conditioners (<= 120 padded units, D <= 12) without Permute layers; other shapes return an error and the
+ * caller keeps its differentiable path. */
+int rabi_maf_log_prob_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* theta_dev,
+                          const float* gout_dev, int S, int B, float* logq_dev, float* g_theta_dev, float* g_A_dev,
+                          float* const* g_weight_dev, float* const* g_bias_dev, rabi_stream_t s);
+
 /* Per-row attack radii for batched eps-sweeps (config/experiment/eval_l2_pyloric.yaml:13-16 sweeps eps over 6 values;
  * run_rob_eval.py:115-140 derives eps_abs and eps_iter per value): rows x eps values are independent, so one call can attack
  * the rows at all radii at once.  While set, every rabi_*_pgd_step / rabi_*_pgd_run / rabi_pgd_update on this handle uses

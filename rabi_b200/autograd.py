@@ -171,7 +171,7 @@ HALF_LOG_2PI = 0.5 * math.log(2 * math.pi)
 
 
 # ----------------------------------------------------------------------------------------------- density pass
-def log_prob_differentiable(post, v: Tensor) -> Tensor:
+def _log_prob_ops(post, v: Tensor) -> Tensor:
     """v [S, Bf, D] (unconstrained space) -> log q(v | ctx) [S, Bf]; K full MADE passes."""
     model = post.model
     st = _struct(model)
@@ -199,6 +199,11 @@ def log_prob_differentiable(post, v: Tensor) -> Tensor:
         logdet = logdet + sh.sum(-1)
     base = (-0.5 * y * y - HALF_LOG_2PI).sum(-1)
     return (base + logdet).reshape(S, Bf)
+
+
+def log_prob_differentiable(post, v: Tensor) -> Tensor:
+    """The op-by-op (any-order differentiable) density pass; kept as the public name of the slow path."""
+    return _log_prob_ops(post, v)
 
 
 # ----------------------------------------------------------------------------------------------- sampling pass
@@ -251,3 +256,81 @@ def rsample_differentiable(post, z: Tensor) -> Tuple[Tensor, Tensor]:
         if st.post is not None:
             x = x.index_select(-1, st.post[k])
     return x.reshape(S, Bf, D), logq.reshape(S, Bf)
+
+
+# ----------------------------------------------------------------------------------------------- fused first-order path
+_force_differentiable = 0
+
+
+class differentiable_only:
+    """Inside this block ``log_prob`` builds the op-by-op graph above even where the fused backward would serve: for code
+    that is known to differentiate the result twice (the Fisher-trace regulariser)."""
+
+    def __enter__(self):
+        global _force_differentiable
+        _force_differentiable += 1
+
+    def __exit__(self, *exc):
+        global _force_differentiable
+        _force_differentiable -= 1
+        return False
+
+
+def _params(model) -> List[Tensor]:
+    out = []
+    for k in range(model.num_transforms):
+        for layer in getattr(model, "t" + str(k)).nn.layers:
+            out += [layer.weight, layer.bias]
+    return out
+
+
+class _FusedLogProb(torch.autograd.Function):
+    """log q(v | ctx) whose backward is ``rabi_maf_log_prob_bwd``: one per-pair tensor-core launch (density passes + their
+    reverse) and one launch for all weight-gradient products; no graph, no per-layer launches.  When the backward itself must
+    be differentiable (``create_graph=True``) it hands over to the op-by-op graph of ``log_prob_differentiable``."""
+
+    @staticmethod
+    def forward(ctx, post, v, ctx_in, *params):
+        ctx.post = post
+        ctx.save_for_backward(v, ctx_in)
+        return post.model.engine().log_prob(post.A, v)
+
+    @staticmethod
+    def backward(ctx, g):
+        post = ctx.post
+        v, ctx_in = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        params = _params(post.model)
+        if torch.is_grad_enabled():   # double backward requested: rebuild the differentiable graph and differentiate that
+            with torch.enable_grad():
+                vv = v if v.requires_grad else v.detach().requires_grad_(need[1])
+                lp = _log_prob_graph(post, vv)
+                wanted = [t for t, n in zip([vv, post.ctx_in] + params, need[1:]) if n]
+                got = iter(torch.autograd.grad(lp, wanted, g, create_graph=True, allow_unused=True))
+            return (None,) + tuple(next(got) if n else None for n in need[1:])
+        eng = post.model.engine()
+        A = post.A
+        rows = _context(post).detach()
+        want_w = any(need[3:])
+        g_v, g_A, grads = eng.log_prob_bwd(rows, A, v.detach(), g.detach(), want_weights=want_w)
+        g_ctx = None
+        if need[2]:
+            g_ctx = eng.ctx_project_bwd(g_A, post.zscore[1] if post.zscore is not None else None)
+        flat = [None] * len(params)
+        if want_w:
+            flat = [t for gk in grads for wb in gk for t in wb]
+            flat = [t if n else None for t, n in zip(flat, need[3:])]
+        return (None, g_v if need[1] else None, g_ctx) + tuple(flat)
+
+
+def _log_prob_graph(post, v: Tensor) -> Tensor:
+    return _log_prob_ops(post, v)
+
+
+def log_prob_training(post, v: Tensor) -> Tensor:
+    """Entry point of ``MAFPosterior.log_prob`` when gradients are needed: the fused kernels where they serve (two-hidden-layer
+    conditioners without Permute layers), else the op-by-op graph."""
+    eng = post.model.engine()
+    if _force_differentiable or not eng.fused_training_ok() or v.numel() == 0:
+        return _log_prob_ops(post, v)
+    return _FusedLogProb.apply(post, v, post.ctx_in, *_params(post.model))

@@ -97,6 +97,14 @@ struct TcArgs {
     const float* eps_rows;      // optional per-row radius / step size
     const float* eps_iter_rows;
     long long zstride;    // floats between the base noise of consecutive iterations (S * B * D)
+    const float* wrow;    // TC_NLL: per-pair loss weights and the per-pair vectors for the weight-gradient products (maf_tc.h)
+    float* em_h0;
+    float* em_a0;
+    float* em_h1;
+    float* em_a1;
+    float* em_o;
+    float* em_y;
+    float* theta_grad;
     int vec_words;        // words of the per-pair region (the tail's tiles live there between the flow phases)
     int xs_off;           // word offset of Xs inside it; the partial gradient tiles of the thread groups lie in front
     long long* dbg;       // optional [16] cycle counters of CTA 0 (RABI_TC_RUN_DBG=1): where an iteration's time goes
@@ -172,8 +180,9 @@ __device__ __forceinline__ void tc_stage4(uint32_t trow, int q, const float (&v)
 template <int MODE, int DP, bool RUN>
 __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, const TcArgs a) {
     extern __shared__ __align__(128) float sm[];
-    constexpr bool GRADM = MODE == TC_GRAD || MODE == TC_FKL;
-    static_assert(!RUN || GRADM, "the persistent attack exists for the two attack losses only");
+    constexpr bool GRADM = MODE == TC_GRAD || MODE == TC_FKL || MODE == TC_NLL;
+    constexpr bool NLLM = MODE == TC_NLL;
+    static_assert(!RUN || (MODE == TC_GRAD || MODE == TC_FKL), "the persistent attack exists for the two attack losses only");
     float* Wb = sm;                                   // the resident (transform, orientation) block
     const int* Wi = reinterpret_cast<const int*>(sm);
     float* vec = sm + a.region_words;                 // [threads][VS]
@@ -401,13 +410,15 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             float ssq = 0.f;
             for (int d = 0; d < D; ++d) {
                 const float zv = live ? zit[(size_t)pidx * D + d] : 0.f;
-                vecp[oV + (MODE == TC_LOGPROB ? K * D : 0) + d] = zv;
+                vecp[oV + ((MODE == TC_LOGPROB || NLLM) ? K * D : 0) + d] = zv;
                 ssq = fmaf(zv, zv, ssq);
             }
-            logp = MODE == TC_LOGPROB ? 0.f : -0.5f * ssq - (float)D * HALF_LOG_2PI;
+            logp = (MODE == TC_LOGPROB || NLLM) ? 0.f : -0.5f * ssq - (float)D * HALF_LOG_2PI;
         }
-        const int nphase = (MODE == TC_GRAD ? 4 : MODE == TC_FKL ? 3 : MODE == TC_RSAMPLE ? 1 : 2) * K;
-        for (int ph = (MODE == TC_LOGPROB ? K : 0); ph < nphase; ++ph) {
+        const int nphase = (MODE == TC_GRAD ? 4 : (MODE == TC_FKL || NLLM) ? 3 : MODE == TC_RSAMPLE ? 1 : 2) * K;
+        const float wp = a.wrow ? (live ? a.wrow[pidx] : 0.f) : a.w;   // weight of this pair in the loss
+        const size_t NP = (size_t)a.npairs;
+        for (int ph = ((MODE == TC_LOGPROB || NLLM) ? K : 0); ph < nphase; ++ph) {
             const int kind = ph / K;
             const int idx = ph - kind * K;
             const int k = (kind == 0 || kind == 2) ? idx : K - 1 - idx;
@@ -449,6 +460,8 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                     y[jj] = (!seq && jj < D) ? vecp[src + permy[jj]] : 0.f;
                     oms[jj] = jj < D ? make_float2(bo[2 * jj], bo[2 * jj + 1]) : make_float2(0.f, 0.f);
                 }
+                if (NLLM && live)
+                    for (int d = 0; d < D; ++d) a.em_y[((size_t)k * D + d) * NP + pidx] = vecp[src + d];
                 float an[TC_KC];   // context projection of the NEXT piece's units (loads in flight during the push)
                 {
                     const TcPiece c0 = P0[0];
@@ -492,6 +505,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                 }
                                 hv[e] = fmaxf(pre, 0.f);
                                 cm |= pre > 0.f ? (1u << (q + e)) : 0u;
+                                if (NLLM && live && q + e < c.nr) a.em_h0[((size_t)k * H0 + c.r0 + q + e) * NP + pidx] = hv[e];
                             }
                             tc_stage4(trow, q, hv);
                         } else if (q < c.nu) {   // columns of the next group inside the last K = 8 step: not known yet
@@ -522,6 +536,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                 for (int e = 0; e < 4; ++e) {
                                     const float hv = fmaxf(val[e], 0.f);
                                     rm |= val[e] > 0.f ? (1u << (q + e)) : 0u;
+                                    if (NLLM && live && q + e < r.nr) a.em_h1[((size_t)k * g.H[1] + r.r0 + q + e) * NP + pidx] = hv;
                                     const float2 hh = make_float2(hv, hv);
                                     const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)(r.u0 + q + e) * 2 * DP);
 #pragma unroll
@@ -568,15 +583,15 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                         for (int d = 0; d < D; ++d) {
                             const float u = vecp[oU + d];
                             ssq = fmaf(u, u, ssq);
-                            if (GRADM) vecp[oG + d] = a.w * u;  // d(-w log q)/d u_0
+                            if (GRADM) vecp[oG + d] = wp * u;  // d(-w log q)/d u_0
                         }
                         logq += -0.5f * ssq - (float)D * HALF_LOG_2PI;
-                        if (a.diff && live) a.diff[pidx] = MODE == TC_LOGPROB ? logq : logp - logq;
+                        if (a.diff && live) a.diff[pidx] = (MODE == TC_LOGPROB || NLLM) ? logq : logp - logq;
                     }
                 }
             } else {
                 // ===================== reverse pass of transform k =====================
-                const float w = a.w;
+                const float w = wp;
                 float yb[DP], yv[DP], sh[DP], mb[DP], sb[DP], zb[DP];
 #pragma unroll
                 for (int jj = 0; jj < DP; ++jj) {
@@ -594,12 +609,16 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                         sb[jj] = fmaf(ub * es, yin, -w);
                         yb[jj] = ub * es;
                         yv[jj] = sh[jj] = 0.f;
+                        if (NLLM && live) {   // d loss / d (mean, log-scale) of the variable this position visits, real row order
+                            a.em_o[((size_t)k * 2 * D + perm[jj]) * NP + pidx] = mb[jj];
+                            a.em_o[((size_t)k * 2 * D + D + perm[jj]) * NP + pidx] = sb[jj];
+                        }
                     } else {
                         mb[jj] = sb[jj] = yb[jj] = yv[jj] = sh[jj] = 0.f;
                     }
                 }
                 float* gAbase = a.gA + (size_t)k * H0 * a.B + b;
-                const bool emit = (seq || MODE == TC_FKL) && live;
+                const bool emit = (seq || MODE == TC_FKL || NLLM) && live;
                 // layer-1 pieces in DESCENDING order (the first push covers every accumulator column)
                 uint32_t cmn = bits1[(size_t)(np1 - 1) * a.bits_stride];
                 for (int pi = np1 - 1; pi >= 0; --pi) {
@@ -639,6 +658,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                     g2 = tc_ffma2(make_float2(wq.z, wq.w), make_float2(mb[2 * q2 + 1], sb[2 * q2 + 1]), g2);
                                 }
                                 gs[e] = ((cm >> (q + e)) & 1u) ? g2.x + g2.y : 0.f;
+                                if (NLLM && live && q + e < c.nr) a.em_a1[((size_t)k * g.H[1] + c.r0 + q + e) * NP + pidx] = gs[e];
                             }
                             tc_stage4(trow, q, gs);
                         } else if (q < c.nu) {
@@ -680,6 +700,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                         yb[4 * q4 + 3] = fmaf(w4.w, gv, yb[4 * q4 + 3]);
                                     }
                                     if (emit && on) atomicAdd(gAp + (size_t)(q + e) * a.B, gv);   // RED.ADD.F32 over the S samples of the row
+                                    if (NLLM && live && q + e < r.nr) a.em_a0[((size_t)k * H0 + r.r0 + q + e) * NP + pidx] = gv;
                                 }
                             }
                         }
@@ -695,6 +716,8 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             }
             mark(9 + kind);
         }
+        if (NLLM && live)
+            for (int d = 0; d < D; ++d) a.theta_grad[(size_t)pidx * D + d] = vecp[oG + d];
         if (MODE == TC_RSAMPLE && live) {
             for (int d = 0; d < D; ++d) a.theta_out[(size_t)pidx * D + d] = vecp[oV + K * D + d];
             if (a.diff) a.diff[pidx] = logp;
@@ -1082,7 +1105,7 @@ static int tc_build(rabi_maf* h, TcState* s) {
 template <int MODE, int DP, bool RUN>
 static int tc_launch_inst(rabi_maf* h, const TcArgs& a, int grid, int T, size_t smem, cudaStream_t st) {
     RABI_CU_OK(h, cudaFuncSetAttribute(k_tc<MODE, DP, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const bool prof = MODE == TC_GRAD || MODE == TC_FKL;
+    const bool prof = MODE == TC_GRAD || MODE == TC_FKL;   // the attack kernels are the profiled ones
     if (prof && rabi_prof_begin(h, st)) return 1;
     k_tc<MODE, DP, RUN><<<grid, T, smem, st>>>(h->img, a);
     h->launches++;
@@ -1105,6 +1128,7 @@ static int tc_launch_mode(rabi_maf* h, const TcArgs& a, int mode, bool run, int 
         case TC_FKL: return tc_launch_inst<TC_FKL, DP, false>(h, a, grid, T, smem, st);
         case TC_RSAMPLE: return tc_launch_inst<TC_RSAMPLE, DP, false>(h, a, grid, T, smem, st);
         case TC_LOGPROB: return tc_launch_inst<TC_LOGPROB, DP, false>(h, a, grid, T, smem, st);
+        case TC_NLL: return tc_launch_inst<TC_NLL, DP, false>(h, a, grid, T, smem, st);
     }
     return 2;
 }
@@ -1148,6 +1172,14 @@ static int tc_prepare(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st, T
     a.S = c.S;
     a.B = c.B;
     a.w = c.w;
+    a.wrow = c.wrow;
+    a.em_h0 = c.em_h0;
+    a.em_a0 = c.em_a0;
+    a.em_h1 = c.em_h1;
+    a.em_a1 = c.em_a1;
+    a.em_o = c.em_o;
+    a.em_y = c.em_y;
+    a.theta_grad = c.theta_grad;
     a.npairs = (long long)c.S * c.B;
     a.img = s->img + s->img_words;
     a.blk[0] = s->blk[0];
@@ -1155,7 +1187,7 @@ static int tc_prepare(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st, T
     a.blk_words = s->blk_words;
     a.region_words = s->blk_words;
     a.VS = ((4 * h->K + 2) * h->D) | 1;
-    if (mode == TC_GRAD || mode == TC_FKL) {
+    if (mode == TC_GRAD || mode == TC_FKL || mode == TC_NLL) {
         const size_t need = (size_t)2 * h->K * 2 * TC_MAXP * (size_t)h->sm_count * TC_MAXTILES * 128;
         if (need > s->bits_words) {
             if (s->bits) {
@@ -1299,6 +1331,7 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
 
 void rabi_tc_destroy(rabi_maf* h) {
     rabi_tcd_destroy(h);
+    rabi_train_destroy(h);
     TcState* s = static_cast<TcState*>(h->tc);
     if (!s) return;
     if (s->img) cudaFree(s->img);

@@ -37,6 +37,7 @@ struct rabi_maf {
     int sm_count = 148;
     int max_smem_optin = 0;
     void* tc = nullptr;        // tensor-core path state (maf_tc.cu), owned by rabi_tc_*
+    void* train = nullptr;     // training-side state (maf_train.cu): device masks, emission buffers
     void* tcd = nullptr;       // three-hidden-layer tensor-core path state (maf_tcd.cu), owned by rabi_tcd_*
     const float* row_eps = nullptr;        // optional per-row attack radii / step sizes (rabi_pgd_set_row_scales)
     const float* row_eps_iter = nullptr;

@@ -113,8 +113,10 @@ class FIMTraceRegularizer(AdditiveRegularizer):
             self._regularizer = self._regularizer_ema
 
     def _trace(self, input: Tensor, output: Distribution, mc_samples: int) -> Tensor:
-        reg = monte_carlo_fisher(self.model, input, output, mc_samples=mc_samples, create_graph=True,
-                                 retain_graph=True, typ="trace")
+        from .autograd import differentiable_only
+        with differentiable_only():   # the score is differentiated again: build the op-by-op graph straight away
+            reg = monte_carlo_fisher(self.model, input, output, mc_samples=mc_samples, create_graph=True,
+                                     retain_graph=True, typ="trace")
         if self.reduce in ("mean", "sum"):
             # mean over the finite entries without a data-dependent shape (== reg[isfinite(reg)].mean(); capturable)
             mask = torch.isfinite(reg)

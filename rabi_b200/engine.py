@@ -101,6 +101,7 @@ class MafEngine:
                                                      m.shape[0], m.shape[1]))
         self._check(self.L.rabi_maf_finalize_structure(self.h))
         self._versions = None
+        self._has_post = post_perms is not None and any(p is not None for p in post_perms)
 
     def set_weights(self, params: List[List[Tuple[torch.Tensor, torch.Tensor]]]):
         """params[k][layer] = (weight, bias) CUDA fp32 tensors; re-packs only what changed since the last call."""
@@ -148,6 +149,36 @@ class MafEngine:
             with torch.cuda.device(self.device):
                 self._check(self.L.rabi_maf_log_prob_fwd(self.h, _ptr(A), _ptr(theta), S, B, _ptr(out), self._stream()))
         return out
+
+    def fused_training_ok(self) -> bool:
+        """rabi_maf_log_prob_bwd serves two-hidden-layer conditioners (the tensor-core path's shapes) without Permute layers."""
+        import os
+        if os.environ.get("RABI_FUSED_TRAIN", "1") == "0":   # A/B switch: op-by-op differentiable path everywhere
+            return False
+        return len(self.hidden) == 2 and self.D <= 12 and max(self.hidden) <= 104 and not getattr(self, "_has_post", False)
+
+    def log_prob_bwd(self, ctx_rows: torch.Tensor, A: torch.Tensor, theta: torch.Tensor, gout: torch.Tensor,
+                     want_weights: bool = True):
+        """theta [S, B, D], ctx_rows [B, C] (after z-score / embedding), A [K, H0, B], gout [S, B] = dL/dlogq ->
+        (g_theta [S, B, D], g_A [K, H0, B], [[(g_weight, g_bias) per layer] per transform] | None); reference layouts."""
+        theta, gout, ctx_rows = _f32c(theta), _f32c(gout), _f32c(ctx_rows)
+        S, B, D = theta.shape
+        g_theta = torch.empty_like(theta)
+        g_A = torch.empty((self.K, self.hidden[0], B), device=self.device, dtype=torch.float32)
+        grads, wp, bp = None, None, None
+        if want_weights:
+            dims = [self.C + self.D] + list(self.hidden)
+            outs = list(self.hidden) + [2 * self.D]
+            grads = [[(torch.empty((outs[l], dims[l]), device=self.device, dtype=torch.float32),
+                       torch.empty((outs[l],), device=self.device, dtype=torch.float32)) for l in range(len(outs))]
+                     for _ in range(self.K)]
+            flat = [g for gk in grads for g in gk]
+            wp = (ctypes.c_void_p * len(flat))(*[g[0].data_ptr() for g in flat])
+            bp = (ctypes.c_void_p * len(flat))(*[g[1].data_ptr() for g in flat])
+        with torch.cuda.device(self.device):
+            self._check(self.L.rabi_maf_log_prob_bwd(self.h, _ptr(ctx_rows), _ptr(A), _ptr(theta), _ptr(gout), S, B, None,
+                                                     _ptr(g_theta), _ptr(g_A), wp, bp, self._stream()))
+        return g_theta, g_A, grads
 
     def rsample(self, A: torch.Tensor, z: torch.Tensor, want_logq: bool = True):
         z = _f32c(z)

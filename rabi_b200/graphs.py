@@ -54,6 +54,7 @@ class GraphedParamFunction:
         self.warmup = warmup
         self._seen: Dict[tuple, int] = {}
         self._graphs: Dict[tuple, dict] = {}
+        self._failed: set = set()
 
     def _key(self, inputs: Sequence[Tensor]):
         return (tuple((tuple(t.shape), t.dtype, t.device) for t in inputs),
@@ -62,6 +63,8 @@ class GraphedParamFunction:
     def ready(self, inputs: Sequence[Tensor]) -> bool:
         """True once this input signature has been seen ``warmup`` times (the eager calls warm every lazy init up)."""
         key = self._key(inputs)
+        if key in self._failed:
+            return False
         n = self._seen.get(key, 0)
         self._seen[key] = n + 1
         return n >= self.warmup
@@ -96,5 +99,15 @@ class GraphedParamFunction:
         key = self._key(inputs)
         st = self._graphs.get(key)
         if st is None:
-            st = self._capture(key, inputs)
+            try:
+                st = self._capture(key, inputs)
+            except RuntimeError as e:
+                # a capture can be refused for reasons outside this module (e.g. the driver loading a kernel image lazily on its
+                # first launch, which is not permitted while a stream captures): this signature then stays on the eager path
+                import warnings
+
+                warnings.warn(f"rabi_b200: CUDA-graph capture failed ({str(e).splitlines()[0][:120]}); running this segment eagerly")
+                self._failed.add(key)
+                torch.cuda.synchronize()
+                return self.fn(*inputs)
         return _Replay.apply(st, len(inputs), *inputs, *self.module.parameters())

@@ -233,8 +233,8 @@ class MAFPosterior(Distribution):
             value = u
         v, full, _ = self._flatten_value(value)
         if self._needs_grad(v):
-            from .autograd import log_prob_differentiable
-            lp = log_prob_differentiable(self, v)
+            from .autograd import log_prob_training
+            lp = log_prob_training(self, v)
         else:
             lp = self.model.engine().log_prob(self.A, v)
         lp = lp.reshape(full)

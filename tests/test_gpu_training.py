@@ -224,3 +224,73 @@ def test_graphed_nll_with_two_forwards_before_one_backward(dev):
     scale = max(float(p.grad.abs().max()) for p in m2.parameters())
     for a, b in zip(m1.parameters(), m2.parameters()):
         assert float((a.grad - b.grad).abs().max()) <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("shape", [dict(dx=100, D=4, hidden=[100, 100], B=512, S=1), dict(dx=10, D=10, hidden=[100, 100], B=130, S=1),
+                                   dict(dx=12, D=3, hidden=[64, 48], B=77, S=3), dict(dx=20, D=4, hidden=[32, 32], B=9, S=2)])
+def test_fused_log_prob_backward_equals_the_op_by_op_graph(shape, dev):
+    """rabi_maf_log_prob_bwd (k_tc<TC_NLL> + k_wgrad: gradients w.r.t. theta, x and all weights / biases in two launches, no
+    autograd graph) against the op-by-op differentiable path and the oracle's autograd, for a non-uniform upstream gradient,
+    S > 1 samples per row sharing the context, and a z-score layer; then a double backward through the fused node."""
+    from oracle import rbi_oracle as O
+    from rabi_b200 import autograd as AG
+    from tests.test_gpu_parity import _fresh
+
+    ref, model, x = _fresh(shape, dev, seed=17)
+    model.train()
+    B, S, D = shape["B"], shape["S"], shape["D"]
+    g = torch.Generator().manual_seed(3)
+    theta = torch.randn(S, B, D, generator=g) if S > 1 else torch.randn(B, D, generator=g)
+    wts = torch.rand(theta.shape[:-1], generator=g) + 0.1            # dL/dlogq differs per pair
+
+    def run(m, xin, th, w, fused):
+        for p in m.parameters():
+            p.grad = None
+        xin = xin.clone().requires_grad_()
+        th = th.clone().requires_grad_()
+        if fused is None:
+            lp = m(xin).log_prob(th)
+        elif fused:
+            lp = m(xin).log_prob(th)
+        else:
+            with AG.differentiable_only():
+                lp = m(xin).log_prob(th)
+        (-(lp * w).sum()).backward()
+        return lp.detach().cpu(), xin.grad.cpu(), th.grad.cpu(), [p.grad.detach().cpu().clone() for p in m.parameters()]
+
+    eng = model.engine()
+    n0 = eng.launches
+    fused = run(model, x.to(dev), theta.to(dev), wts.to(dev), True)
+    n_fused = eng.launches - n0
+    slow = run(model, x.to(dev), theta.to(dev), wts.to(dev), False)
+    oracle = run(ref, x, theta, wts, None)
+    assert n_fused <= 8, n_fused     # projection, log-prob, negate, per-pair kernel, weight products, back-projection (+ packs)
+    for name, other in (("op-by-op path", slow), ("oracle autograd", oracle)):
+        assert rel_err(fused[0], other[0]) < RTOL
+        assert rel_err(fused[1], other[1]) < RTOL, f"d/dx vs {name}"
+        assert rel_err(fused[2], other[2]) < RTOL, f"d/dtheta vs {name}"
+        scale = max(float(t.abs().max()) for t in other[3])
+        for a, b in zip(fused[3], other[3]):
+            assert a.shape == b.shape
+            assert float((a - b).abs().max()) <= RTOL * scale, f"weight gradient vs {name}"
+    # masked entries receive exact zeros (autograd of weight * mask)
+    grads = dict(zip([n for n, _ in model.named_parameters()], fused[3]))
+    for n, gval in grads.items():
+        if n.endswith(".weight"):
+            mask = dict(model.named_buffers())[n[:-6] + "mask"].cpu()
+            assert float(gval[mask == 0].abs().max() if (mask == 0).any() else 0.0) == 0.0
+    # double backward through the fused node falls back to the differentiable graph
+    for p in model.parameters():
+        p.grad = None
+    xin = x.to(dev).clone().requires_grad_()
+    lp = model(xin).log_prob(theta.to(dev))
+    (score,) = torch.autograd.grad(lp.sum(), xin, create_graph=True)
+    (score ** 2).sum().backward()
+    xr = x.clone().requires_grad_()
+    (score_r,) = torch.autograd.grad(ref(xr).log_prob(theta).sum(), xr, create_graph=True)
+    for p in ref.parameters():
+        p.grad = None
+    (score_r ** 2).sum().backward()
+    scale = max(float(p.grad.abs().max()) for p in ref.parameters())
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert float((a.grad.cpu() - b.grad).abs().max()) <= 5 * RTOL * scale
