@@ -131,6 +131,16 @@ int rabi_maf_log_prob_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_de
                           const float* gout_dev, int S, int B, float* logq_dev, float* g_theta_dev, float* g_A_dev,
                           float* const* g_weight_dev, float* const* g_bias_dev, rabi_stream_t s);
 
+/* Reverse of the reparameterised sampling chain (TransformedDistribution.rsample, rbi/rbi/models/base.py:417-446, as
+ * differentiated by the TRADES regulariser, rbi/rbi/defenses/trades_regularizers.py:58-64, and by the Fisher regulariser's path
+ * through its samples, rbi/rbi/utils/fisher_info.py:213-221): for base noise z_dev [S,B,D], theta = T(z; x, W) and its own
+ * log-density, and upstream gradients g_theta_dev [S,B,D] = dL/dtheta, g_logq_dev [S,B] = dL/dlog q(theta), writes theta_dev /
+ * logq_dev (optional: the forward values), g_A_dev [K,H0,B] (optional) and the weight / bias gradients exactly as
+ * rabi_maf_log_prob_bwd does.  Same shape restrictions. */
+int rabi_maf_rsample_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev,
+                         const float* g_theta_dev, const float* g_logq_dev, int S, int B, float* theta_dev, float* logq_dev,
+                         float* g_A_dev, float* const* g_weight_dev, float* const* g_bias_dev, rabi_stream_t s);
+
 /* Per-row attack radii for batched eps-sweeps (config/experiment/eval_l2_pyloric.yaml:13-16 sweeps eps over 6 values;
  * run_rob_eval.py:115-140 derives eps_abs and eps_iter per value): rows x eps values are independent, so one call can attack
  * the rows at all radii at once.  While set, every rabi_*_pgd_step / rabi_*_pgd_run / rabi_pgd_update on this handle uses

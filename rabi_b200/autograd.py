@@ -208,6 +208,11 @@ def log_prob_differentiable(post, v: Tensor) -> Tensor:
 
 # ----------------------------------------------------------------------------------------------- sampling pass
 def rsample_differentiable(post, z: Tensor) -> Tuple[Tensor, Tensor]:
+    """Public name of the op-by-op (any-order differentiable) sampling pass."""
+    return _rsample_ops(post, z)
+
+
+def _rsample_ops(post, z: Tensor) -> Tuple[Tensor, Tensor]:
     """z [S, Bf, D] -> (theta [S, Bf, D], log q(theta) [S, Bf]); one pass-equivalent per transform."""
     model = post.model
     st = _struct(model)
@@ -321,6 +326,55 @@ class _FusedLogProb(torch.autograd.Function):
             flat = [t for gk in grads for wb in gk for t in wb]
             flat = [t if n else None for t, n in zip(flat, need[3:])]
         return (None, g_v if need[1] else None, g_ctx) + tuple(flat)
+
+
+class _FusedRSample(torch.autograd.Function):
+    """theta, log q(theta) = rsample(z) whose backward is ``rabi_maf_rsample_bwd`` (sampling chain + its reverse on the tensor
+    cores, one launch for the weight-gradient products); a differentiable backward hands over to ``rsample_differentiable``."""
+
+    @staticmethod
+    def forward(ctx, post, z, ctx_in, *params):
+        ctx.post = post
+        ctx.save_for_backward(z, ctx_in)
+        theta, logq = post.model.engine().rsample(post.A, z, want_logq=True)
+        return theta, logq
+
+    @staticmethod
+    def backward(ctx, g_theta, g_logq):
+        post = ctx.post
+        z, ctx_in = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        params = _params(post.model)
+        if g_theta is None:
+            g_theta = torch.zeros_like(z)
+        if g_logq is None:
+            g_logq = torch.zeros(z.shape[:-1], device=z.device, dtype=z.dtype)
+        if torch.is_grad_enabled():
+            with torch.enable_grad():
+                theta, logq = _rsample_ops(post, z)
+                wanted = [t for t, n in zip([z, post.ctx_in] + params, need[1:]) if n]
+                got = iter(torch.autograd.grad([theta, logq], wanted, [g_theta, g_logq], create_graph=True, allow_unused=True))
+            return (None,) + tuple(next(got) if n else None for n in need[1:])
+        if need[1]:
+            raise NotImplementedError("gradient w.r.t. the base noise is not provided by the fused sampling backward")
+        eng = post.model.engine()
+        want_w = any(need[3:])
+        g_A, grads = eng.rsample_bwd(_context(post).detach(), post.A, z.detach(), g_theta.detach(), g_logq.detach(),
+                                     want_weights=want_w)
+        g_ctx = eng.ctx_project_bwd(g_A, post.zscore[1] if post.zscore is not None else None) if need[2] else None
+        flat = [None] * len(params)
+        if want_w:
+            flat = [t for gk in grads for wb in gk for t in wb]
+            flat = [t if n else None for t, n in zip(flat, need[3:])]
+        return (None, None, g_ctx) + tuple(flat)
+
+
+def rsample_training(post, z: Tensor) -> Tuple[Tensor, Tensor]:
+    """Entry point of ``MAFPosterior.rsample`` when gradients are needed."""
+    eng = post.model.engine()
+    if _force_differentiable or not eng.fused_training_ok() or z.numel() == 0 or z.requires_grad:
+        return _rsample_ops(post, z)
+    return _FusedRSample.apply(post, z, post.ctx_in, *_params(post.model))
 
 
 def _log_prob_graph(post, v: Tensor) -> Tensor:

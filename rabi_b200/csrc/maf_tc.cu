@@ -180,8 +180,10 @@ __device__ __forceinline__ void tc_stage4(uint32_t trow, int q, const float (&v)
 template <int MODE, int DP, bool RUN>
 __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, const TcArgs a) {
     extern __shared__ __align__(128) float sm[];
-    constexpr bool GRADM = MODE == TC_GRAD || MODE == TC_FKL || MODE == TC_NLL;
+    constexpr bool GRADM = MODE == TC_GRAD || MODE == TC_FKL || MODE == TC_NLL || MODE == TC_RSB;
     constexpr bool NLLM = MODE == TC_NLL;
+    constexpr bool RSBM = MODE == TC_RSB;
+    constexpr bool EMITM = NLLM || RSBM;   // training side: per-pair vectors for the weight-gradient products are written out
     static_assert(!RUN || (MODE == TC_GRAD || MODE == TC_FKL), "the persistent attack exists for the two attack losses only");
     float* Wb = sm;                                   // the resident (transform, orientation) block
     const int* Wi = reinterpret_cast<const int*>(sm);
@@ -414,12 +416,15 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                 ssq = fmaf(zv, zv, ssq);
             }
             logp = (MODE == TC_LOGPROB || NLLM) ? 0.f : -0.5f * ssq - (float)D * HALF_LOG_2PI;
+            if (RSBM)
+                for (int d = 0; d < D; ++d) vecp[oG + d] = live ? a.theta_grad[(size_t)pidx * D + d] : 0.f;
         }
-        const int nphase = (MODE == TC_GRAD ? 4 : (MODE == TC_FKL || NLLM) ? 3 : MODE == TC_RSAMPLE ? 1 : 2) * K;
+        const int nphase = ((MODE == TC_GRAD || RSBM) ? 4 : (MODE == TC_FKL || NLLM) ? 3 : MODE == TC_RSAMPLE ? 1 : 2) * K;
         const float wp = a.wrow ? (live ? a.wrow[pidx] : 0.f) : a.w;   // weight of this pair in the loss
         const size_t NP = (size_t)a.npairs;
         for (int ph = ((MODE == TC_LOGPROB || NLLM) ? K : 0); ph < nphase; ++ph) {
             const int kind = ph / K;
+            if (RSBM && (kind == 1 || kind == 2)) continue;   // sampling chain and its reverse only
             const int idx = ph - kind * K;
             const int k = (kind == 0 || kind == 2) ? idx : K - 1 - idx;
             const bool seq = (kind == 0 || kind == 3);
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                 }
                                 hv[e] = fmaxf(pre, 0.f);
                                 cm |= pre > 0.f ? (1u << (q + e)) : 0u;
-                                if (NLLM && live && q + e < c.nr) a.em_h0[((size_t)k * H0 + c.r0 + q + e) * NP + pidx] = hv[e];
+                                if (EMITM && live && q + e < c.nr) a.em_h0[((size_t)k * H0 + c.r0 + q + e) * NP + pidx] = hv[e];
                             }
                             tc_stage4(trow, q, hv);
                         } else if (q < c.nu) {   // columns of the next group inside the last K = 8 step: not known yet
@@ -536,7 +541,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                 for (int e = 0; e < 4; ++e) {
                                     const float hv = fmaxf(val[e], 0.f);
                                     rm |= val[e] > 0.f ? (1u << (q + e)) : 0u;
-                                    if (NLLM && live && q + e < r.nr) a.em_h1[((size_t)k * g.H[1] + r.r0 + q + e) * NP + pidx] = hv;
+                                    if (EMITM && live && q + e < r.nr) a.em_h1[((size_t)k * g.H[1] + r.r0 + q + e) * NP + pidx] = hv;
                                     const float2 hh = make_float2(hv, hv);
                                     const float4* wo = reinterpret_cast<const float4*>(WoT + (size_t)(r.u0 + q + e) * 2 * DP);
 #pragma unroll
@@ -568,6 +573,8 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                         vecp[oV + (k + 1) * D + permy[j]] = yj;
                     }
                 }
+                if (seq && RSBM && live)
+                    for (int d = 0; d < D; ++d) a.em_y[((size_t)k * D + d) * NP + pidx] = vecp[oV + (k + 1) * D + d];
                 if (!seq) {  // u_k = exp(clamp(s)) * u_{k+1} + m
 #pragma unroll
                     for (int jj = 0; jj < DP; ++jj) {
@@ -641,6 +648,10 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                             mb[jj] = jj == j ? -zbj : mb[jj];
                             sb[jj] = jj == j ? fmaf(-ybj, yj, w) : sb[jj];
                         }
+                        if (RSBM && live) {
+                            a.em_o[((size_t)k * 2 * D + perm[j]) * NP + pidx] = -zbj;
+                            a.em_o[((size_t)k * 2 * D + D + perm[j]) * NP + pidx] = fmaf(-ybj, yj, w);
+                        }
                     }
                     // ---- layer-1 cotangents of the piece: g = relu'(.) * (WoT[v] . (mbar, sbar)), staged as (hi, lo)
 #pragma unroll
@@ -658,7 +669,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                     g2 = tc_ffma2(make_float2(wq.z, wq.w), make_float2(mb[2 * q2 + 1], sb[2 * q2 + 1]), g2);
                                 }
                                 gs[e] = ((cm >> (q + e)) & 1u) ? g2.x + g2.y : 0.f;
-                                if (NLLM && live && q + e < c.nr) a.em_a1[((size_t)k * g.H[1] + c.r0 + q + e) * NP + pidx] = gs[e];
+                                if (EMITM && live && q + e < c.nr) a.em_a1[((size_t)k * g.H[1] + c.r0 + q + e) * NP + pidx] = gs[e];
                             }
                             tc_stage4(trow, q, gs);
                         } else if (q < c.nu) {
@@ -700,7 +711,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                         yb[4 * q4 + 3] = fmaf(w4.w, gv, yb[4 * q4 + 3]);
                                     }
                                     if (emit && on) atomicAdd(gAp + (size_t)(q + e) * a.B, gv);   // RED.ADD.F32 over the S samples of the row
-                                    if (NLLM && live && q + e < r.nr) a.em_a0[((size_t)k * H0 + r.r0 + q + e) * NP + pidx] = gv;
+                                    if (EMITM && live && q + e < r.nr) a.em_a0[((size_t)k * H0 + r.r0 + q + e) * NP + pidx] = gv;
                                 }
                             }
                         }
@@ -718,8 +729,9 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
         }
         if (NLLM && live)
             for (int d = 0; d < D; ++d) a.theta_grad[(size_t)pidx * D + d] = vecp[oG + d];
-        if (MODE == TC_RSAMPLE && live) {
-            for (int d = 0; d < D; ++d) a.theta_out[(size_t)pidx * D + d] = vecp[oV + K * D + d];
+        if ((MODE == TC_RSAMPLE || RSBM) && live) {
+            if (a.theta_out)
+                for (int d = 0; d < D; ++d) a.theta_out[(size_t)pidx * D + d] = vecp[oV + K * D + d];
             if (a.diff) a.diff[pidx] = logp;
         }
         if constexpr (RUN) {
@@ -1129,6 +1141,7 @@ static int tc_launch_mode(rabi_maf* h, const TcArgs& a, int mode, bool run, int 
         case TC_RSAMPLE: return tc_launch_inst<TC_RSAMPLE, DP, false>(h, a, grid, T, smem, st);
         case TC_LOGPROB: return tc_launch_inst<TC_LOGPROB, DP, false>(h, a, grid, T, smem, st);
         case TC_NLL: return tc_launch_inst<TC_NLL, DP, false>(h, a, grid, T, smem, st);
+        case TC_RSB: return tc_launch_inst<TC_RSB, DP, false>(h, a, grid, T, smem, st);
     }
     return 2;
 }
@@ -1187,7 +1200,7 @@ static int tc_prepare(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st, T
     a.blk_words = s->blk_words;
     a.region_words = s->blk_words;
     a.VS = ((4 * h->K + 2) * h->D) | 1;
-    if (mode == TC_GRAD || mode == TC_FKL || mode == TC_NLL) {
+    if (mode == TC_GRAD || mode == TC_FKL || mode == TC_NLL || mode == TC_RSB) {
         const size_t need = (size_t)2 * h->K * 2 * TC_MAXP * (size_t)h->sm_count * TC_MAXTILES * 128;
         if (need > s->bits_words) {
             if (s->bits) {

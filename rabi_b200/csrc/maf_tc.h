@@ -5,7 +5,7 @@
 namespace rabi {
 
 // same numbering as FastMode (maf_fast.cuh)
-enum TcMode { TC_FWD = 0, TC_GRAD = 1, TC_FKL = 2, TC_RSAMPLE = 3, TC_LOGPROB = 4, TC_NLL = 5 };
+enum TcMode { TC_FWD = 0, TC_GRAD = 1, TC_FKL = 2, TC_RSAMPLE = 3, TC_LOGPROB = 4, TC_NLL = 5, TC_RSB = 6 };
 
 struct TcCall {
     const float* A_p;   // [K,H0,B] projection of the sampled-from posterior (LOGPROB: unused)
@@ -26,7 +26,9 @@ struct TcCall {
     float* em_a1;
     float* em_o;        // [K][2D][P] d loss / d (mean, log-scale) outputs, REAL row order (row d = mean of theta_d, D + d = log-scale)
     float* em_y;        // [K][D][P]  theta-side input of transform k, real index order
-    float* theta_grad;  // [P][D]     d loss / d theta
+    float* theta_grad;  // [P][D]     TC_NLL: d loss / d theta (out);  TC_RSB: d loss / d theta_sample (in)
+    // TC_RSB (reverse of the reparameterised sampling chain): z = base noise, A_p = the projection, loss = sum_p
+    // <theta_grad_p, theta_p> + wrow_p log q(theta_p); the same per-pair vectors are emitted (em_y = the transforms' outputs)
 };
 
 // The whole L2-PGD attack (nb_iter iterations) as one persistent launch (two-hidden-layer conditioners, identity / z-score

@@ -138,10 +138,13 @@ void rabi_train_destroy(rabi_maf* h) {
     h->train = nullptr;
 }
 
+// Common body of the two training-side entry points.
+//   mode TC_NLL: in = theta, gout = dL/dlogq, logq / g_theta optional outputs;
+//   mode TC_RSB: in = base noise z, gout = dL/dlogq(own sample), g_theta_in = dL/dtheta_sample, theta_out / logq optional outputs.
 // 0 = done, 1 = error, 2 = this shape is not served by the fused training path (the caller keeps its autograd path)
-int rabi_train_log_prob_bwd(rabi_maf* h, const float* ctx, const float* A, const float* theta, const float* gout, int S, int B,
-                            float* logq, float* g_theta, float* g_A, float* const* g_weight, float* const* g_bias,
-                            cudaStream_t st) {
+static int train_bwd(rabi_maf* h, int mode, const float* ctx, const float* A, const float* in, const float* gout,
+                     const float* g_theta_in, int S, int B, float* theta_out, float* logq, float* g_theta, float* g_A,
+                     float* const* g_weight, float* const* g_bias, cudaStream_t st) {
     if (h->L != 2) return 2;
     for (int k = 0; k < h->K; ++k)
         if (!h->post[k].empty()) return 2;   // Permute layers between the transforms: index bookkeeping not done here
@@ -162,7 +165,7 @@ int rabi_train_log_prob_bwd(rabi_maf* h, const float* ctx, const float* A, const
     }
     // emission buffers: h0, a0bar [K][H0][P]; h1, a1bar [K][H1][P]; obar [K][2D][P]; y [K][D][P]; w [P]
     const size_t n0 = (size_t)K * H0 * P, n1 = (size_t)K * H1 * P, no = (size_t)K * 2 * D * P, ny = (size_t)K * D * P;
-    const size_t need = 2 * n0 + 2 * n1 + no + ny + P + (g_A ? 0 : (size_t)K * H0 * B) + (g_theta ? 0 : P * D);
+    const size_t need = 2 * n0 + 2 * n1 + no + ny + P + (size_t)K * H0 * B + P * D;
     if (need > s->ws_floats) {
         if (s->ws) {
             RABI_CU_OK(h, cudaDeviceSynchronize());
@@ -181,29 +184,35 @@ int rabi_train_log_prob_bwd(rabi_maf* h, const float* ctx, const float* A, const
     float* em_y = em_o + no;
     float* wrow = em_y + ny;
     float* gA = g_A ? g_A : wrow + P;
-    float* gth = g_theta ? g_theta : gA + (g_A ? 0 : (size_t)K * H0 * B);
+    float* gth = g_theta ? g_theta : wrow + P + (size_t)K * H0 * B;
     // the kernel differentiates  - sum_p w_p log q_p : w = - dL / d log q
     RABI_CU_OK(h, cudaMemsetAsync(gA, 0, (size_t)K * H0 * B * sizeof(float), st));
-    k_negate<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(gout, wrow, P);
-    h->launches++;
     TcCall c = {};
-    c.A_p = nullptr;
-    c.A_q = A;
-    c.z = theta;
+    if (mode == TC_NLL) {   // the kernel differentiates - sum_p w_p log q_p
+        k_negate<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(gout, wrow, P);
+        h->launches++;
+        c.A_q = A;
+        c.wrow = wrow;
+    } else {                // ... and, for the sampling chain, + sum_p (<g_theta_p, theta_p> + w_p log q_p)
+        c.A_p = A;
+        c.A_q = A;
+        c.wrow = gout;
+        c.theta_out = theta_out;
+    }
+    c.z = in;
     c.diff = logq;
     c.gA = gA;
     c.S = S;
     c.B = B;
     c.w = 0.f;
-    c.wrow = wrow;
     c.em_h0 = em_h0;
     c.em_a0 = em_a0;
     c.em_h1 = em_h1;
     c.em_a1 = em_a1;
     c.em_o = em_o;
     c.em_y = em_y;
-    c.theta_grad = gth;
-    const int rc = rabi_tc_launch(h, c, TC_NLL, st);
+    c.theta_grad = mode == TC_NLL ? gth : const_cast<float*>(g_theta_in);
+    const int rc = rabi_tc_launch(h, c, mode, st);
     if (rc) return rc;
     if (!g_weight) return 0;
     // ---- all weight-gradient products in one launch
@@ -257,7 +266,28 @@ int rabi_train_log_prob_bwd(rabi_maf* h, const float* ctx, const float* A, const
     return 0;
 }
 
+int rabi_train_log_prob_bwd(rabi_maf* h, const float* ctx, const float* A, const float* theta, const float* gout, int S, int B,
+                            float* logq, float* g_theta, float* g_A, float* const* g_weight, float* const* g_bias,
+                            cudaStream_t st) {
+    return train_bwd(h, TC_NLL, ctx, A, theta, gout, nullptr, S, B, nullptr, logq, g_theta, g_A, g_weight, g_bias, st);
+}
+
 }  // namespace rabi
+
+extern "C" int rabi_maf_rsample_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev,
+                                    const float* g_theta_dev, const float* g_logq_dev, int S, int B, float* theta_dev,
+                                    float* logq_dev, float* g_A_dev, float* const* g_weight_dev, float* const* g_bias_dev,
+                                    rabi_stream_t s) {
+    if (!h) return 1;
+    if (!h->finalized) return rabi_fail(h, "rabi_maf_finalize_structure was not called");
+    if (cudaSetDevice(h->device) != cudaSuccess) return rabi_fail(h, "cudaSetDevice failed");
+    if (S <= 0 || B <= 0) return 0;
+    const int rc = rabi::train_bwd(h, rabi::TC_RSB, ctx_dev, A_dev, z_dev, g_logq_dev, g_theta_dev, S, B, theta_dev, logq_dev,
+                                   nullptr, g_A_dev, g_weight_dev, g_bias_dev, (cudaStream_t)s);
+    if (rc == 2) return rabi_fail(h, "rabi_maf_rsample_bwd serves two-hidden-layer conditioners (up to 120 padded units, D <= 12) "
+                                     "without Permute layers; use the differentiable path for this model");
+    return rc;
+}
 
 extern "C" int rabi_maf_log_prob_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* theta_dev,
                                      const float* gout_dev, int S, int B, float* logq_dev, float* g_theta_dev, float* g_A_dev,

@@ -180,6 +180,28 @@ class MafEngine:
                                                      _ptr(g_theta), _ptr(g_A), wp, bp, self._stream()))
         return g_theta, g_A, grads
 
+    def rsample_bwd(self, ctx_rows: torch.Tensor, A: torch.Tensor, z: torch.Tensor, g_theta: torch.Tensor,
+                    g_logq: torch.Tensor, want_weights: bool = True):
+        """Reverse of theta, log q = rsample(z): upstream g_theta [S, B, D], g_logq [S, B] ->
+        (g_A [K, H0, B], [[(g_weight, g_bias) per layer] per transform] | None)."""
+        z, g_theta, g_logq, ctx_rows = _f32c(z), _f32c(g_theta), _f32c(g_logq), _f32c(ctx_rows)
+        S, B, D = z.shape
+        g_A = torch.empty((self.K, self.hidden[0], B), device=self.device, dtype=torch.float32)
+        grads, wp, bp = None, None, None
+        if want_weights:
+            dims = [self.C + self.D] + list(self.hidden)
+            outs = list(self.hidden) + [2 * self.D]
+            grads = [[(torch.empty((outs[l], dims[l]), device=self.device, dtype=torch.float32),
+                       torch.empty((outs[l],), device=self.device, dtype=torch.float32)) for l in range(len(outs))]
+                     for _ in range(self.K)]
+            flat = [g for gk in grads for g in gk]
+            wp = (ctypes.c_void_p * len(flat))(*[g[0].data_ptr() for g in flat])
+            bp = (ctypes.c_void_p * len(flat))(*[g[1].data_ptr() for g in flat])
+        with torch.cuda.device(self.device):
+            self._check(self.L.rabi_maf_rsample_bwd(self.h, _ptr(ctx_rows), _ptr(A), _ptr(z), _ptr(g_theta), _ptr(g_logq), S, B,
+                                                    None, None, _ptr(g_A), wp, bp, self._stream()))
+        return g_A, grads
+
     def rsample(self, A: torch.Tensor, z: torch.Tensor, want_logq: bool = True):
         z = _f32c(z)
         S, B, _ = z.shape

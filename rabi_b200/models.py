@@ -197,8 +197,8 @@ class MAFPosterior(Distribution):
         S = int(sample_shape.numel())
         z = noise.standard_normal(sample_shape + self.batch_shape + (D,), self.ctx_in.device).reshape(S, Bf, D)
         if self._needs_grad():
-            from .autograd import rsample_differentiable
-            theta, logq = rsample_differentiable(self, z)
+            from .autograd import rsample_training
+            theta, logq = rsample_training(self, z)
         else:
             theta, logq = self.model.engine().rsample(self.A, z, want_logq=True)
         out = theta.reshape(sample_shape + self.batch_shape + (D,))

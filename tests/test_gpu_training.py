@@ -294,3 +294,57 @@ def test_fused_log_prob_backward_equals_the_op_by_op_graph(shape, dev):
     scale = max(float(p.grad.abs().max()) for p in ref.parameters())
     for a, b in zip(model.parameters(), ref.parameters()):
         assert float((a.grad.cpu() - b.grad).abs().max()) <= 5 * RTOL * scale
+
+
+@pytest.mark.parametrize("shape", [dict(dx=100, D=4, hidden=[100, 100], B=512, S=1), dict(dx=10, D=10, hidden=[100, 100], B=130, S=2),
+                                   dict(dx=12, D=3, hidden=[64, 48], B=77, S=3)])
+def test_fused_rsample_backward_equals_the_op_by_op_graph(shape, dev):
+    """rabi_maf_rsample_bwd (k_tc<TC_RSB> + k_wgrad: the reverse of the reparameterised sampling chain with weight / bias / x
+    gradients in two launches) against the op-by-op differentiable path and the oracle's autograd, for a loss that uses both the
+    samples and their log-density with non-uniform weights."""
+    from oracle import rbi_oracle as O
+    from rabi_b200 import autograd as AG
+    from rabi_b200 import noise
+    from tests.test_gpu_parity import _fresh
+
+    ref, model, x = _fresh(shape, dev, seed=19)
+    model.train()
+    B, S, D = shape["B"], shape["S"], shape["D"]
+    g = torch.Generator().manual_seed(4)
+    z = torch.randn(S, B, D, generator=g)
+    c_theta = torch.randn(S, B, D, generator=g)
+    c_logq = torch.rand(S, B, generator=g) + 0.2
+
+    def run(m, xin, fused, device):
+        for p in m.parameters():
+            p.grad = None
+        xin = xin.clone().requires_grad_()
+        if fused is None:
+            with O.injected_base_noise([z]):
+                q = m(xin)
+                th = q.rsample((S,))
+                lq = q.log_prob(th)
+        else:
+            ctxm = AG.differentiable_only() if not fused else None
+            if ctxm:
+                ctxm.__enter__()
+            try:
+                with noise.injected([z.to(device)]):
+                    q = m(xin)
+                    th = q.rsample((S,))
+                    lq = q.log_prob(th)          # the free log-density of the fresh sample (same object): no second pass
+            finally:
+                if ctxm:
+                    ctxm.__exit__(None, None, None)
+        ((th * c_theta.to(device)).sum() + (lq * c_logq.to(device)).sum()).backward()
+        return th.detach().cpu(), lq.detach().cpu(), xin.grad.cpu(), [p.grad.detach().cpu().clone() for p in m.parameters()]
+
+    fused = run(model, x.to(dev), True, dev)
+    slow = run(model, x.to(dev), False, dev)
+    oracle = run(ref, x, None, "cpu")
+    for name, other in (("op-by-op path", slow), ("oracle autograd", oracle)):
+        assert rel_err(fused[0], other[0]) < RTOL and rel_err(fused[1], other[1]) < RTOL
+        assert rel_err(fused[2], other[2]) < RTOL, f"d/dx vs {name}"
+        scale = max(float(t.abs().max()) for t in other[3])
+        for a, b in zip(fused[3], other[3]):
+            assert float((a - b).abs().max()) <= RTOL * scale, f"weight gradient vs {name}"
