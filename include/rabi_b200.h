@@ -141,6 +141,16 @@ int rabi_maf_rsample_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev
                          const float* g_theta_dev, const float* g_logq_dev, int S, int B, float* theta_dev, float* logq_dev,
                          float* g_A_dev, float* const* g_weight_dev, float* const* g_bias_dev, rabi_stream_t s);
 
+/* Fisher-information trace of q(theta | x) w.r.t. the observation, MC score estimator (rbi/rbi/utils/fisher_info.py:185-280,
+ * method "score_based", typ "trace"; the quantity FIMTraceRegularizer penalises, rbi/rbi/defenses/fisher_regularization.py:67-95):
+ *   theta_s = T(z_s; x_b) (sampling chain), score_{s,b} = d log q(theta_s | x_b) / d x_b (density passes, their reverse and the
+ *   back-projection with every (s, b) pair as a row), trace_b = mean_s ||score_{s,b}||^2 -- four launch groups, no autograd.
+ * ctx_dev [B,C] context rows (after z-score / embedding), A_dev [K,H0,B] their projection, z_dev [S,B,D] base noise,
+ * zs_std_dev [C] or NULL (the z-score's 1/std of the back-projection); outputs trace_dev [B] (optional), score_dev [S,B,C],
+ * theta_dev [S,B,D] (both required: they double as workspace).  Same shape restrictions as rabi_maf_log_prob_bwd. */
+int rabi_fisher_trace_fwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev, const float* zs_std_dev,
+                          int S, int B, float* trace_dev, float* score_dev, float* theta_dev, rabi_stream_t s);
+
 /* Per-row attack radii for batched eps-sweeps (config/experiment/eval_l2_pyloric.yaml:13-16 sweeps eps over 6 values;
  * run_rob_eval.py:115-140 derives eps_abs and eps_iter per value): rows x eps values are independent, so one call can attack
  * the rows at all radii at once.  While set, every rabi_*_pgd_step / rabi_*_pgd_run / rabi_pgd_update on this handle uses

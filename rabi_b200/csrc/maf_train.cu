@@ -113,6 +113,11 @@ __global__ void __launch_bounds__(256) k_wgrad(const WgArgs a) {
     if (d.bias && n0 == 0 && threadIdx.x < WG_TM && m0 + (int)threadIdx.x < d.M) atomicAdd(d.bias + m0 + threadIdx.x, bsum);
 }
 
+__global__ void k_fill(float* __restrict__ out, float v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
 __global__ void k_negate(const float* __restrict__ in, float* __restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = -in[i];
@@ -144,7 +149,7 @@ void rabi_train_destroy(rabi_maf* h) {
 // 0 = done, 1 = error, 2 = this shape is not served by the fused training path (the caller keeps its autograd path)
 static int train_bwd(rabi_maf* h, int mode, const float* ctx, const float* A, const float* in, const float* gout,
                      const float* g_theta_in, int S, int B, float* theta_out, float* logq, float* g_theta, float* g_A,
-                     float* const* g_weight, float* const* g_bias, cudaStream_t st) {
+                     float* const* g_weight, float* const* g_bias, cudaStream_t st, float** em_a0_out = nullptr) {
     if (h->L != 2) return 2;
     for (int k = 0; k < h->K; ++k)
         if (!h->post[k].empty()) return 2;   // Permute layers between the transforms: index bookkeeping not done here
@@ -185,6 +190,7 @@ static int train_bwd(rabi_maf* h, int mode, const float* ctx, const float* A, co
     float* wrow = em_y + ny;
     float* gA = g_A ? g_A : wrow + P;
     float* gth = g_theta ? g_theta : wrow + P + (size_t)K * H0 * B;
+    if (em_a0_out) *em_a0_out = em_a0;
     // the kernel differentiates  - sum_p w_p log q_p : w = - dL / d log q
     RABI_CU_OK(h, cudaMemsetAsync(gA, 0, (size_t)K * H0 * B * sizeof(float), st));
     TcCall c = {};
@@ -273,6 +279,58 @@ int rabi_train_log_prob_bwd(rabi_maf* h, const float* ctx, const float* A, const
 }
 
 }  // namespace rabi
+
+// trace[b] = (1/S) sum_s ||score[s, b, :]||^2 ; one warp per row
+__global__ void k_score_trace(const float* __restrict__ score, int S, int B, int C, float* __restrict__ trace) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= B) return;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float* r = score + ((size_t)s * B + row) * C;
+        for (int c = lane; c < C; c += 32) acc = fmaf(r[c], r[c], acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) trace[row] = acc / (float)S;
+}
+
+extern "C" int rabi_fisher_trace_fwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev,
+                                     const float* zs_std_dev, int S, int B, float* trace_dev, float* score_dev,
+                                     float* theta_dev, rabi_stream_t s) {
+    if (!h) return 1;
+    if (!h->finalized) return rabi_fail(h, "rabi_maf_finalize_structure was not called");
+    if (cudaSetDevice(h->device) != cudaSuccess) return rabi_fail(h, "cudaSetDevice failed");
+    if (S <= 0 || B <= 0) return 0;
+    if (!score_dev || !theta_dev) return rabi_fail(h, "rabi_fisher_trace_fwd: score_dev [S,B,C] and theta_dev [S,B,D] are required");
+    cudaStream_t st = (cudaStream_t)s;
+    // 1. theta_s = T(z_s; x): the sampling chain
+    int rc = rabi_maf_rsample_fwd(h, A_dev, z_dev, S, B, theta_dev, nullptr, s);
+    if (rc) return rc;
+    // 2. per pair: density passes + their reverse for L = sum_p log q(theta_p | x_b): d L / d (layer-0 pre-activations)
+    const size_t P = (size_t)S * B;
+    float* ones = nullptr;   // dL/dlogq = 1: reuse the score buffer's head (overwritten by step 3)
+    if ((size_t)h->C < 1) return 1;
+    ones = score_dev;
+    rabi::k_fill<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(ones, 1.f, P);
+    h->launches++;
+    float* em_a0 = nullptr;
+    rc = rabi::train_bwd(h, rabi::TC_NLL, ctx_dev, A_dev, theta_dev, ones, nullptr, S, B, nullptr, nullptr, nullptr, nullptr, nullptr,
+                         nullptr, st, &em_a0);
+    if (rc == 2) return rabi_fail(h, "rabi_fisher_trace_fwd serves two-hidden-layer conditioners (up to 120 padded units, D <= 12) "
+                                     "without Permute layers");
+    if (rc) return rc;
+    // 3. score_p = d log q / d x = (1/std) W0c^T a0bar_p, every pair a row of the back-projection
+    rc = rabi_maf_ctx_project_bwd(h, em_a0, zs_std_dev, (int)P, score_dev, s);
+    if (rc) return rc;
+    // 4. tr F(x_b) ~= mean_s ||score_{s,b}||^2
+    if (trace_dev) {
+        k_score_trace<<<(B + 3) / 4, 128, 0, st>>>(score_dev, S, B, h->C, trace_dev);
+        h->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return rabi_fail(h, "rabi_fisher_trace_fwd launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
 
 extern "C" int rabi_maf_rsample_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev,
                                     const float* g_theta_dev, const float* g_logq_dev, int S, int B, float* theta_dev,

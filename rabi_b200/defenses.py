@@ -150,10 +150,10 @@ class FIMTraceRegularizer(AdditiveRegularizer):
         if shared is None or shared["key"] != (input.device, tuple(id(p) for p in params)):
             shared = self._ema_static = {"key": (input.device, tuple(id(p) for p in params)),
                                          "t": torch.zeros((), device=input.device),
-                                         "m": [m.detach().clone() for m in self.ema._x_old]}
+                                         "m": [m.detach().clone() for m in self.ema.state]}
             self._graphs = {}
-        if self.ema._x_old is not shared["m"]:   # an eager step ran in between: take its state over
-            for m_s, m_h in zip(shared["m"], self.ema._x_old):
+        if self.ema.state is not shared["m"]:   # an eager step ran in between: take its state over
+            for m_s, m_h in zip(shared["m"], self.ema.state):
                 m_s.copy_(m_h.detach())
         shared["t"].fill_(float(self.ema.t))
         st = self._graphs.get(key)
@@ -191,7 +191,7 @@ class FIMTraceRegularizer(AdditiveRegularizer):
         st["z"].normal_()
         st["graph"].replay()
         self.ema.t += 1
-        self.ema._x_old = shared["m"]
+        self.ema.state = shared["m"]
         for p, g_ in zip(params, st["grads"]):
             p.grad = g_
         if self.grad_clamp_val is not None:

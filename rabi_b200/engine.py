@@ -180,6 +180,19 @@ class MafEngine:
                                                      _ptr(g_theta), _ptr(g_A), wp, bp, self._stream()))
         return g_theta, g_A, grads
 
+    def fisher_trace(self, ctx_rows: torch.Tensor, A: torch.Tensor, z: torch.Tensor, zs_std: Optional[torch.Tensor] = None):
+        """z [S, B, D] -> (trace [B], score [S, B, C], theta [S, B, D]): the MC score estimate of tr F(x) on the kernels."""
+        z, ctx_rows = _f32c(z), _f32c(ctx_rows)
+        S, B, D = z.shape
+        trace = torch.empty((B,), device=self.device, dtype=torch.float32)
+        score = torch.empty((S, B, self.C), device=self.device, dtype=torch.float32)
+        theta = torch.empty_like(z)
+        if S * B:
+            with torch.cuda.device(self.device):
+                self._check(self.L.rabi_fisher_trace_fwd(self.h, _ptr(ctx_rows), _ptr(A), _ptr(z), _ptr(zs_std), S, B, _ptr(trace),
+                                                         _ptr(score), _ptr(theta), self._stream()))
+        return trace, score, theta
+
     def rsample_bwd(self, ctx_rows: torch.Tensor, A: torch.Tensor, z: torch.Tensor, g_theta: torch.Tensor,
                     g_logq: torch.Tensor, want_weights: bool = True):
         """Reverse of theta, log q = rsample(z): upstream g_theta [S, B, D], g_logq [S, B] ->

@@ -348,3 +348,33 @@ def test_fused_rsample_backward_equals_the_op_by_op_graph(shape, dev):
         scale = max(float(t.abs().max()) for t in other[3])
         for a, b in zip(fused[3], other[3]):
             assert float((a - b).abs().max()) <= RTOL * scale, f"weight gradient vs {name}"
+
+
+@pytest.mark.parametrize("shape", [dict(dx=100, D=4, hidden=[100, 100], B=96), dict(dx=10, D=10, hidden=[100, 100], B=33)])
+def test_fisher_trace_kernel_path_equals_the_reference_estimator(shape, dev):
+    """rabi_fisher_trace_fwd (sampling chain -> per-pair density passes + reverse -> back-projection of every pair -> squared
+    norms; no autograd) against the oracle's restatement of monte_carlo_fisher(typ='trace') on the same base noise."""
+    from oracle import rbi_oracle as O
+    from rabi_b200 import noise
+    from rabi_b200.fisher import fisher_trace, monte_carlo_fisher
+    from tests.test_gpu_parity import _fresh
+
+    ref, model, x = _fresh(shape, dev, seed=23)
+    S = 5
+    z = torch.randn(S, shape["B"], shape["D"], generator=torch.Generator().manual_seed(8))
+    eng = model.engine()
+    n0 = eng.launches
+    with noise.injected([z.to(dev)]):
+        tr, scores = fisher_trace(model, x.to(dev), mc_samples=S, return_scores=True)
+    assert eng.launches - n0 <= 9
+    with O.injected_base_noise([z]):
+        q = ref(x)
+        theta = q.rsample((S,))
+        sc_ref = O.score_function(theta, x, ref, create_graph=False).reshape(S, shape["B"], -1)
+    tr_ref = (sc_ref ** 2).mean(0).sum(-1)
+    assert rel_err(scores, sc_ref) < RTOL
+    assert rel_err(tr, tr_ref) < RTOL
+    # the differentiable estimator of the same module agrees with the kernel path
+    with noise.injected([z.to(dev)]):
+        tr2 = monte_carlo_fisher(model, x.to(dev), mc_samples=S, create_graph=True, typ="trace")
+    assert rel_err(tr2.detach(), tr_ref) < RTOL

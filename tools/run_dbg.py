@@ -5,7 +5,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.getcwd())
-os.environ["RABI_TC_RUN_DBG"] = "1"
+os.environ.setdefault("RABI_TC_RUN_DBG", "0")
 import bench  # noqa: E402
 from rabi_b200.models import ZScoreLayer  # noqa: E402
 
