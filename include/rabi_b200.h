@@ -151,6 +151,12 @@ int rabi_maf_rsample_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev
 int rabi_fisher_trace_fwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev, const float* zs_std_dev,
                           int S, int B, float* trace_dev, float* score_dev, float* theta_dev, rabi_stream_t s);
 
+/* The per-pair vectors of the LAST training-side call on this handle (same S, B), copied unit-major ([.][P], P = S*B, the pair
+ * index fastest) into dst_dev: [h0 | a0bar : K*H0*P each][h1 | a1bar : K*H1*P each][obar : K*2D*P][y : K*D*P] -- layer
+ * activations, cotangents of the pre-activations / outputs (reference row order) and the theta-side inputs of the transforms.
+ * Host code builds further products on them (the Fisher regulariser's closed-form weight gradient, rabi_b200/fisher.py). */
+int rabi_train_emissions(rabi_maf_t* h, int S, int B, float* dst_dev, rabi_stream_t s);
+
 /* Per-row attack radii for batched eps-sweeps (config/experiment/eval_l2_pyloric.yaml:13-16 sweeps eps over 6 values;
  * run_rob_eval.py:115-140 derives eps_abs and eps_iter per value): rows x eps values are independent, so one call can attack
  * the rows at all radii at once.  While set, every rabi_*_pgd_step / rabi_*_pgd_run / rabi_pgd_update on this handle uses

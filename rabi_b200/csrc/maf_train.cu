@@ -294,6 +294,19 @@ __global__ void k_score_trace(const float* __restrict__ score, int S, int B, int
     if (lane == 0) trace[row] = acc / (float)S;
 }
 
+// Copies the per-pair vectors the last rabi_maf_log_prob_bwd / rabi_maf_rsample_bwd / rabi_fisher_trace_fwd call left in the
+// library's workspace into a caller buffer: [h0 | a0bar : K*H0*P each][h1 | a1bar : K*H1*P each][obar : K*2D*P][y : K*D*P], P = S*B.
+extern "C" int rabi_train_emissions(rabi_maf_t* h, int S, int B, float* dst_dev, rabi_stream_t s) {
+    if (!h || !h->train) return rabi_fail(h, "rabi_train_emissions: no training-side call was made on this handle");
+    rabi::TrainState* ts = static_cast<rabi::TrainState*>(h->train);
+    const size_t P = (size_t)S * B;
+    const size_t n = (size_t)h->K * P * (2 * (size_t)h->H[0] + 2 * (size_t)h->H[1] + 3 * (size_t)h->D);
+    if (!ts->ws || n > ts->ws_floats) return rabi_fail(h, "rabi_train_emissions: S, B do not match the last training-side call");
+    if (cudaMemcpyAsync(dst_dev, ts->ws, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s) != cudaSuccess)
+        return rabi_fail(h, "rabi_train_emissions: copy failed");
+    return 0;
+}
+
 extern "C" int rabi_fisher_trace_fwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev,
                                      const float* zs_std_dev, int S, int B, float* trace_dev, float* score_dev,
                                      float* theta_dev, rabi_stream_t s) {

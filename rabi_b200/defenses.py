@@ -129,6 +129,27 @@ class FIMTraceRegularizer(AdditiveRegularizer):
             reg = reg.clamp(min=0, max=self.clamp_val)
         return self.beta * self._reduce(reg)
 
+    def _closed_form_ok(self, input: Tensor) -> bool:
+        """The graph-free closed form (rabi_b200/fisher.py::fisher_trace_weight_grad) serves two-hidden-layer conditioners with an
+        identity (+ z-score) embedding; ``RABI_FIM_CLOSED_FORM=0`` keeps the op-by-op double backward."""
+        import os
+        from .models import _split_embedding
+        if os.environ.get("RABI_FIM_CLOSED_FORM", "1") == "0" or not input.is_cuda or input.dim() != 2:
+            return False
+        if self.reduce not in ("mean", "sum") or _split_embedding(self.model.embedding_net)[1] is not None:
+            return False
+        return self.model.engine().fused_training_ok()
+
+    def _reg_and_grads(self, input: Tensor, output, mc_samples: int, params):
+        """(beta * reduce tr F, its gradient w.r.t. ``params``): closed form on the kernels where it serves, else the op-by-op
+        double backward."""
+        if self._closed_form_ok(input):
+            from .fisher import fisher_trace_weight_grad
+            return fisher_trace_weight_grad(self.model, input, mc_samples, beta=self.beta, reduce=self.reduce,
+                                            clamp_val=self.clamp_val)
+        reg = self._trace(input, output if output is not None else self.model(input), mc_samples)
+        return reg, torch.autograd.grad(reg, params, retain_graph=True)
+
     def _regularizer_exact(self, input: Tensor, output: Distribution, target: Tensor) -> Tensor:
         # for a flow the reference's fisher_information_matrix dispatches to the MC score estimator as well
         return self._trace(input, output, self.mc_samples)
@@ -177,8 +198,8 @@ class FIMTraceRegularizer(AdditiveRegularizer):
                     leaves = {n: p.detach().requires_grad_() for n, p in self.model.named_parameters()}
                     with stateless._reparametrize_module(self.model, leaves):
                         with noise.injected([st["z"]]):
-                            reg = self._trace(st["x"], self.model(st["x"]), self.ema_mc_samples)
-                        grads = torch.autograd.grad(reg, [leaves[n] for n, _ in self.model.named_parameters()])
+                            _, grads = self._reg_and_grads(st["x"], None, self.ema_mc_samples,
+                                                           [leaves[n] for n, _ in self.model.named_parameters()])
                     st["t"].add_(1.0)
                     corr = 1.0 - torch.pow(torch.full_like(st["t"], 1.0 - d), st["t"])
                     for m, g_, out in zip(st["m"], grads, st["grads"]):
@@ -201,8 +222,7 @@ class FIMTraceRegularizer(AdditiveRegularizer):
     def _regularizer_ema(self, input: Tensor, output: Distribution, target: Tensor) -> Tensor:
         if self._graph_eligible(input):
             return self._ema_graphed(input)
-        reg = self._trace(input, output, self.ema_mc_samples)
-        grads = torch.autograd.grad(reg, list(self.model.parameters()), retain_graph=True)
+        _, grads = self._reg_and_grads(input, output, self.ema_mc_samples, list(self.model.parameters()))
         self.ema(grads)
         for params, grad in zip(self.model.parameters(), self.ema.value):
             params.grad = torch.nan_to_num(grad.detach())

@@ -193,6 +193,18 @@ class MafEngine:
                                                          _ptr(score), _ptr(theta), self._stream()))
         return trace, score, theta
 
+    def train_emissions(self, S: int, B: int) -> dict:
+        """Per-pair vectors of the last training-side kernel call (same S, B), as [K, units, P] views of one copied buffer."""
+        K, H0, H1, D, P = self.K, self.hidden[0], self.hidden[1], self.D, S * B
+        buf = torch.empty((K * P * (2 * H0 + 2 * H1 + 3 * D),), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.L.rabi_train_emissions(self.h, S, B, _ptr(buf), self._stream()))
+        out, off = {}, 0
+        for name, n in (("h0", H0), ("a0", H0), ("h1", H1), ("a1", H1), ("o", 2 * D), ("y", D)):
+            out[name] = buf[off: off + K * n * P].view(K, n, P)
+            off += K * n * P
+        return out
+
     def rsample_bwd(self, ctx_rows: torch.Tensor, A: torch.Tensor, z: torch.Tensor, g_theta: torch.Tensor,
                     g_logq: torch.Tensor, want_weights: bool = True):
         """Reverse of theta, log q = rsample(z): upstream g_theta [S, B, D], g_logq [S, B] ->

@@ -378,3 +378,22 @@ def test_fisher_trace_kernel_path_equals_the_reference_estimator(shape, dev):
     with noise.injected([z.to(dev)]):
         tr2 = monte_carlo_fisher(model, x.to(dev), mc_samples=S, create_graph=True, typ="trace")
     assert rel_err(tr2.detach(), tr_ref) < RTOL
+
+
+def test_closed_form_fisher_gradient_matches_reference_and_double_backward(case, dev):
+    """fisher_trace_weight_grad (kernels + dense products, no autograd graph) against the reference's double backward stored in
+    the fixtures and against the op-by-op path of this repo, where the closed form serves (two hidden layers, no Permute)."""
+    from rabi_b200 import noise
+    from rabi_b200.fisher import fisher_trace_weight_grad
+
+    name, g, model = case
+    eng = model.engine()
+    if not eng.fused_training_ok() or g["cfg"]["shuffle"]:
+        pytest.skip("closed form serves two-hidden-layer conditioners without Permute layers")
+    x = g["x"].to(dev)
+    n0 = eng.launches
+    with noise.injected([g["z_fim"]]):
+        reg, grads = fisher_trace_weight_grad(model, x, 5, beta=0.05)
+    assert abs(float(reg) - 0.05 * float(g["fim_trace"].mean())) <= 3 * RTOL * abs(0.05 * float(g["fim_trace"].mean()))
+    _check_grads([t.cpu() for t in grads], g["fim_grads"], 3 * RTOL)
+    print(f"\n[{name}] closed-form Fisher gradient: {eng.launches - n0} launches of the flow library")

@@ -209,3 +209,11 @@ def test_l2_ball_noise_is_uniform_in_the_ball():
         assert abs(float((n <= r).float().mean()) - (r / eps) ** d) < 0.015
     v = O.sample_l2_uniformly(20000, d, eps)
     assert float(v.mean(0).abs().max()) < 0.01
+
+
+def test_closed_form_fisher_trace_gradient_equals_autograd_double_backward():
+    """The derivation behind the product's Fisher-trace weight gradient (dual density pass, two masked reverse passes per
+    transform, reverse of the sampling chain) against autograd's double backward on the oracle, in fp64."""
+    from oracle.fim_closed_form_check import check
+
+    assert check() < 1e-9
