@@ -164,6 +164,12 @@ int rabi_train_emissions(rabi_maf_t* h, int S, int B, float* dst_dev, rabi_strea
  * arguments.  Pass NULL, NULL to return to the scalars. */
 int rabi_pgd_set_row_scales(rabi_maf_t* h, const float* eps_rows_dev, const float* eps_iter_rows_dev);
 
+/* Masked-feature attacks (RobustnessMetric(mask=...), rbibm/rbibm/metric/base.py:232-250: only the features selected by the mask
+ * are perturbed -- the reference attacks the sub-vector x[..., mask] through a wrapper model).  While set, every PGD update on
+ * this handle multiplies the input gradient by col_mask_dev [C] (1 = attacked, 0 = frozen) before the normalisation and keeps
+ * delta == 0 on the frozen columns (they are not clamped either).  NULL clears it. */
+int rabi_pgd_set_column_mask(rabi_maf_t* h, const float* col_mask_dev);
+
 /* Forward-KL attack loss (ForwardKLLoss, rbi/rbi/loss/eval_loss.py:108-126 -- the default attack_loss_fn of
  * config/eval_rob/attack/l2pgd.yaml): loss = inv_B * sum_b KL(target_b || q(.|x_b + delta_b)); samples are drawn from the
  * fixed target (projection A_t_dev; NULL in the run = the clean x), the gradient flows through the density pass only.

@@ -92,12 +92,14 @@ class L2PGDAttack(Attack):
         return type(self.loss_fn) in (ReverseKLLoss, ForwardKLLoss) and self.loss_fn.reduction == "mean"
 
     def perturb(self, x: Tensor, y: Optional[Any] = None, delta_init: Optional[Tensor] = None,
-                chunk_size: Optional[int] = None) -> Tensor:
+                chunk_size: Optional[int] = None, feature_mask: Optional[Tensor] = None) -> Tensor:
         """x [B, dx] -> x_adv [B, dx] (detached).
 
         ``delta_init`` injects delta0 (parity tests); ``chunk_size`` makes the loss mean (Q2: the 1/B factor in
         front of every row gradient) behave as if rows were attacked in independent chunks of that size, so a
-        whole sharded data set can go through in one call.
+        whole sharded data set can go through in one call.  ``feature_mask`` (bool [dx]): only these features are attacked
+        (``RobustnessMetric(mask=...)``, rbibm/rbibm/metric/base.py:232-250 attacks the sub-vector x[..., mask] through a wrapper
+        model): the perturbation, its L2 ball and the clip box live on the masked columns, the others stay exactly x.
         """
         x, y = self._verify_and_process_inputs(x, y)
         if x.dim() != 2:
@@ -114,12 +116,27 @@ class L2PGDAttack(Attack):
         if per_row and self.eps.shape[0] != B:
             raise ValueError(f"per-row eps has {self.eps.shape[0]} entries for {B} rows")
         eps0 = self.eps.to(x) if per_row else float(self.eps)
+        fm = None
+        if feature_mask is not None:
+            fm = torch.as_tensor(feature_mask, device=x.device).bool().reshape(-1)
+            if fm.numel() != dx:
+                raise ValueError(f"feature_mask has {fm.numel()} entries for {dx} features")
         if delta_init is not None:
             delta = delta_init.detach().to(x).clone().contiguous()
+            if fm is not None and delta.shape[1] == int(fm.sum()):      # given on the sub-vector, like the reference's attack sees it
+                full = torch.zeros_like(x)
+                full[:, fm] = delta
+                delta = full
         elif self.rand_init:
-            delta = rand_init_delta_l2(x, eps0, float(self.clip_min), float(self.clip_max)).contiguous()
+            if fm is None:
+                delta = rand_init_delta_l2(x, eps0, float(self.clip_min), float(self.clip_max)).contiguous()
+            else:                                                       # drawn in the subspace the attack lives in
+                delta = torch.zeros_like(x)
+                delta[:, fm] = rand_init_delta_l2(x[:, fm].contiguous(), eps0, float(self.clip_min), float(self.clip_max))
         else:
             delta = torch.zeros_like(x)
+        if fm is not None:
+            delta = (delta * fm.to(delta.dtype)).contiguous()
         S = int(self.loss_fn.mc_samples)
         D = model.output_dim
         if noise._queue is not None:
@@ -134,17 +151,24 @@ class L2PGDAttack(Attack):
         if per_row:
             step = self.eps_iter.to(x) if isinstance(self.eps_iter, Tensor) else torch.full_like(eps0, float(self.eps_iter))
             eng.set_row_scales(eps0, step)
+        if fm is not None:
+            eng.set_column_mask(fm.to(torch.float32))
         try:
             if _split_embedding(model.embedding_net)[1] is not None:
-                return self._run_embedded(model, eng, x, delta, y, z_all, inv_B).detach()
+                x_adv = self._run_embedded(model, eng, x, delta, y, z_all, inv_B).detach()
+                return torch.where(fm, x_adv, x) if fm is not None else x_adv
             _, zs, _ = model.condition_inputs(x)
             zs = zs if zs is not None else (None, None)
             # A_q: the target's projection (== projection of the clean x when untargeted)
             x_adv = self._run(eng, x, delta, zs, y, z_all, inv_B)
+            if fm is not None:
+                x_adv = torch.where(fm, x_adv, x)
             return x_adv.detach()
         finally:
             if per_row:
                 eng.set_row_scales()
+            if fm is not None:
+                eng.set_column_mask()
 
     def perturb_sweep(self, x: Tensor, eps_values, eps_iter_values=None, delta_init: Optional[Tensor] = None,
                       chunk_size: Optional[int] = None) -> Tensor:

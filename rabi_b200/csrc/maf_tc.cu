@@ -96,6 +96,7 @@ struct TcArgs {
     float eps, eps_iter, cmin, cmax, floor_;
     const float* eps_rows;      // optional per-row radius / step size
     const float* eps_iter_rows;
+    const float* col_mask;      // optional [C] attack mask
     long long zstride;    // floats between the base noise of consecutive iterations (S * B * D)
     const float* wrow;    // TC_NLL: per-pair loss weights and the per-pair vectors for the weight-gradient products (maf_tc.h)
     float* em_h0;
@@ -830,12 +831,13 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                 constexpr int NE = 4;                  // context entries per lane (C <= 128: checked by the launcher)
                 constexpr int NB = 6;                  // rows per warp handled together: their dependent chains (two warp
                                                        // reductions, sqrt, divisions) interleave instead of running one after the other
-                float isd[NE], mu[NE];
+                float isd[NE], mu[NE], mk[NE];
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     const int c = lane + 32 * e;
                     isd[e] = (a.zstd && c < C) ? a.zstd[c] : 1.f;
                     mu[e] = (a.zmean && c < C) ? a.zmean[c] : 0.f;
+                    mk[e] = (a.col_mask && c < C) ? a.col_mask[c] : 1.f;   // masked-feature attack: 0 = frozen column
                 }
                 for (int rb = warp; rb < RT; rb += NB * nwarps) {
                     float xv[NB][NE], dv[NB][NE], gv[NB][NE], n2[NB], d2[NB];
@@ -861,6 +863,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                             if (r < nr && c < C) {
                                 v = vec[(size_t)r * CG + c];
                                 if (a.zstd) v /= isd[e];
+                                v *= mk[e];
                             }
                             gv[q][e] = v;
                             n2[q] = fmaf(v, v, n2[q]);
@@ -882,7 +885,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                         for (int e = 0; e < NE; ++e) {
                             float d = dv[q][e] + (gv[q][e] * inv) * step;
                             d = fminf(fmaxf(xv[q][e] + d, a.cmin), a.cmax) - xv[q][e];
-                            dv[q][e] = (lane + 32 * e < C) ? d : 0.f;
+                            dv[q][e] = (lane + 32 * e < C && mk[e] != 0.f) ? d : 0.f;
                             d2[q] = fmaf(dv[q][e], dv[q][e], d2[q]);
                         }
                     }
@@ -1312,6 +1315,7 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
     a.floor_ = r.floor_;
     a.eps_rows = r.eps_rows;
     a.eps_iter_rows = r.eps_iter_rows;
+    a.col_mask = r.col_mask;
     a.zstride = (long long)r.S * r.B * h->D;
     const int grid = std::min(nblocks, h->sm_count);
     const int T = NT * 128;

@@ -46,6 +46,7 @@ struct TcRunCall {
     float eps, eps_iter, cmin, cmax, inv_B, floor_;
     const float* eps_rows;       // optional [B] per-row radius / step size (batched eps-sweep); else the scalars
     const float* eps_iter_rows;
+    const float* col_mask;       // optional [C] attack mask (1 = attacked, 0 = frozen)
 };
 int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st);
 

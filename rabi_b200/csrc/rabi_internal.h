@@ -41,6 +41,7 @@ struct rabi_maf {
     void* tcd = nullptr;       // three-hidden-layer tensor-core path state (maf_tcd.cu), owned by rabi_tcd_*
     const float* row_eps = nullptr;        // optional per-row attack radii / step sizes (rabi_pgd_set_row_scales)
     const float* row_eps_iter = nullptr;
+    const float* col_mask = nullptr;       // optional per-column attack mask (rabi_pgd_set_column_mask)
     unsigned long long weights_version = 0;   // bumped by rabi_maf_set_weights / finalize: derived images re-pack lazily
 };
 

@@ -646,7 +646,8 @@ __global__ void k_mean_over_s(const float* __restrict__ in, int S, int B, float*
 // advertorch perturb_iterative(ord=2) update, one warp per row.
 __global__ void k_pgd_update(const float* __restrict__ x, float* __restrict__ delta, const float* __restrict__ grad,
                              int B, int dx, float eps, float eps_iter, float cmin, float cmax, float floor_,
-                             const float* __restrict__ eps_rows, const float* __restrict__ eps_iter_rows) {
+                             const float* __restrict__ eps_rows, const float* __restrict__ eps_iter_rows,
+                             const float* __restrict__ col_mask) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     if (eps_rows) {   // batched eps-sweep: every row carries its own radius and step size
@@ -657,14 +658,18 @@ __global__ void k_pgd_update(const float* __restrict__ x, float* __restrict__ de
     const float* xr = x + (size_t)warp * dx;
     float* dr = delta + (size_t)warp * dx;
     float n2 = 0.f;
-    for (int c = lane; c < dx; c += 32) n2 = fmaf(gr[c], gr[c], n2);
+    for (int c = lane; c < dx; c += 32) {
+        const float gm = col_mask ? gr[c] * col_mask[c] : gr[c];   // masked-feature attack: frozen columns carry no gradient
+        n2 = fmaf(gm, gm, n2);
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
     float inv = 1.f / fmaxf(sqrtf(n2), floor_);
     float d2 = 0.f;
     for (int c = lane; c < dx; c += 32) {
-        float d = dr[c] + (gr[c] * inv) * eps_iter;
-        d = fminf(fmaxf(xr[c] + d, cmin), cmax) - xr[c];
+        const float mk = col_mask ? col_mask[c] : 1.f;
+        float d = dr[c] + (gr[c] * mk * inv) * eps_iter;
+        d = mk != 0.f ? fminf(fmaxf(xr[c] + d, cmin), cmax) - xr[c] : 0.f;
         dr[c] = d;
         d2 = fmaf(d, d, d2);
     }
@@ -1491,7 +1496,7 @@ grad_done:
     }
     int threads = 128, rows_per_block = threads / 32;
     k_pgd_update<<<(B + rows_per_block - 1) / rows_per_block, threads, 0, st>>>(x, delta, gx, B, h->C, eps, eps_iter,
-                                                                                   cmin, cmax, floor_, h->row_eps, h->row_eps_iter);
+                                                                                   cmin, cmax, floor_, h->row_eps, h->row_eps_iter, h->col_mask);
     LAUNCH_CHECK(h);
     if (kl) {
         k_mean_over_s<<<(B + 127) / 128, 128, 0, st>>>(diff, S, B, kl);
@@ -1524,6 +1529,12 @@ extern "C" int rabi_pgd_set_row_scales(rabi_maf_t* h, const float* eps_rows_dev,
     return 0;
 }
 
+extern "C" int rabi_pgd_set_column_mask(rabi_maf_t* h, const float* col_mask_dev) {
+    if (!h) return 1;
+    h->col_mask = col_mask_dev;
+    return 0;
+}
+
 extern "C" int rabi_pgd_update(rabi_maf_t* h, const float* x_dev, float* delta_dev, const float* grad_dev, int B, int dx,
                                float eps, float eps_iter, float clip_min, float clip_max, float norm_floor,
                                rabi_stream_t s) {
@@ -1531,7 +1542,7 @@ extern "C" int rabi_pgd_update(rabi_maf_t* h, const float* x_dev, float* delta_d
     if (B <= 0 || dx <= 0) return 0;
     int threads = 128, rows_per_block = threads / 32;
     k_pgd_update<<<(B + rows_per_block - 1) / rows_per_block, threads, 0, (cudaStream_t)s>>>(
-        x_dev, delta_dev, grad_dev, B, dx, eps, eps_iter, clip_min, clip_max, norm_floor, h->row_eps, h->row_eps_iter);
+        x_dev, delta_dev, grad_dev, B, dx, eps, eps_iter, clip_min, clip_max, norm_floor, h->row_eps, h->row_eps_iter, h->col_mask);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -1597,6 +1608,7 @@ static int pgd_run_fused(rabi_maf* h, const float* x, float* delta, const float*
     r.floor_ = floor_;
     r.eps_rows = h->row_eps;
     r.eps_iter_rows = h->row_eps_iter;
+    r.col_mask = h->col_mask;
     return rabi::rabi_tc_run(h, r, forward_kl ? rabi::TC_FKL : rabi::TC_GRAD, st);
 }
 

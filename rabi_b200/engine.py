@@ -268,6 +268,11 @@ class MafEngine:
         a, b = self._row_scales if self._row_scales else (None, None)
         self._check(self.L.rabi_pgd_set_row_scales(self.h, _ptr(a), _ptr(b)))
 
+    def set_column_mask(self, mask=None):
+        """Masked-feature attacks: [C] fp32 device tensor (1 = attacked, 0 = frozen), kept alive here until cleared."""
+        self._col_mask = None if mask is None else _f32c(mask)
+        self._check(self.L.rabi_pgd_set_column_mask(self.h, _ptr(self._col_mask)))
+
     def pgd_update(self, x, delta, grad, eps, eps_iter, clip_min, clip_max, norm_floor=1e-6):
         """In-place L2 step / box clamp / projection of ``delta`` given d loss / d delta."""
         B, dx = x.shape

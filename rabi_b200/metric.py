@@ -111,7 +111,9 @@ class RobustnessMetric(Metric):
                  target_wrapper: Callable = lambda x: x, mask: Optional[Tensor] = None, descending: bool = True,
                  batch_size: Optional[int] = None, reduction: Optional[str] = None, device: str = "cuda"):
         if mask is not None:
-            raise NotImplementedError("masked-feature attacks are outside the maf_pyro / l2pgd / KL path")
+            mask = torch.as_tensor(mask).bool()
+            if not isinstance(attack, L2PGDAttack):
+                raise NotImplementedError("masked-feature attacks are served for L2PGDAttack")
         super().__init__(model, reduction=reduction, batch_size=batch_size, descending=descending, device=device)
         self.loss_fn = loss_fn
         self.loss_fn.reduction = None
@@ -140,6 +142,8 @@ class RobustnessMetric(Metric):
         chunk = self.batch_size if (self.batch_size is not None and self.batch_size < x.shape[0]) else None
         for i in range(self.attack_attemps):
             kw = {"chunk_size": chunk} if isinstance(self.attack, L2PGDAttack) else {}
+            if self.mask is not None:   # metric/base.py:232-250: only the masked features are attacked
+                kw["feature_mask"] = self.mask
             if target is None or not self.attack.targeted:
                 x_tilde = self.attack.perturb(x, **kw)
             else:

@@ -214,3 +214,56 @@ def test_trades_forward_kl(case, dev):
         _check_grads(_grads(model), t["grads_clean"], 3 * RTOL)
     finally:
         trades.deactivate()
+
+
+def test_masked_feature_attack_vs_oracle(dev):
+    """``RobustnessMetric(mask=...)`` (rbibm/rbibm/metric/base.py:232-250): the attack perturbs only the masked features.  The
+    reference attacks the sub-vector through a wrapper model; here the full-width attack carries a column mask
+    (rabi_pgd_set_column_mask).  Checked against the oracle's L2-PGD run on the sub-vector with the same starting point and base
+    noise, through the persistent kernel and the per-iteration path."""
+    import os
+
+    from oracle import rbi_oracle as O
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+    from rabi_b200.metric import ReverseKLRobMetric
+    from tests.test_gpu_parity import _fresh
+    from tests.util import pgd_near_kink_rows
+
+    shape = dict(dx=24, D=3, hidden=[40, 36], B=300)
+    ref, model, x = _fresh(shape, dev, seed=41)
+    mask = torch.zeros(shape["dx"], dtype=torch.bool)
+    mask[[1, 2, 5, 8, 13, 21]] = True
+    S, n_it = 5, 6
+    g = torch.Generator().manual_seed(2)
+    zs = [torch.randn(S, shape["B"], shape["D"], generator=g) for _ in range(n_it)]
+    d0 = 0.05 * torch.randn(shape["B"], int(mask.sum()), generator=g)
+    eps = float(0.5 * x[:, mask].std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+
+    def masked_model(xm):            # what the reference installs as attack.predict
+        xh = x.clone()
+        xh[..., mask] = xm
+        return ref(xh)
+
+    with O.injected_base_noise(zs):
+        xm_ref = O.l2pgd_perturb(masked_model, x[:, mask], O.ReverseKLLoss(mc_samples=S), eps, n_it, eps / 4, cmin, cmax, delta0=d0)
+    for q in ref.parameters():
+        q.grad = None
+    atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=S), eps=eps, nb_iter=n_it, eps_iter=eps / 4, clip_min=cmin, clip_max=cmax)
+    for env in ({"RABI_TC_RUN_MIN_PAIRS": "1"}, {"RABI_TC_RUN": "0"}):
+        os.environ.update(env)
+        try:
+            with noise.injected(zs):
+                xa = atk.perturb(x.to(dev), delta_init=d0.to(dev), feature_mask=mask).cpu()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        assert torch.equal(xa[:, ~mask], x[:, ~mask]), "frozen features must stay exactly x"
+        e = (xa[:, mask] - xm_ref).norm(dim=1) / (xm_ref - x[:, mask]).norm(dim=1)
+        assert float(e.median()) < 1e-5 and int((e > RTOL).sum()) <= int(0.03 * e.numel()), (float(e.median()), float(e.max()))
+        assert float((xa - x).norm(dim=1).max()) <= eps * (1 + 1e-5)
+    met = ReverseKLRobMetric(model, atk, mc_samples=16, attack_attemps=1, device=dev, reduction=None, mask=mask)
+    losses = met.eval(x)
+    assert torch.isfinite(losses).all() and torch.equal(met._cached_xs_tilde.cpu()[:, ~mask], x[:, ~mask])
