@@ -151,6 +151,19 @@ int rabi_maf_rsample_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev
 int rabi_fisher_trace_fwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev, const float* zs_std_dev,
                           int S, int B, float* trace_dev, float* score_dev, float* theta_dev, rabi_stream_t s);
 
+/* Weight gradient of the Fisher-trace regulariser R = sum_b w_b tr F(x_b) (w_row_dev [B] = dR / d tr F_b: beta / (n S) for the
+ * rows the reduction keeps, 0 for the others) -- what FIMTraceRegularizer obtains from autograd.grad of the MC estimator with
+ * create_graph=True (rbi/rbi/defenses/fisher_regularization.py:67-95, rbi/rbi/utils/fisher_info.py:185-280), as a closed form
+ * without an autograd graph (derivation and fp64 check: oracle/fim_closed_form_check.py).  Must follow rabi_fisher_trace_fwd on
+ * the same handle with the same ctx / A / z / S / B (it consumes the per-pair vectors that call left in the workspace) and the
+ * scores it returned.  Launches: k_fim_cdot, k_fim_dual (tangent density pass + the two masked reverse passes per transform,
+ * 64 pairs per CTA), k_wgrad (24 stacked weight products), then the sampling-chain reverse (k_tc<TC_RSB> + k_wgrad) seeded with
+ * d phi / d theta.  wm_dev[k*3 + l]: weight * mask of transform k, layer l in the reference layout ([H0, C+D], [H1, H0],
+ * [2D, H1]); bo_dev[k]: output-layer bias [2D]; g_weight_dev / g_bias_dev as in rabi_maf_log_prob_bwd (overwritten). */
+int rabi_fisher_trace_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev, const float* zs_std_dev,
+                          int S, int B, const float* score_dev, const float* w_row_dev, const float* const* wm_dev,
+                          const float* const* bo_dev, float* const* g_weight_dev, float* const* g_bias_dev, rabi_stream_t s);
+
 /* The per-pair vectors of the LAST training-side call on this handle (same S, B), copied unit-major ([.][P], P = S*B, the pair
  * index fastest) into dst_dev: [h0 | a0bar : K*H0*P each][h1 | a1bar : K*H1*P each][obar : K*2D*P][y : K*D*P] -- layer
  * activations, cotangents of the pre-activations / outputs (reference row order) and the theta-side inputs of the transforms.

@@ -35,7 +35,7 @@ EXPORTS = [
     "rabi_maf_ctx_project_bwd", "rabi_maf_log_prob_fwd", "rabi_maf_rsample_fwd", "rabi_rkl_fwd",
     "rabi_rkl_input_grad", "rabi_rkl_pgd_step", "rabi_rkl_pgd_run", "rabi_launch_count",
     "rabi_profile", "rabi_profile_read", "rabi_fma_peak_tflops", "rabi_sgemm", "rabi_sgemm_launch_count",
-    "rabi_fkl_input_grad", "rabi_fkl_pgd_run", "rabi_pgd_update", "rabi_pgd_set_row_scales", "rabi_pgd_set_column_mask", "rabi_maf_log_prob_bwd", "rabi_maf_rsample_bwd", "rabi_fisher_trace_fwd", "rabi_train_emissions",
+    "rabi_fkl_input_grad", "rabi_fkl_pgd_run", "rabi_pgd_update", "rabi_pgd_set_row_scales", "rabi_pgd_set_column_mask", "rabi_maf_log_prob_bwd", "rabi_maf_rsample_bwd", "rabi_fisher_trace_fwd", "rabi_fisher_trace_bwd", "rabi_train_emissions",
 ]
 
 
@@ -139,6 +139,8 @@ def lib() -> ctypes.CDLL:
     L.rabi_pgd_set_column_mask.argtypes = [vp, vp]
     L.rabi_pgd_set_column_mask.restype = c_int
     L.rabi_maf_log_prob_bwd.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    L.rabi_fisher_trace_bwd.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.rabi_fisher_trace_bwd.restype = c_int
     L.rabi_train_emissions.argtypes = [vp, c_int, c_int, vp, vp]
     L.rabi_train_emissions.restype = c_int
     L.rabi_fisher_trace_fwd.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp]

@@ -36,6 +36,9 @@
 
 namespace rabi {
 
+#ifndef RABI_TC_FASTPOLL
+#define RABI_TC_FASTPOLL 64
+#endif
 constexpr int TC_KC = 24;          // staged inputs per push (columns of the hi half and of the lo half)
 constexpr int TC_ACC = 120;        // accumulator columns = max padded units per hidden layer on this path
 constexpr int TC_SH = TC_ACC;      // staging columns, hi half
@@ -135,6 +138,16 @@ __device__ __forceinline__ void tc_commit(uint64_t* mbar) {
 }
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t done = 0;
+#ifndef RABI_TC_NO_FASTPOLL
+    // the waits of this kernel are short (one MMA chain): poll without suspending first -- try_wait parks the thread for a
+    // hardware-chosen interval, which is long compared to a push round trip
+#pragma unroll 1
+    for (int i = 0; i < RABI_TC_FASTPOLL; ++i) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(tc_smem_u32(mbar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+#endif
     unsigned spins = 0;
     long long t0 = 0;
     while (true) {

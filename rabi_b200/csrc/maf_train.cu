@@ -35,6 +35,7 @@ struct WgDesc {
     const float* mask;   // [M][ldo] (+ the same offset) or null
     float* bias;         // [M] += sum_p A[m][p]  (null: none)
     int M, N, P, lda, ldb, ldo, b_pmajor;
+    int b_mod;           // b_pmajor: row of B = p % b_mod (0: p)
     int tile0;           // first CTA of this product
     int tn, ksplit;      // tiles along N, K chunks
 };
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) k_wgrad(const WgArgs a) {
             for (int i = threadIdx.x; i < WG_TN * WG_KC; i += 256) {
                 const int nn = i % WG_TN, kk = i / WG_TN;
                 const int n = n0 + nn, p = pc + kk;
-                Bs[kk][nn] = (n < d.N && p < p1) ? d.B[(size_t)p * d.ldb + n] : 0.f;
+                Bs[kk][nn] = (n < d.N && p < p1) ? d.B[(size_t)(d.b_mod ? p % d.b_mod : p) * d.ldb + n] : 0.f;
             }
         } else {
             for (int i = threadIdx.x; i < WG_TN * WG_KC; i += 256) {
@@ -129,16 +130,43 @@ struct TrainState {
     unsigned long long masks_of = ~0ull;    // structure version the masks were uploaded for (weights_version at upload)
     float* ws = nullptr;                    // emission buffers
     size_t ws_floats = 0;
+    float* fim = nullptr;                   // buffers of the Fisher-gradient dual pass
+    size_t fim_floats = 0;
 };
 
 static int layer_out(const rabi_maf* h, int layer) { return layer < h->L ? h->H[layer] : 2 * h->D; }
 static int layer_in(const rabi_maf* h, int layer) { return layer == 0 ? h->C + h->D : h->H[layer - 1]; }
+
+// Zeroes the gradient buffers: ONE memset when the caller laid them out as one block [W(k,l) | b(k,l)] in (k, l) order (the
+// Python binding does), else one per tensor.
+static int zero_grads(rabi_maf* h, float* const* g_weight, float* const* g_bias, cudaStream_t st) {
+    const int n = h->K * (h->L + 1);
+    bool contiguous = true;
+    size_t total = 0;
+    for (int i = 0; i < n && contiguous; ++i) {
+        const int l = i % (h->L + 1);
+        const size_t nw = (size_t)layer_out(h, l) * layer_in(h, l), nb = (size_t)layer_out(h, l);
+        contiguous = g_bias[i] == g_weight[i] + nw && (i + 1 == n || g_weight[i + 1] == g_bias[i] + nb);
+        total += nw + nb;
+    }
+    if (contiguous) {
+        RABI_CU_OK(h, cudaMemsetAsync(g_weight[0], 0, total * sizeof(float), st));
+        return 0;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int l = i % (h->L + 1);
+        RABI_CU_OK(h, cudaMemsetAsync(g_weight[i], 0, (size_t)layer_out(h, l) * layer_in(h, l) * sizeof(float), st));
+        RABI_CU_OK(h, cudaMemsetAsync(g_bias[i], 0, (size_t)layer_out(h, l) * sizeof(float), st));
+    }
+    return 0;
+}
 
 void rabi_train_destroy(rabi_maf* h) {
     TrainState* s = static_cast<TrainState*>(h->train);
     if (!s) return;
     if (s->masks) cudaFree(s->masks);
     if (s->ws) cudaFree(s->ws);
+    if (s->fim) cudaFree(s->fim);
     delete s;
     h->train = nullptr;
 }
@@ -149,7 +177,8 @@ void rabi_train_destroy(rabi_maf* h) {
 // 0 = done, 1 = error, 2 = this shape is not served by the fused training path (the caller keeps its autograd path)
 static int train_bwd(rabi_maf* h, int mode, const float* ctx, const float* A, const float* in, const float* gout,
                      const float* g_theta_in, int S, int B, float* theta_out, float* logq, float* g_theta, float* g_A,
-                     float* const* g_weight, float* const* g_bias, cudaStream_t st, float** em_a0_out = nullptr) {
+                     float* const* g_weight, float* const* g_bias, cudaStream_t st, float** em_a0_out = nullptr,
+                     bool accumulate = false) {
     if (h->L != 2) return 2;
     for (int k = 0; k < h->K; ++k)
         if (!h->post[k].empty()) return 2;   // Permute layers between the transforms: index bookkeeping not done here
@@ -253,10 +282,7 @@ static int train_bwd(rabi_maf* h, int mode, const float* ctx, const float* A, co
         float* W0 = g_weight[k * (L + 1) + 0];
         float* W1 = g_weight[k * (L + 1) + 1];
         float* Wo = g_weight[k * (L + 1) + 2];
-        for (int l = 0; l <= L; ++l) {
-            RABI_CU_OK(h, cudaMemsetAsync(g_weight[k * (L + 1) + l], 0, (size_t)layer_out(h, l) * layer_in(h, l) * sizeof(float), st));
-            RABI_CU_OK(h, cudaMemsetAsync(g_bias[k * (L + 1) + l], 0, (size_t)layer_out(h, l) * sizeof(float), st));
-        }
+        if (k == 0 && !accumulate && zero_grads(h, g_weight, g_bias, st)) return 1;
         // layer 0, context columns: the S samples of a row share the context -> the reduced gA [H0][B] times ctx [B][C]
         add(gA + (size_t)k * H0 * B, H0, ctx, C, B, B, C, 1, W0, C + D, m0, g_bias[k * (L + 1) + 0]);
         // layer 0, theta columns: per pair
@@ -279,6 +305,342 @@ int rabi_train_log_prob_bwd(rabi_maf* h, const float* ctx, const float* A, const
 }
 
 }  // namespace rabi
+
+namespace rabi {
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Fisher-trace regulariser, weight gradient (rbi/rbi/defenses/fisher_regularization.py:67-95 takes autograd.grad of the MC
+// estimator of rbi/rbi/utils/fisher_info.py:185-280 with create_graph=True).  Closed form, derivation and fp64 check in
+// oracle/fim_closed_form_check.py: with the scores g_p held constant, dR = sum_p d phi_p, phi_p = the derivative of
+// log q(theta_p | x) along xdot_p = 2 w_p g_p.  k_fim_dual runs, for a tile of 64 pairs per CTA,
+//   * the TANGENT density pass (the primal pass with the stored ReLU masks instead of the sign tests, zero biases), and
+//   * the reverse over the (primal, tangent) program seeded on the tangent of log q: two masked reverse passes per transform
+//     (adjoints "t" of the tangent and "b" of the primal variables),
+// as a chain of small dense products [units x 64 pairs] on masked reference-layout weights (packed FMAs, inputs staged in shared
+// memory), and leaves every vector the stacked weight products need unit-major in global memory for k_wgrad.
+constexpr int FD_NP = 64;   // pairs per CTA
+
+struct FimArgs {
+    const float* W0[RABI_MAXK];   // [H0][C + D] weight * mask
+    const float* W1[RABI_MAXK];   // [H1][H0]
+    const float* Wo[RABI_MAXK];   // [2D][H1]
+    const float* bo[RABI_MAXK];   // [2D]
+    const float* h0;              // [K][H0][P] primal activations (emitted by k_tc<TC_NLL>)
+    const float* h1;              // [K][H1][P]
+    const float* y;               // [K][D][P]  theta-side inputs of the transforms
+    const float* cdot;            // [C][P]     tangent of the (z-scored) context
+    float *h0d, *h1d, *ydot;      // tangent activations / inputs, same shapes as h0, h1, y
+    float *a0t, *a0b, *a1t, *a1b; // adjoints of the (tangent, primal) pre-activations
+    float *ot, *ob;               // [K][2D][P] adjoints of the (tangent, primal) outputs (mean rows, then log-scale rows)
+    float* aux;                   // [K][3][D][P]: exp(clamp(s)), sdot, u
+    float* theta_bar;             // [P][D] d phi / d theta
+    int K, D, C, H0, H1, P;
+    float lo, hi;
+};
+
+// Out[m][0..63] (+)= sum_k W(m, k) In[k][0..63];  W(m, k) = TRANS ? W[k * ldw + m] : W[m * ldw + k]
+template <bool TRANS>
+__device__ __forceinline__ void fd_prod(const float* __restrict__ W, int ldw, int M, int Kd, const float* In, float* Out, bool acc) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    for (int m = ty; m < M; m += 16) {
+        float4 a = acc ? *reinterpret_cast<const float4*>(Out + m * FD_NP + 4 * tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int k = 0; k < Kd; ++k) {
+            const float w = __ldg(TRANS ? W + (size_t)k * ldw + m : W + (size_t)m * ldw + k);
+            const float4 v = *reinterpret_cast<const float4*>(In + k * FD_NP + 4 * tx);
+            a.x = fmaf(w, v.x, a.x);
+            a.y = fmaf(w, v.y, a.y);
+            a.z = fmaf(w, v.z, a.z);
+            a.w = fmaf(w, v.w, a.w);
+        }
+        *reinterpret_cast<float4*>(Out + m * FD_NP + 4 * tx) = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fim_dual(const FimArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int K = a.K, D = a.D, C = a.C, H0 = a.H0, H1 = a.H1, P = a.P;
+    const int HM = max(H0, H1);
+    float* bC = sm;                       // [C][64]   cdot tile
+    float* bX = bC + C * FD_NP;           // [HM][64]
+    float* bY = bX + HM * FD_NP;          // [HM][64]
+    float* bOd = bY + HM * FD_NP;         // [2D][64]  tangent outputs | tangent-adjoint outputs
+    float* bOv = bOd + 2 * D * FD_NP;     // [2D][64]  primal outputs  | primal-adjoint outputs
+    float* bYd = bOv + 2 * D * FD_NP;     // [D][64]   ydot chain | ut chain
+    float* bUb = bYd + D * FD_NP;         // [D][64]   ub chain
+    const int p0 = blockIdx.x * FD_NP, tid = threadIdx.x, T = blockDim.x;
+    // element (row r, column c) of a [rows][64] tile <-> global [rows][P] at pair p0 + c: consecutive threads walk the pairs
+    auto gl = [&](const float* base, int r, int c) { return p0 + c < P ? base[(size_t)r * P + p0 + c] : 0.f; };
+    auto gs = [&](float* base, int r, int c, float v) { if (p0 + c < P) base[(size_t)r * P + p0 + c] = v; };
+    for (int i = tid; i < C * FD_NP; i += T) bC[i] = gl(a.cdot, i / FD_NP, i % FD_NP);
+    for (int i = tid; i < D * FD_NP; i += T) bYd[i] = 0.f;
+    __syncthreads();
+    // ================= tangent density pass: transform K-1 first (theta itself has no tangent)
+    for (int k = K - 1; k >= 0; --k) {
+        const float* W0 = a.W0[k];
+        const int ld0 = C + D;
+        fd_prod<false>(W0, ld0, H0, C, bC, bX, false);
+        __syncthreads();
+        fd_prod<false>(W0 + C, ld0, H0, D, bYd, bX, true);
+        __syncthreads();
+        for (int i = tid; i < H0 * FD_NP; i += T) {
+            const int r = i / FD_NP, c = i % FD_NP;
+            const float v = gl(a.h0 + (size_t)k * H0 * P, r, c) > 0.f ? bX[i] : 0.f;
+            bX[i] = v;
+            gs(a.h0d + (size_t)k * H0 * P, r, c, v);
+        }
+        for (int i = tid; i < D * FD_NP; i += T) gs(a.ydot + (size_t)k * D * P, i / FD_NP, i % FD_NP, bYd[i]);
+        __syncthreads();
+        fd_prod<false>(a.W1[k], H0, H1, H0, bX, bY, false);
+        __syncthreads();
+        for (int i = tid; i < H1 * FD_NP; i += T) {
+            const int r = i / FD_NP, c = i % FD_NP;
+            const float h = gl(a.h1 + (size_t)k * H1 * P, r, c);
+            const float v = h > 0.f ? bY[i] : 0.f;
+            bY[i] = v;
+            gs(a.h1d + (size_t)k * H1 * P, r, c, v);
+            bX[i] = h;                     // primal activations: the outputs (mean, log-scale) are recomputed from them
+        }
+        __syncthreads();
+        fd_prod<false>(a.Wo[k], H1, 2 * D, H1, bY, bOd, false);
+        fd_prod<false>(a.Wo[k], H1, 2 * D, H1, bX, bOv, false);
+        __syncthreads();
+        for (int i = tid; i < D * FD_NP; i += T) {
+            const int d = i / FD_NP, c = i % FD_NP;
+            const float mu = bOv[i] + __ldg(a.bo[k] + d);
+            const float s = bOv[(D + d) * FD_NP + c] + __ldg(a.bo[k] + D + d);
+            const float es = expf(fminf(fmaxf(s, a.lo), a.hi));
+            const float yv = gl(a.y + (size_t)k * D * P, d, c);
+            const float sd = bOd[(D + d) * FD_NP + c], mud = bOd[i], ydin = bYd[i];
+            float* aux = a.aux + (size_t)k * 3 * D * P;
+            gs(aux, d, c, es);
+            gs(aux + (size_t)D * P, d, c, sd);
+            gs(aux + (size_t)2 * D * P, d, c, fmaf(es, yv, mu));
+            bYd[i] = fmaf(es, fmaf(sd, yv, ydin), mud);     // tangent of u = exp(s) y + mu: the next transform's ydot
+        }
+        __syncthreads();
+    }
+    // ================= reverse over the dual program; seed 1 on the tangent of log q = sum sdot - u0 . u0dot
+    for (int i = tid; i < D * FD_NP; i += T) {
+        const int d = i / FD_NP, c = i % FD_NP;
+        bUb[i] = -bYd[i];                                   // adjoint of u0      = -u0dot
+        bYd[i] = -gl(a.aux + (size_t)2 * D * P, d, c);      // adjoint of u0dot   = -u0      (aux of transform 0)
+    }
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+        const float* aux = a.aux + (size_t)k * 3 * D * P;
+        for (int i = tid; i < D * FD_NP; i += T) {
+            const int d = i / FD_NP, c = i % FD_NP;
+            const float es = gl(aux, d, c), sd = gl(aux + (size_t)D * P, d, c);
+            const float yv = gl(a.y + (size_t)k * D * P, d, c), yd = gl(a.ydot + (size_t)k * D * P, d, c);
+            const float ut = bYd[i], ub = bUb[i];
+            const float ot_m = ut, ot_s = fmaf(ut * es, yv, 1.f);
+            const float ob_m = ub, ob_s = fmaf(ub * es, yv, ut * es * fmaf(sd, yv, yd));
+            bOd[i] = ot_m;
+            bOd[(D + d) * FD_NP + c] = ot_s;
+            bOv[i] = ob_m;
+            bOv[(D + d) * FD_NP + c] = ob_s;
+            gs(a.ot + (size_t)k * 2 * D * P, d, c, ot_m);
+            gs(a.ot + (size_t)k * 2 * D * P, D + d, c, ot_s);
+            gs(a.ob + (size_t)k * 2 * D * P, d, c, ob_m);
+            gs(a.ob + (size_t)k * 2 * D * P, D + d, c, ob_s);
+            bYd[i] = ut * es;                               // direct parts of the adjoints of (ydot, y)
+            bUb[i] = fmaf(ub, es, ut * es * sd);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {           // 0: adjoints of the tangent variables, 1: of the primal ones
+            const float* Oin = which == 0 ? bOd : bOv;
+            float* a1out = (which == 0 ? a.a1t : a.a1b) + (size_t)k * H1 * P;
+            float* a0out = (which == 0 ? a.a0t : a.a0b) + (size_t)k * H0 * P;
+            float* chain = which == 0 ? bYd : bUb;
+            fd_prod<true>(a.Wo[k], H1, H1, 2 * D, Oin, bX, false);
+            __syncthreads();
+            for (int i = tid; i < H1 * FD_NP; i += T) {
+                const int r = i / FD_NP, c = i % FD_NP;
+                const float v = gl(a.h1 + (size_t)k * H1 * P, r, c) > 0.f ? bX[i] : 0.f;
+                bX[i] = v;
+                gs(a1out, r, c, v);
+            }
+            __syncthreads();
+            fd_prod<true>(a.W1[k], H0, H0, H1, bX, bY, false);
+            __syncthreads();
+            for (int i = tid; i < H0 * FD_NP; i += T) {
+                const int r = i / FD_NP, c = i % FD_NP;
+                const float v = gl(a.h0 + (size_t)k * H0 * P, r, c) > 0.f ? bY[i] : 0.f;
+                bY[i] = v;
+                gs(a0out, r, c, v);
+            }
+            __syncthreads();
+            fd_prod<true>(a.W0[k] + C, C + D, D, H0, bY, chain, true);
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < D * FD_NP; i += T) {
+        const int d = i / FD_NP, c = i % FD_NP;
+        if (p0 + c < P) a.theta_bar[(size_t)(p0 + c) * D + d] = bUb[i];
+    }
+}
+
+// cdot[c][p] = 2 w_row[p % B] score[p][c] / std[c]   (rows the reduction dropped carry weight 0 and contribute nothing)
+__global__ void k_fim_cdot(const float* __restrict__ score, const float* __restrict__ w_row, const float* __restrict__ zstd,
+                           int P, int B, int C, float* __restrict__ cdot) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)P * C) return;
+    const int c = (int)(i / P), p = (int)(i % P);
+    const float w = w_row[p % B];
+    float v = 0.f;
+    if (w != 0.f) {
+        v = 2.f * w * score[(size_t)p * C + c];
+        if (zstd) v /= zstd[c];
+    }
+    cdot[i] = v;
+}
+
+}  // namespace rabi
+
+extern "C" int rabi_fisher_trace_bwd(rabi_maf_t* h, const float* ctx_dev, const float* A_dev, const float* z_dev,
+                                     const float* zs_std_dev, int S, int B, const float* score_dev, const float* w_row_dev,
+                                     const float* const* wm_dev, const float* const* bo_dev, float* const* g_weight_dev,
+                                     float* const* g_bias_dev, rabi_stream_t s) {
+    using namespace rabi;
+    if (!h || !h->train) return rabi_fail(h, "rabi_fisher_trace_bwd: call rabi_fisher_trace_fwd on this handle first");
+    if (cudaSetDevice(h->device) != cudaSuccess) return rabi_fail(h, "cudaSetDevice failed");
+    if (S <= 0 || B <= 0) return 0;
+    if (h->L != 2 || h->K > RABI_MAXK) return rabi_fail(h, "rabi_fisher_trace_bwd serves two-hidden-layer conditioners");
+    cudaStream_t st = (cudaStream_t)s;
+    TrainState* ts = static_cast<TrainState*>(h->train);
+    const int K = h->K, D = h->D, C = h->C, H0 = h->H[0], H1 = h->H[1], L = h->L;
+    const size_t P = (size_t)S * B;
+    const size_t n0 = (size_t)K * H0 * P, n1 = (size_t)K * H1 * P, no = (size_t)K * 2 * D * P, ny = (size_t)K * D * P;
+    if (!ts->ws || 2 * n0 + 2 * n1 + no + ny > ts->ws_floats) return rabi_fail(h, "rabi_fisher_trace_bwd: S, B do not match the forward call");
+    const float* em_h0 = ts->ws;
+    const float* em_h1 = ts->ws + 2 * n0;
+    const float* em_y = ts->ws + 2 * n0 + 2 * n1 + no;
+    // own buffers: cdot [C][P] | h0d, a0t, a0b [n0] | h1d, a1t, a1b [n1] | ot, ob [no] | ydot [ny] | aux [3 ny] | theta_bar [P D]
+    const size_t need = (size_t)C * P + 3 * n0 + 3 * n1 + 2 * no + 4 * ny + P * D + P;
+    if (need > ts->fim_floats) {
+        if (ts->fim) {
+            RABI_CU_OK(h, cudaDeviceSynchronize());
+            RABI_CU_OK(h, cudaFree(ts->fim));
+            ts->fim = nullptr;
+            ts->fim_floats = 0;
+        }
+        RABI_CU_OK(h, cudaMalloc(&ts->fim, need * sizeof(float)));
+        ts->fim_floats = need;
+    }
+    float* cdot = ts->fim;
+    float* h0d = cdot + (size_t)C * P;
+    float* a0t = h0d + n0;
+    float* a0b = a0t + n0;
+    float* h1d = a0b + n0;
+    float* a1t = h1d + n1;
+    float* a1b = a1t + n1;
+    float* ot = a1b + n1;
+    float* ob = ot + no;
+    float* ydot = ob + no;
+    float* aux = ydot + ny;
+    float* theta_bar = aux + 3 * ny;
+    float* zero_w = theta_bar + P * D;    // [P] dL/dlog q of the sample-path reverse: none
+    k_fim_cdot<<<(unsigned)((P * C + 255) / 256), 256, 0, st>>>(score_dev, w_row_dev, zs_std_dev, (int)P, B, C, cdot);
+    h->launches++;
+    FimArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    for (int k = 0; k < K; ++k) {
+        fa.W0[k] = wm_dev[k * 3 + 0];
+        fa.W1[k] = wm_dev[k * 3 + 1];
+        fa.Wo[k] = wm_dev[k * 3 + 2];
+        fa.bo[k] = bo_dev[k];
+    }
+    fa.h0 = em_h0;
+    fa.h1 = em_h1;
+    fa.y = em_y;
+    fa.cdot = cdot;
+    fa.h0d = h0d;
+    fa.h1d = h1d;
+    fa.ydot = ydot;
+    fa.a0t = a0t;
+    fa.a0b = a0b;
+    fa.a1t = a1t;
+    fa.a1b = a1b;
+    fa.ot = ot;
+    fa.ob = ob;
+    fa.aux = aux;
+    fa.theta_bar = theta_bar;
+    fa.K = K;
+    fa.D = D;
+    fa.C = C;
+    fa.H0 = H0;
+    fa.H1 = H1;
+    fa.P = (int)P;
+    fa.lo = h->lo;
+    fa.hi = h->hi;
+    const size_t smem = ((size_t)C + 2 * (size_t)std::max(H0, H1) + 4 * (size_t)D + 2 * (size_t)D) * FD_NP * sizeof(float);
+    if (smem > (size_t)h->max_smem_optin) return rabi_fail(h, "rabi_fisher_trace_bwd: conditioner too wide for the dual kernel");
+    RABI_CU_OK(h, cudaFuncSetAttribute(k_fim_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fim_dual<<<(unsigned)((P + FD_NP - 1) / FD_NP), 256, smem, st>>>(fa);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return rabi_fail(h, "k_fim_dual launch failed: %s", cudaGetErrorString(e));
+    // ---- stacked weight products (zeroing the gradient buffers), then the path through the samples accumulates on top
+    if (!ts->masks) return rabi_fail(h, "rabi_fisher_trace_bwd: masks not uploaded (forward call missing)");
+    WgArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    int nd = 0, tiles = 0;
+    auto add = [&](const float* Aop, int M, const float* Bop, int N, int Pn, int ldb, int b_pmajor, int b_mod, float* out, int ldo,
+                   const float* mask, float* bias) {
+        WgDesc& d = wa.d[nd++];
+        d.A = Aop;
+        d.B = Bop;
+        d.out = out;
+        d.mask = mask;
+        d.bias = bias;
+        d.M = M;
+        d.N = N;
+        d.P = Pn;
+        d.lda = Pn;
+        d.ldb = ldb;
+        d.ldo = ldo;
+        d.b_pmajor = b_pmajor;
+        d.b_mod = b_mod;
+        d.tile0 = tiles;
+        d.tn = (N + WG_TN - 1) / WG_TN;
+        d.ksplit = std::max(1, std::min(32, (Pn + 255) / 256));
+        tiles += ((M + WG_TM - 1) / WG_TM) * d.tn * d.ksplit;
+    };
+    if (K * 8 > WG_MAXD) return rabi_fail(h, "rabi_fisher_trace_bwd: too many transforms for one weight-product launch");
+    const int Pn = (int)P;
+    for (int k = 0; k < K; ++k) {
+        const float* m0 = ts->masks + ts->mask_off[(size_t)k * (L + 1) + 0];
+        const float* m1 = ts->masks + ts->mask_off[(size_t)k * (L + 1) + 1];
+        const float* mo = ts->masks + ts->mask_off[(size_t)k * (L + 1) + 2];
+        float* W0 = g_weight_dev[k * (L + 1) + 0];
+        float* W1 = g_weight_dev[k * (L + 1) + 1];
+        float* Wo = g_weight_dev[k * (L + 1) + 2];
+        if (k == 0 && zero_grads(h, g_weight_dev, g_bias_dev, st)) return 1;
+        const size_t o0 = (size_t)k * H0 * P, o1 = (size_t)k * H1 * P, oo = (size_t)k * 2 * D * P, oy = (size_t)k * D * P;
+        add(a0t + o0, H0, cdot, C, Pn, Pn, 0, 0, W0, C + D, m0, nullptr);
+        add(a0b + o0, H0, ctx_dev, C, Pn, C, 1, B, W0, C + D, m0, g_bias_dev[k * (L + 1) + 0]);
+        add(a0t + o0, H0, ydot + oy, D, Pn, Pn, 0, 0, W0 + C, C + D, m0 + C, nullptr);
+        add(a0b + o0, H0, em_y + oy, D, Pn, Pn, 0, 0, W0 + C, C + D, m0 + C, nullptr);
+        add(a1t + o1, H1, h0d + o0, H0, Pn, Pn, 0, 0, W1, H0, m1, nullptr);
+        add(a1b + o1, H1, em_h0 + o0, H0, Pn, Pn, 0, 0, W1, H0, m1, g_bias_dev[k * (L + 1) + 1]);
+        add(ot + oo, 2 * D, h1d + o1, H1, Pn, Pn, 0, 0, Wo, H1, mo, nullptr);
+        add(ob + oo, 2 * D, em_h1 + o1, H1, Pn, Pn, 0, 0, Wo, H1, mo, g_bias_dev[k * (L + 1) + 2]);
+    }
+    wa.nd = nd;
+    k_wgrad<<<tiles, 256, 0, st>>>(wa);
+    h->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return rabi_fail(h, "k_wgrad launch failed: %s", cudaGetErrorString(e));
+    // the path through the reparameterised samples: reverse of the sampling chain seeded with d phi / d theta (overwrites the
+    // primal emissions, which the launch above has consumed), accumulating into the same gradient buffers
+    RABI_CU_OK(h, cudaMemsetAsync(zero_w, 0, P * sizeof(float), st));
+    const int rc = train_bwd(h, TC_RSB, ctx_dev, A_dev, z_dev, zero_w, theta_bar, S, B, nullptr, nullptr, nullptr, nullptr,
+                             g_weight_dev, g_bias_dev, st, nullptr, true);
+    if (rc == 2) return rabi_fail(h, "rabi_fisher_trace_bwd: shape not served by the sampling-chain reverse");
+    return rc;
+}
 
 // trace[b] = (1/S) sum_s ||score[s, b, :]||^2 ; one warp per row
 __global__ void k_score_trace(const float* __restrict__ score, int S, int B, int C, float* __restrict__ trace) {

@@ -150,6 +150,25 @@ class MafEngine:
                 self._check(self.L.rabi_maf_log_prob_fwd(self.h, _ptr(A), _ptr(theta), S, B, _ptr(out), self._stream()))
         return out
 
+    def _grad_buffers(self):
+        """[[(g_weight, g_bias) per layer] per transform] as views of ONE block laid out [W(k,l) | b(k,l)] in (k, l) order: the
+        library then clears all of them with a single memset."""
+        dims = [self.C + self.D] + list(self.hidden)
+        outs = list(self.hidden) + [2 * self.D]
+        total = self.K * sum(o * d + o for o, d in zip(outs, dims))
+        flat = torch.empty((total,), device=self.device, dtype=torch.float32)
+        grads, off = [], 0
+        for _ in range(self.K):
+            gk = []
+            for o, d in zip(outs, dims):
+                w = flat[off: off + o * d].view(o, d)
+                off += o * d
+                b = flat[off: off + o]
+                off += o
+                gk.append((w, b))
+            grads.append(gk)
+        return grads
+
     def fused_training_ok(self) -> bool:
         """rabi_maf_log_prob_bwd serves two-hidden-layer conditioners (the tensor-core path's shapes) without Permute layers."""
         import os
@@ -167,11 +186,7 @@ class MafEngine:
         g_A = torch.empty((self.K, self.hidden[0], B), device=self.device, dtype=torch.float32)
         grads, wp, bp = None, None, None
         if want_weights:
-            dims = [self.C + self.D] + list(self.hidden)
-            outs = list(self.hidden) + [2 * self.D]
-            grads = [[(torch.empty((outs[l], dims[l]), device=self.device, dtype=torch.float32),
-                       torch.empty((outs[l],), device=self.device, dtype=torch.float32)) for l in range(len(outs))]
-                     for _ in range(self.K)]
+            grads = self._grad_buffers()
             flat = [g for gk in grads for g in gk]
             wp = (ctypes.c_void_p * len(flat))(*[g[0].data_ptr() for g in flat])
             bp = (ctypes.c_void_p * len(flat))(*[g[1].data_ptr() for g in flat])
@@ -192,6 +207,25 @@ class MafEngine:
                 self._check(self.L.rabi_fisher_trace_fwd(self.h, _ptr(ctx_rows), _ptr(A), _ptr(z), _ptr(zs_std), S, B, _ptr(trace),
                                                          _ptr(score), _ptr(theta), self._stream()))
         return trace, score, theta
+
+    def fisher_trace_bwd(self, ctx_rows, A, z, zs_std, score, w_row, masked_weights, out_biases):
+        """Weight gradient of sum_b w_row[b] tr F(x_b) right after ``fisher_trace`` (same ctx_rows / A / z): the closed form on the
+        kernels (k_fim_dual + k_wgrad + the sampling-chain reverse).  masked_weights[k] = (W0*m0, W1*m1, Wo*mo) in the reference
+        layout, out_biases[k] = output-layer bias.  -> [[(g_weight, g_bias) per layer] per transform]."""
+        z, ctx_rows, score, w_row = _f32c(z), _f32c(ctx_rows), _f32c(score), _f32c(w_row)
+        S, B, _ = z.shape
+        grads = self._grad_buffers()
+        flat = [g for gk in grads for g in gk]
+        wp = (ctypes.c_void_p * len(flat))(*[g[0].data_ptr() for g in flat])
+        bp = (ctypes.c_void_p * len(flat))(*[g[1].data_ptr() for g in flat])
+        keep = [_f32c(w) for wk in masked_weights for w in wk] + [_f32c(b) for b in out_biases]
+        n = 3 * self.K
+        wm = (ctypes.c_void_p * n)(*[t.data_ptr() for t in keep[:n]])
+        bo = (ctypes.c_void_p * self.K)(*[t.data_ptr() for t in keep[n:]])
+        with torch.cuda.device(self.device):
+            self._check(self.L.rabi_fisher_trace_bwd(self.h, _ptr(ctx_rows), _ptr(A), _ptr(z), _ptr(zs_std), S, B, _ptr(score),
+                                                     _ptr(w_row), wm, bo, wp, bp, self._stream()))
+        return grads
 
     def train_emissions(self, S: int, B: int) -> dict:
         """Per-pair vectors of the last training-side kernel call (same S, B), as [K, units, P] views of one copied buffer."""
@@ -214,11 +248,7 @@ class MafEngine:
         g_A = torch.empty((self.K, self.hidden[0], B), device=self.device, dtype=torch.float32)
         grads, wp, bp = None, None, None
         if want_weights:
-            dims = [self.C + self.D] + list(self.hidden)
-            outs = list(self.hidden) + [2 * self.D]
-            grads = [[(torch.empty((outs[l], dims[l]), device=self.device, dtype=torch.float32),
-                       torch.empty((outs[l],), device=self.device, dtype=torch.float32)) for l in range(len(outs))]
-                     for _ in range(self.K)]
+            grads = self._grad_buffers()
             flat = [g for gk in grads for g in gk]
             wp = (ctypes.c_void_p * len(flat))(*[g[0].data_ptr() for g in flat])
             bp = (ctypes.c_void_p * len(flat))(*[g[1].data_ptr() for g in flat])

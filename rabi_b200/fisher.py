@@ -57,7 +57,7 @@ def fisher_trace(model, x: Tensor, mc_samples: int = 20, return_scores: bool = F
 
 
 def fisher_trace_weight_grad(model, x: Tensor, mc_samples: int, beta: float = 1.0, reduce: str = "mean",
-                             clamp_val: Optional[float] = None):
+                             clamp_val: Optional[float] = None, dense_products: Optional[bool] = None):
     """Value and WEIGHT GRADIENT of the regulariser  R = beta * reduce_b tr F(x_b)  (tr F estimated from ``mc_samples`` scores
     per row) without an autograd graph -- what ``FIMTraceRegularizer`` needs every training step
     (rbi/rbi/defenses/fisher_regularization.py:67-95: ``autograd.grad(reg, parameters)`` of the estimator with
@@ -74,8 +74,14 @@ def fisher_trace_weight_grad(model, x: Tensor, mc_samples: int, beta: float = 1.
          (adjoints of the tangent and of the primal variables);
       4. weight products  ot (x) h1dot + ob (x) h1,  a1t (x) h0dot + a1b (x) h0,  a0t (x) [ctxdot, ydot] + a0b (x) [ctx, y];
       5. the path through the samples: ``rabi_maf_rsample_bwd`` seeded with d phi / d theta.
-    Steps 2-4 are dense [units x pairs] products on ``rabi_sgemm`` with elementwise glue (about 60 launches instead of the
-    ~1700 of the op-by-op double backward).  -> (R (0-dim tensor), [grad per parameter, in ``model.parameters()`` order])."""
+    Steps 2-5 run as ``rabi_fisher_trace_bwd``: one kernel for the tangent pass and the dual reverse (``k_fim_dual``, 64 pairs per
+    CTA), one launch for the 24 stacked weight products (``k_wgrad``) and the sampling-chain reverse -- about 10 launches per
+    step instead of the ~1700 of the op-by-op double backward.  ``dense_products=True`` (or ``RABI_FIM_DENSE=1``) runs steps 2-4 as
+    [units x pairs] products on ``rabi_sgemm`` with elementwise glue instead: the same arithmetic written out, kept as the
+    cross-check of the kernel.  -> (R (0-dim tensor), [grad per parameter, in ``model.parameters()`` order])."""
+    import os
+    if dense_products is None:
+        dense_products = os.environ.get("RABI_FIM_DENSE", "0") == "1"
     from .autograd import _sgemm
     from .models import MAFPosterior, _split_embedding
 
@@ -97,7 +103,6 @@ def fisher_trace_weight_grad(model, x: Tensor, mc_samples: int, beta: float = 1.
         A = q.A
         # ---- 1. kernels: samples, primal passes, scores
         trace, score, theta = eng.fisher_trace(rows, A, z, std)
-        em = eng.train_emissions(S, B)
         finite = torch.isfinite(trace)
         tr = torch.where(finite, trace, torch.zeros_like(trace))
         live = finite
@@ -107,6 +112,15 @@ def fisher_trace_weight_grad(model, x: Tensor, mc_samples: int, beta: float = 1.
         n = finite.sum().clamp_min(1) if reduce == "mean" else torch.ones((), device=trace.device)
         reg = beta * tr.sum() / n
         w_row = torch.where(live, beta / (n * S), torch.zeros_like(trace))               # d R / d ||g_{s,b}||^2
+        if not dense_products:
+            mw, bo_ = [], []
+            for k in range(K):
+                net = getattr(model, "t" + str(k)).nn
+                mw.append([(l.weight.detach() * l.mask).contiguous() for l in net.layers])
+                bo_.append(net.layers[-1].bias.detach())
+            grads = eng.fisher_trace_bwd(rows, A, z, std, score, w_row, mw, bo_)
+            return reg, [t for gk in grads for wb in gk for t in wb]
+        em = eng.train_emissions(S, B)
         g = torch.nan_to_num(score.reshape(P, C))
         xdot = 2.0 * w_row.repeat(S).unsqueeze(1) * g                                     # [P, C]
         cdot = (xdot / std if std is not None else xdot).t().contiguous()                 # [C, P] tangent of the context rows

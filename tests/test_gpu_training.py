@@ -397,3 +397,22 @@ def test_closed_form_fisher_gradient_matches_reference_and_double_backward(case,
     assert abs(float(reg) - 0.05 * float(g["fim_trace"].mean())) <= 3 * RTOL * abs(0.05 * float(g["fim_trace"].mean()))
     _check_grads([t.cpu() for t in grads], g["fim_grads"], 3 * RTOL)
     print(f"\n[{name}] closed-form Fisher gradient: {eng.launches - n0} launches of the flow library")
+
+
+def test_fisher_dual_kernel_equals_dense_product_form(case, dev):
+    """k_fim_dual + k_wgrad (rabi_fisher_trace_bwd) against the same closed form written out as dense products on rabi_sgemm."""
+    from rabi_b200 import noise
+    from rabi_b200.fisher import fisher_trace_weight_grad
+
+    name, g, model = case
+    if not model.engine().fused_training_ok() or g["cfg"]["shuffle"]:
+        pytest.skip("closed form serves two-hidden-layer conditioners without Permute layers")
+    x = g["x"].to(dev)
+    outs = []
+    for dense in (False, True):
+        with noise.injected([g["z_fim"]]):
+            outs.append(fisher_trace_weight_grad(model, x, 5, beta=0.05, dense_products=dense))
+    assert abs(float(outs[0][0]) - float(outs[1][0])) <= 1e-6 * abs(float(outs[1][0]))
+    scale = max(float(t.abs().max()) for t in outs[1][1])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert float((a - b).abs().max()) <= RTOL * scale
