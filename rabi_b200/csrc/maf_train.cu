@@ -312,13 +312,14 @@ namespace rabi {
 // Fisher-trace regulariser, weight gradient (rbi/rbi/defenses/fisher_regularization.py:67-95 takes autograd.grad of the MC
 // estimator of rbi/rbi/utils/fisher_info.py:185-280 with create_graph=True).  Closed form, derivation and fp64 check in
 // oracle/fim_closed_form_check.py: with the scores g_p held constant, dR = sum_p d phi_p, phi_p = the derivative of
-// log q(theta_p | x) along xdot_p = 2 w_p g_p.  k_fim_dual runs, for a tile of 64 pairs per CTA,
+// log q(theta_p | x) along xdot_p = 2 w_p g_p.  k_fim_dual runs, for a tile of FD_NP pairs per CTA,
 //   * the TANGENT density pass (the primal pass with the stored ReLU masks instead of the sign tests, zero biases), and
 //   * the reverse over the (primal, tangent) program seeded on the tangent of log q: two masked reverse passes per transform
 //     (adjoints "t" of the tangent and "b" of the primal variables),
-// as a chain of small dense products [units x 64 pairs] on masked reference-layout weights (packed FMAs, inputs staged in shared
+// as a chain of small dense products [units x FD_NP pairs] on masked reference-layout weights (packed FMAs, inputs staged in shared
 // memory), and leaves every vector the stacked weight products need unit-major in global memory for k_wgrad.
-constexpr int FD_NP = 64;   // pairs per CTA
+constexpr int FD_NP = 16;            // pairs per CTA: 2560 pairs (batch 512 x 5 samples) spread over 160 CTAs
+constexpr int FD_TX = FD_NP / 4;     // threads across the pairs of a tile (4 pairs each); the other 256 / FD_TX walk the rows
 
 struct FimArgs {
     const float* W0[RABI_MAXK];   // [H0][C + D] weight * mask
@@ -338,13 +339,13 @@ struct FimArgs {
     float lo, hi;
 };
 
-// Out[m][0..63] (+)= sum_k W(m, k) In[k][0..63];  W(m, k) = TRANS ? W[k * ldw + m] : W[m * ldw + k]
+// Out[m][0..FD_NP) (+)= sum_k W(m, k) In[k][0..FD_NP);  W(m, k) = TRANS ? W[k * ldw + m] : W[m * ldw + k]
 template <bool TRANS>
 __device__ __forceinline__ void fd_prod(const float* __restrict__ W, int ldw, int M, int Kd, const float* In, float* Out, bool acc) {
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    for (int m = ty; m < M; m += 16) {
+    const int tx = threadIdx.x % FD_TX, ty = threadIdx.x / FD_TX;
+    for (int m = ty; m < M; m += 256 / FD_TX) {
         float4 a = acc ? *reinterpret_cast<const float4*>(Out + m * FD_NP + 4 * tx) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
         for (int k = 0; k < Kd; ++k) {
             const float w = __ldg(TRANS ? W + (size_t)k * ldw + m : W + (size_t)m * ldw + k);
             const float4 v = *reinterpret_cast<const float4*>(In + k * FD_NP + 4 * tx);
@@ -361,15 +362,15 @@ __global__ void __launch_bounds__(256) k_fim_dual(const FimArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int K = a.K, D = a.D, C = a.C, H0 = a.H0, H1 = a.H1, P = a.P;
     const int HM = max(H0, H1);
-    float* bC = sm;                       // [C][64]   cdot tile
-    float* bX = bC + C * FD_NP;           // [HM][64]
-    float* bY = bX + HM * FD_NP;          // [HM][64]
-    float* bOd = bY + HM * FD_NP;         // [2D][64]  tangent outputs | tangent-adjoint outputs
-    float* bOv = bOd + 2 * D * FD_NP;     // [2D][64]  primal outputs  | primal-adjoint outputs
-    float* bYd = bOv + 2 * D * FD_NP;     // [D][64]   ydot chain | ut chain
-    float* bUb = bYd + D * FD_NP;         // [D][64]   ub chain
+    float* bC = sm;                       // [C][FD_NP]   cdot tile
+    float* bX = bC + C * FD_NP;           // [HM][FD_NP]
+    float* bY = bX + HM * FD_NP;          // [HM][FD_NP]
+    float* bOd = bY + HM * FD_NP;         // [2D][FD_NP]  tangent outputs | tangent-adjoint outputs
+    float* bOv = bOd + 2 * D * FD_NP;     // [2D][FD_NP]  primal outputs  | primal-adjoint outputs
+    float* bYd = bOv + 2 * D * FD_NP;     // [D][FD_NP]   ydot chain | ut chain
+    float* bUb = bYd + D * FD_NP;         // [D][FD_NP]   ub chain
     const int p0 = blockIdx.x * FD_NP, tid = threadIdx.x, T = blockDim.x;
-    // element (row r, column c) of a [rows][64] tile <-> global [rows][P] at pair p0 + c: consecutive threads walk the pairs
+    // element (row r, column c) of a [rows][FD_NP] tile <-> global [rows][P] at pair p0 + c: consecutive threads walk the pairs
     auto gl = [&](const float* base, int r, int c) { return p0 + c < P ? base[(size_t)r * P + p0 + c] : 0.f; };
     auto gs = [&](float* base, int r, int c, float v) { if (p0 + c < P) base[(size_t)r * P + p0 + c] = v; };
     for (int i = tid; i < C * FD_NP; i += T) bC[i] = gl(a.cdot, i / FD_NP, i % FD_NP);
