@@ -12,7 +12,10 @@ best of ``attack_attemps`` is kept; the summary is mean + quantiles over the fin
 B200-first difference in *scheduling only*: the reference walks the data in ``batch_size`` chunks to bound memory
 (rbibm/utils/batched_processing.py:5-15).  Rows are independent except for the 1/batch factor in the attack
 gradient, so here all rows of a shard go through ONE call with that factor passed explicitly
-(``chunk_size``); results per row are identical to the chunked walk.
+(``chunk_size``); results per row are those of the chunked walk (overflowed estimates are replaced by the median of their own
+chunk, as there).  One stated deviation: a last, PARTIAL chunk is attacked with 1/chunk in front of its row gradients where the
+reference has 1/len(partial chunk); the factor cancels in the normalised step and only moves advertorch's 1e-6 gradient-norm
+floor, and the reference itself cannot evaluate ragged chunk splits (its ``vstack`` of per-chunk losses fails).
 """
 from __future__ import annotations
 
@@ -152,7 +155,10 @@ class RobustnessMetric(Metric):
                 q_tilde = self.model(x_tilde)
                 q = self._get_goal(x, target)
                 loss = self.loss_fn(q_tilde, q)
-                loss = self._ensure_loss_constraint(loss)
+                if chunk is None:
+                    loss = self._ensure_loss_constraint(loss)
+                else:   # the reference repairs overflowed estimates inside every ``batch_size`` chunk (median of THAT chunk)
+                    loss = torch.cat([self._ensure_loss_constraint(l) for l in torch.split(loss, chunk)])
             if i == 0:
                 xs_tilde, losses = x_tilde.detach(), loss.detach()
             else:
