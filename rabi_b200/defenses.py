@@ -54,7 +54,7 @@ class AdditiveRegularizer(Defense):
     @property
     def algorithm(self) -> str:
         if self._algorithm is None:
-            raise NotImplementedError("No algorithm to compute the regularizer is implemeneted")
+            raise NotImplementedError("this regulariser has no algorithm selected: call activate(algorithm=...)")
         return self._algorithm
 
     @algorithm.setter
@@ -145,7 +145,8 @@ class FIMTraceRegularizer(AdditiveRegularizer):
         double backward."""
         if self._closed_form_ok(input):
             from .fisher import fisher_trace_weight_grad
-            return fisher_trace_weight_grad(self.model, input, mc_samples, beta=self.beta, reduce=self.reduce,
+            # reduce "sum" is the mean as well in the reference (defenses/base.py:109-110, kept by _reduce above)
+            return fisher_trace_weight_grad(self.model, input, mc_samples, beta=self.beta, reduce="mean",
                                             clamp_val=self.clamp_val)
         reg = self._trace(input, output if output is not None else self.model(input), mc_samples)
         return reg, torch.autograd.grad(reg, params, retain_graph=True)
@@ -318,7 +319,7 @@ class DataAugmentationRegularizer(Defense):
         return self._transform
 
     def _transform(self, input: Tensor, target):
-        raise NotImplementedError("Transfrom not implemented")
+        raise NotImplementedError("a data-augmentation defense must define how it transforms (input, target)")
 
     def activate(self):
         self.loss_fn.register_pre_loss_regularizer(self.__class__.__name__, self.regularizer)
