@@ -700,3 +700,46 @@ def test_batched_eps_sweep_equals_one_attack_per_eps(shape, dev):
     vals = met.eval_sweep(xd, eps_rel)
     v = [float(vals[e]) for e in eps_rel]
     assert all(torch.isfinite(torch.tensor(v))) and v[0] < v[1] < v[2], v
+
+
+@pytest.mark.parametrize("kernel", ["k_warp", "k_fast2", "k_fast", "k_tc"])
+def test_every_attack_gradient_kernel_against_the_oracle_at_its_own_launch_size(kernel, dev):
+    """d[1/B sum_b KL(q(.|x~_b) || q(.|x_b))]/dx~ from each kernel family, at a launch size the dispatcher gives to THAT family,
+    against the oracle's autograd gradient on the same base noise (lotka_volterra shapes): k_warp (<= 1024 pairs), k_fast2 (two
+    lanes per pair, up to 40 pairs per SM), k_fast (thread per pair) and the tensor-core k_tc."""
+    import os
+
+    from oracle import rbi_oracle as O
+
+    B, env = {"k_warp": (200, {}), "k_fast2": (400, {"RABI_TC": "0"}), "k_fast": (2000, {"RABI_TC": "0", "RABI_FAST2": "0"}),
+              "k_tc": (2000, {})}[kernel]
+    shape = dict(SHAPES["lotka_volterra"], B=B)
+    ref, model, x = _fresh(shape, dev, seed=51)
+    S, D = 5, shape["D"]
+    z = torch.randn(S, B, D, generator=torch.Generator().manual_seed(6))
+    xt = x + 0.05 * torch.randn(B, shape["dx"], generator=torch.Generator().manual_seed(7))
+    # oracle: autograd through the MC reverse KL
+    xr = xt.clone().requires_grad_()
+    with O.injected_base_noise([z]):
+        loss = O.ReverseKLLoss(mc_samples=S)(ref(xr), ref(x))
+    loss.backward()
+    for q in ref.parameters():
+        q.grad = None
+    eng = model.engine()
+    os.environ.update(env)
+    try:
+        with torch.no_grad():
+            q = model(x.to(dev))
+            _, zs, _ = model.condition_inputs(x.to(dev))
+            gx, kl = eng.rkl_input_grad(xt.to(dev), zs[0], zs[1], q.A, z.to(dev), 1.0 / B)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    prone = relu_margins(ref, xt, x, z) < TAU
+    e = assert_trajectories_match(gx.cpu(), xr.grad, RTOL, prone=prone)
+    with torch.no_grad(), O.injected_base_noise([z]):
+        kl_ref = O.ReverseKLLoss(mc_samples=S, reduction=None)(ref(xt), ref(x))
+        lp_scale = float(ref(x).log_prob(ref(x).sample()).abs().max())
+    assert_kl_close(kl, kl_ref, lp_scale, f"{kernel}: per-row rKL of the attack loss")
+    print(f"\n[{kernel}, {S * B} pairs] input gradient vs oracle autograd: max row rel. err {float(e.max()):.2e} "
+          f"(near-kink rows {int(prone.sum())}/{B})")
