@@ -78,7 +78,7 @@ struct TdArgs {
     const TdPush* push;    // push tables
     int ps_off[RABI_MAXK][2], ps_cnt[RABI_MAXK][2];   // per transform: forward and reverse push streams
     float* vec;            // [(4K+2) D][stride]
-    uint32_t* bits;        // [2K][3][TD_MAXP][stride]
+    uint8_t* bits;         // [2K][3][TD_MAXP][stride] ReLU masks, one BYTE per piece (a piece has <= 8 units)
     int stride;            // grid * 128
 };
 
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
         const uint32_t tcol = tmem_base_s;
         const uint32_t trow = tcol + ((uint32_t)(32 * warp) << 16);
         float* vecp = a.vec + (blockIdx.x * 128 + tid);
-        uint32_t* bitp = a.bits + (blockIdx.x * 128 + tid);
+        uint8_t* bitp = a.bits + (blockIdx.x * 128 + tid);
         const size_t VS = (size_t)a.stride;
         float2* msp = ms + tid;
         const int oV = 0, oU = (K + 1) * D, oSHP = (2 * K + 1) * D, oSHQ = (3 * K + 1) * D, oG = (4 * K + 1) * D;
@@ -303,8 +303,11 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
             if (tile >= a.ntiles) break;
             const long long p = (long long)tile * 128 + tid;
             const bool live = p < a.npairs;
-            const long long pidx = live ? p : 0;
-            const int b = (int)(pidx % a.B);
+            // pairs are walked ROW-major (the S samples of an observation row sit in neighbouring lanes): the context projections
+            // A[k,u,b] of a row are then read once, by one warp, instead of once per sample by tiles of different rounds
+            // (4.6x fewer DRAM reads of A_p / A_q at pyloric size); pidx is the canonical index s * B + b of z / diff / theta
+            const int b = live ? (int)(p / a.S) : 0;
+            const long long pidx = live ? (long long)(p - (long long)b * a.S) * a.B + b : 0;
             float logp = 0.f, logq = 0.f;
             {
                 float ssq = 0.f;
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                 const int* permy = Wi + bk.permy;
                 const int* pstart = Wi + bk.pstart;                                   // [3][D + 1]
                 const TdPiece* pieces = reinterpret_cast<const TdPiece*>(Wi + bk.pieces);   // [3][TD_MAXP]
-                uint32_t* bits = bitp + (size_t)((seq ? k : K + k) * 3 * TD_MAXP) * VS;  // [layer][piece]
+                uint8_t* bits = bitp + (size_t)((seq ? k : K + k) * 3 * TD_MAXP) * VS;  // [layer][piece]
                 const int src = (k == K - 1) ? oV + K * D : oU + (k + 1) * D;
                 const int* ps0 = pstart;
                 const int* ps1 = pstart + (D + 1);
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                                 hv0[i] = on ? pre[i] : 0.f;
                                 cm |= on ? (1u << i) : 0u;
                             }
-                            if (GRADM) bits[(size_t)pi * VS] = cm;
+                            if (GRADM) bits[(size_t)pi * VS] = (uint8_t)cm;
                             if (c.flags & TD_F_FWD) stage_push(hv0);
                         }
                         const unsigned mark0 = e;
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                                 hv1[i] = on ? val : 0.f;
                                 cm |= on ? (1u << i) : 0u;
                             }
-                            if (GRADM) bits[(size_t)(TD_MAXP + pi) * VS] = cm;
+                            if (GRADM) bits[(size_t)(TD_MAXP + pi) * VS] = (uint8_t)cm;
                             if (c.flags & TD_F_FWD) stage_push(hv1);
                         }
                         const unsigned mark1 = e;
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) k_tcd(const MafImg g, const TdA
                                 hv2[i] = on ? val : 0.f;
                                 cm |= on ? (1u << i) : 0u;
                             }
-                            if (GRADM) bits[(size_t)(2 * TD_MAXP + pi) * VS] = cm;
+                            if (GRADM) bits[(size_t)(2 * TD_MAXP + pi) * VS] = (uint8_t)cm;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float2 wj = *reinterpret_cast<const float2*>(WoT + (size_t)(c.r0 + i) * 2 * DP + 2 * j);
@@ -783,7 +786,8 @@ struct TdState {
     int ps_off[RABI_MAXK][2], ps_cnt[RABI_MAXK][2];
     unsigned long long packed_version = ~0ull;
     float* vec = nullptr;
-    uint32_t* bits = nullptr;
+    uint8_t* bits = nullptr;   // inside the allocation of vec
+    size_t scratch_bytes = 0, l2_window = 0;
     size_t scratch_pairs = 0;
 };
 
@@ -796,7 +800,6 @@ static void td_free(TdState* s) {
     if (s->strip_tbl) cudaFree(s->strip_tbl);
     if (s->push) cudaFree(s->push);
     if (s->vec) cudaFree(s->vec);
-    if (s->bits) cudaFree(s->bits);
     s->blocks = nullptr;
     s->strips = nullptr;
     s->strip_tbl = nullptr;
@@ -1058,29 +1061,61 @@ int rabi_tcd_launch(rabi_maf* h, const TcCall& c, int mode, cudaStream_t st) {
         if (s->vec) {
             RABI_CU_OK(h, cudaDeviceSynchronize());
             cudaFree(s->vec);
-            cudaFree(s->bits);
             s->vec = nullptr;
             s->bits = nullptr;
         }
-        RABI_CU_OK(h, cudaMalloc(&s->vec, (size_t)(4 * K + 2) * D * pairs * sizeof(float)));
-        RABI_CU_OK(h, cudaMalloc(&s->bits, (size_t)2 * K * 3 * TD_MAXP * pairs * sizeof(uint32_t)));
+        // ONE allocation [chain vectors | ReLU bytes] so that a single L2 access-policy window covers the whole per-pair scratch
+        const size_t vec_bytes = (size_t)(4 * K + 2) * D * pairs * sizeof(float);
+        const size_t bits_bytes = (size_t)2 * K * 3 * TD_MAXP * pairs * sizeof(uint8_t);
+        RABI_CU_OK(h, cudaMalloc(&s->vec, vec_bytes + bits_bytes));
+        s->bits = reinterpret_cast<uint8_t*>(s->vec) + vec_bytes;
+        s->scratch_bytes = vec_bytes + bits_bytes;
         s->scratch_pairs = pairs;
+        // the scratch is rewritten and re-read by every tile round while A_p / A_q / gA stream through: ask for it to stay in L2
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+        s->l2_window = 0;
+        if (max_persist > 0 && max_window > 0 && rabi_env_int("RABI_TCD_L2_PERSIST", 1)) {
+            const size_t want = std::min<size_t>(s->scratch_bytes, (size_t)max_persist);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+                s->l2_window = std::min<size_t>(s->scratch_bytes, (size_t)max_window);
+            cudaGetLastError();
+        }
     }
     a.vec = s->vec;
     a.bits = s->bits;
     a.stride = (int)pairs;
     const size_t smem = (size_t)TD_NSLOT * TD_SLOT + (size_t)s->blk.words * 4 + (size_t)s->DP * 128 * sizeof(float2);
     if (smem > (size_t)h->max_smem_optin) return 2;
+    // L2 access-policy window over the per-pair scratch for this launch (persisting hits; everything else streams)
+    if (s->l2_window) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = s->vec;
+        av.accessPolicyWindow.num_bytes = s->l2_window;
+        av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    }
+    int rc = 2;
     switch (s->DP) {
 #ifndef RABI_LEAN
-        case 4: return td_launch_mode<4>(h, a, mode, grid, smem, st);
-        case 8: return td_launch_mode<8>(h, a, mode, grid, smem, st);
-        case 12: return td_launch_mode<12>(h, a, mode, grid, smem, st);
-        case 16: return td_launch_mode<16>(h, a, mode, grid, smem, st);
+        case 4: rc = td_launch_mode<4>(h, a, mode, grid, smem, st); break;
+        case 8: rc = td_launch_mode<8>(h, a, mode, grid, smem, st); break;
+        case 12: rc = td_launch_mode<12>(h, a, mode, grid, smem, st); break;
+        case 16: rc = td_launch_mode<16>(h, a, mode, grid, smem, st); break;
 #endif
-        case 32: return td_launch_mode<32>(h, a, mode, grid, smem, st);
+        case 32: rc = td_launch_mode<32>(h, a, mode, grid, smem, st); break;
     }
-    return 2;
+    if (s->l2_window) {   // later kernels on this stream see no window
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.num_bytes = 0;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    }
+    return rc;
 }
 
 void rabi_tcd_destroy(rabi_maf* h) {
