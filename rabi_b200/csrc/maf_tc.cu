@@ -1336,6 +1336,44 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
     a.xs_off = a.vec_words - C * RP;
     const size_t smem = (region + (size_t)a.vec_words) * 4;
     if (smem > budget) return 2;
+    // The slabs the kernel rewrites every iteration ([A_pert | gA], contiguous in the caller's workspace) are CTA-private and
+    // re-read within microseconds, while 0.8 MB of fresh base noise per iteration streams through L2: ask for the slabs to stay
+    // resident (persisting hits, everything else streaming) for the duration of this launch.
+    struct L2Window {
+        cudaStream_t st;
+        bool on = false;
+        L2Window(rabi_maf* h, cudaStream_t st_, const void* base, size_t bytes) : st(st_) {
+            if (!rabi_env_int("RABI_TC_L2_PERSIST", 1)) return;
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+            if (max_persist <= 0 || max_window <= 0) return;
+            static size_t limit_set = 0;
+            const size_t want = std::min<size_t>(bytes, (size_t)max_persist);
+            if (want > limit_set) {
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+                    cudaGetLastError();
+                    return;
+                }
+                limit_set = want;
+            }
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            on = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+            if (!on) cudaGetLastError();
+        }
+        ~L2Window() {
+            if (!on) return;
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+        }
+    } l2win(h, st, mode == TC_GRAD ? (const void*)r.A_p : (const void*)r.A_q, (size_t)2 * K * H0 * r.B * sizeof(float));
     if (rabi_env_int("RABI_TC_RUN_DBG", 0)) {   // development aid: cycle counters of CTA 0 per section of an iteration
         long long* d = nullptr;
         RABI_CU_OK(h, cudaMalloc(&d, 16 * sizeof(long long)));

@@ -11,6 +11,7 @@ from rabi_b200.models import ZScoreLayer  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "lotka_volterra_l2pgd_rkl"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
+N_IT = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 w = dict(bench.WORKLOADS[wl])
 dx, D = w["dx"], w["D"]
 dev = torch.device("cuda:0")
@@ -20,7 +21,7 @@ model = model.to(dev).eval()
 eng = model.engine()
 zm, zs = torch.zeros(dx, device=dev), torch.ones(dx, device=dev)
 x = torch.randn(B, dx, device=dev)
-for n_it in (20, 20):
+for n_it in (N_IT, N_IT):
     z = torch.randn(n_it, 5, B, D, device=dev)
     delta = torch.zeros_like(x)
     torch.cuda.synchronize()
