@@ -100,6 +100,12 @@ struct TcArgs {
     const float* eps_rows;      // optional per-row radius / step size
     const float* eps_iter_rows;
     const float* col_mask;      // optional [C] attack mask
+    // tensor-core tail (tct): the projection and the back-projection of a block as 3xTF32 MMAs with A AND B in shared memory
+    int tct;              // 0: the packed-FMA products
+    const float* pimg;    // [2 orientations][K][strip] context weights as (hi | lo) strips in the K-major core-matrix layout
+    int strip_words;      // floats per strip (both orientations padded to the same size)
+    int nch0, NB0;        // projection:      K dimension = C  in nch0 chunks of 4, N = NB0 (H0 rounded to 8)
+    int nch1, NB1;        // back-projection: K dimension = H0 in nch1 chunks of 4, N = NB1 (C rounded to 8)
     long long zstride;    // floats between the base noise of consecutive iterations (S * B * D)
     const float* wrow;    // TC_NLL: per-pair loss weights and the per-pair vectors for the weight-gradient products (maf_tc.h)
     float* em_h0;
@@ -133,6 +139,14 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
                  :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// A and B from shared memory (both K-major, no swizzle)
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// generic-proxy writes to shared memory (st.shared) become visible to the async proxy (the MMA's operand reads)
+__device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tc_smem_u32(mbar)) : "memory");
 }
@@ -203,14 +217,14 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
     const int* Wi = reinterpret_cast<const int*>(sm);
     float* vec = sm + a.region_words;                 // [threads][VS]
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(8) uint64_t mbar[TC_MAXTILES + 1];   // one per tile (MMA completion) + the block loader
+    __shared__ __align__(8) uint64_t mbar[TC_MAXTILES + 2];   // one per tile (MMA completion) + the block loader + the tail's MMAs
     const int tid = threadIdx.x, warp = tid >> 5, wg = warp >> 2, lane128 = tid & 127;
     const int NT = blockDim.x >> 7;
     const int K = g.K, D = g.D, H0 = g.H[0];
     const float HALF_LOG_2PI = 0.91893853320467274178f;
 
     if (tid == 0) {
-        for (int i = 0; i <= TC_MAXTILES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tc_smem_u32(&mbar[i])) : "memory");
+        for (int i = 0; i <= TC_MAXTILES + 1; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tc_smem_u32(&mbar[i])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -225,7 +239,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
     float* vecp = vec + (size_t)tid * a.VS;
     uint32_t* bitp = a.bits + (blockIdx.x * blockDim.x + tid);
     uint64_t* my_mbar = &mbar[wg];
-    uint32_t mphase = 0, wphase = 0;
+    uint32_t mphase = 0, wphase = 0, tphase = 0;
 
     const int oV = 0, oU = (K + 1) * D, oSHP = (2 * K + 1) * D, oSHQ = (3 * K + 1) * D, oG = (4 * K + 1) * D;
 
@@ -312,6 +326,49 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
         bulk_expect(wbytes);
         bulk_piece(0u, g.f + g.W0cT, wbytes);
     };
+    // ---- tensor-core tail (a.tct): both products as 3xTF32 MMAs with A and B in shared memory, D in the (idle) tensor memory
+    const int NCA = RUN ? max(a.nch0, a.nch1) : 0;   // chunks of 4 K-indices in the A-operand buffers
+    const int ACS = RT * 4 + 4;                      // floats per chunk of the A operand: RT rows x 4 + one quad of padding, so that
+                                                     // walks along the K index hit 32 different banks
+    float* Ahi = vec;                                // [NCA][ACS] hi halves of the A operand: z-scored x + delta rows | gA chunk
+    float* Alo = vec + (size_t)NCA * ACS;            //            lo halves
+    float* Gt2 = vec + (size_t)2 * NCA * ACS;        // [RT][CG]   input gradient of the block's rows
+    const uint32_t trow0 = tmem_base_s + ((uint32_t)(32 * (warp & 3)) << 16);   // this warp's lane quadrant, column 0
+    auto put_a = [&](int kidx, int r, float v) {     // element (row r, K-index kidx) of the A operand as TF32 (hi, lo)
+        const int off = (kidx >> 2) * ACS + r * 4 + (kidx & 3);
+        const float hi = tc_hi(v);
+        Ahi[off] = hi;
+        Alo[off] = v - hi;
+    };
+    auto load_strip = [&](int ori, int kk) {         // (hi | lo) weight strip of transform kk -> weight region
+        const uint32_t bytes = (uint32_t)a.strip_words * 4u;
+        bulk_expect(bytes);
+        bulk_piece(0u, a.pimg + ((size_t)ori * K + kk) * a.strip_words, bytes);
+    };
+    // D[128 x NB] (+)= A[128 x 4 nch] B^T as a 3xTF32 chain; callers made the A buffers visible (fence + barrier) and hold the strip
+    auto tail_mma = [&](uint32_t dcol, int nch, int NB, bool first) {
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t idesc = tc_make_idesc(128, NB);
+            const uint32_t lboA = (uint32_t)ACS * 4u, lboB = (uint32_t)NB * 16u;
+            const uint64_t ahi = tc_make_desc(tc_smem_u32(Ahi), lboA, 128u), alo = tc_make_desc(tc_smem_u32(Alo), lboA, 128u);
+            const uint64_t bhi = tc_make_desc(tc_smem_u32(Wb), lboB, 128u);
+            const uint64_t blo = tc_make_desc(tc_smem_u32(Wb) + (uint32_t)nch * lboB, lboB, 128u);
+            const uint64_t sa = (uint64_t)((2u * lboA) >> 4), sb = (uint64_t)((2u * lboB) >> 4);   // one K = 8 step = two chunks
+            const int nks = nch >> 1;
+            uint32_t acc = first ? 0u : 1u;
+            for (int ks = 0; ks < nks; ++ks) {
+                tc_mma_ss(tmem_base_s + dcol, ahi + ks * sa, bhi + ks * sb, idesc, acc);
+                acc = 1u;
+            }
+            for (int ks = 0; ks < nks; ++ks) tc_mma_ss(tmem_base_s + dcol, alo + ks * sa, bhi + ks * sb, idesc, 1u);
+            for (int ks = 0; ks < nks; ++ks) tc_mma_ss(tmem_base_s + dcol, ahi + ks * sa, blo + ks * sb, idesc, 1u);
+            tc_commit(&mbar[TC_MAXTILES + 1]);
+        }
+        tc_mbar_wait(&mbar[TC_MAXTILES + 1], tphase);
+        tphase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
 
     long long tmark = 0;
     auto mark = [&](int slot) {
@@ -348,23 +405,76 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
         if constexpr (RUN) {   // Xs <- ((x + delta_0) - mean) / std, rows of the block (lanes walk the context dimension)
             __syncthreads();
             resident = -1;
-            load_ctx_weights();
+            if (a.tct) load_strip(0, 0);
+            else load_ctx_weights();
             for (int r = warp; r < RT; r += nwarps) {
                 const bool in = r < nr;
-                for (int c = lane; c < C; c += 32) {
+                for (int c = lane; c < 4 * NCA; c += 32) {   // tct: the K-index padding [C, 4 NCA) is zero-filled as well
                     float v = 0.f;
-                    if (in) {
+                    if (in && c < C) {
                         v = a.x[(size_t)(b0 + r) * C + c] + a.delta[(size_t)(b0 + r) * C + c];
                         if (a.zmean) v = (v - a.zmean[c]) / a.zstd[c];
                     }
-                    Xs[c * RP + r] = v;
+                    if (a.tct) put_a(c, r, v);
+                    else if (c < C) Xs[c * RP + r] = v;
                 }
+                if (!a.tct)
+                    for (int c = 4 * NCA + lane; c < C; c += 32) {   // (NCA may be 0 without the tensor-core tail)
+                        float v = 0.f;
+                        if (in) {
+                            v = a.x[(size_t)(b0 + r) * C + c] + a.delta[(size_t)(b0 + r) * C + c];
+                            if (a.zmean) v = (v - a.zmean[c]) / a.zstd[c];
+                        }
+                        Xs[c * RP + r] = v;
+                    }
             }
+            if (a.tct) tc_fence_async_smem();
         }
       for (int it = 0; it < (RUN ? a.nb_iter : 1); ++it) {
         if constexpr (RUN) {
             // ================= projection of the block's rows: A[k,u,b] = b0_k[u] + sum_c W0_k[u,c] ctx[b,c] =================
             mark(-1);
+            if (a.tct) {
+                // ---- tensor cores: per transform D[:, kk NB0 ..] = X~ W0c_kk^T (A = the (hi, lo) rows in shared memory, B = the strip)
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();                      // the A operand is complete and fenced for the async proxy
+                for (int kk = 0; kk < K; ++kk) {
+                    if (kk) load_strip(0, kk);
+                    bulk_wait();
+                    tail_mma((uint32_t)(kk * a.NB0), a.nch0, a.NB0, true);
+                }
+                mark(0);
+                const int row = 32 * (warp & 3) + lane, part = warp >> 2, nparts = nwarps >> 2, H0q = (H0 + 3) >> 2;
+                for (int i0 = part; i0 < K * H0q; i0 += 5 * nparts) {
+                    float4 v[5];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const int i = i0 + j * nparts;
+                        const int kk = i / H0q, u = 4 * (i - kk * H0q);
+                        v[j] = i < K * H0q ? tc_ld4(trow0 + (uint32_t)(kk * a.NB0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                                 : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[0].z), "+f"(v[0].w), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[1].z), "+f"(v[1].w),
+                                   "+f"(v[2].x), "+f"(v[2].y), "+f"(v[2].z), "+f"(v[2].w), "+f"(v[3].x), "+f"(v[3].y), "+f"(v[3].z), "+f"(v[3].w),
+                                   "+f"(v[4].x), "+f"(v[4].y), "+f"(v[4].z), "+f"(v[4].w) :: "memory");
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const int i = i0 + j * nparts;
+                        if (i < K * H0q && row < nr) {
+                            const int kk = i / H0q, u = 4 * (i - kk * H0q);
+                            const float vals[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (u + e < H0)
+                                    __stcg(pertA + ((size_t)kk * H0 + u + e) * a.B + b0 + row, vals[e] + __ldg(g.f + g.t[kk].b0 + u + e));
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();                      // the projection is visible to the block; tensor memory free for the tiles
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                mark(1);
+            } else {
             __syncthreads();                          // Xs complete
             bulk_wait();
             mark(0);                              // context weights (issued before the update / the first Xs)
@@ -419,6 +529,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             }
             __syncthreads();                          // the projection is visible to the block; Xs and the weights are dead
             mark(1);
+            }
         }
         const float* zit = a.z + (RUN ? (size_t)it * (size_t)a.zstride : (size_t)0);
         float logp = 0.f, logq = 0.f;
@@ -754,6 +865,59 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             __syncthreads();
             mark(2);
             resident = -1;
+            const int CG = (C + 7) & ~7;
+            const float* Gsrc = a.tct ? Gt2 : vec;    // the gradient tile [row][CG] the update reads
+            if (a.tct) {
+                // ---- tensor cores: D[:, 0 .. NB1) = sum_kk gA_kk^T W0c_kk (A = the cotangent chunk as (hi, lo) rows, B = the strip)
+                for (int kk = 0; kk < K; ++kk) {
+                    load_strip(1, kk);
+                    const int n = NCA * RT, T = (int)blockDim.x;   // items = (chunk of 4 units, row), row fastest: coalesced slab reads
+                    for (int base = tid; base < n; base += 4 * T) {
+                        float v[4][4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int idx = base + i * T;
+                            const int q = idx / RT, r = idx - q * RT;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int u = 4 * q + e;
+                                v[i][e] = (idx < n && u < H0 && r < nr) ? __ldcg(a.gA + ((size_t)kk * H0 + u) * a.B + b0 + r) : 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int idx = base + i * T;
+                            if (idx < n) {
+                                const int q = idx / RT, r = idx - q * RT;
+                                const float h0 = tc_hi(v[i][0]), h1 = tc_hi(v[i][1]), h2 = tc_hi(v[i][2]), h3 = tc_hi(v[i][3]);
+                                *reinterpret_cast<float4*>(Ahi + q * ACS + r * 4) = make_float4(h0, h1, h2, h3);
+                                *reinterpret_cast<float4*>(Alo + q * ACS + r * 4) =
+                                    make_float4(v[i][0] - h0, v[i][1] - h1, v[i][2] - h2, v[i][3] - h3);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (4 * q + e < H0 && r < nr) __stcg(a.gA + ((size_t)kk * H0 + 4 * q + e) * a.B + b0 + r, 0.f);
+                            }
+                        }
+                    }
+                    tc_fence_async_smem();
+                    bulk_wait();
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncthreads();
+                    tail_mma(0u, a.nch1, a.NB1, kk == 0);
+                }
+                mark(3);
+                const int row = 32 * (warp & 3) + lane, part = warp >> 2, nparts = nwarps >> 2;
+                for (int i = part; i < (CG >> 2); i += nparts) {
+                    float4 v = tc_ld4(trow0 + (uint32_t)(4 * i));
+                    tc_wait_ld(v);
+                    if (row < RT) *reinterpret_cast<float4*>(Gt2 + (size_t)row * CG + 4 * i) = v;
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();                      // gradient tile complete; A buffers, strip and tensor memory free
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                mark(4);
+                if (it + 1 < a.nb_iter) load_strip(0, 0);   // the next projection's first strip arrives while the update runs
+            } else {
             const int ldc = g.t[0].ldc, KH = K * H0;  // the K context blocks [H0][ldc] land back to back: row kk * H0 + u
             {
                 const uint32_t nbytes = (uint32_t)H0 * (uint32_t)ldc * 4u;
@@ -819,7 +983,6 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
             mark(4);
             if (it + 1 < a.nb_iter) load_ctx_weights();   // arrives while the update runs
             // the groups add their partial sums into the row-major gradient tile Gt[row][CG] in turn (128-bit accesses)
-            const int CG = (C + 7) & ~7;
             for (int gi = 0; gi < G; ++gi) {
                 if (worker && grp == gi) {
 #pragma unroll
@@ -837,6 +1000,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                     }
                 }
                 __syncthreads();
+            }
             }
             mark(5);
             // ================= advertorch perturb_iterative(ord=2) update, one warp per row; Xs for the next projection =================
@@ -874,7 +1038,7 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                             const int c = lane + 32 * e;
                             float v = 0.f;
                             if (r < nr && c < C) {
-                                v = vec[(size_t)r * CG + c];
+                                v = Gsrc[(size_t)r * CG + c];
                                 if (a.zstd) v /= isd[e];
                                 v *= mk[e];
                             }
@@ -925,11 +1089,15 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                     v = xv[q][e] + d;
                                     if (a.zmean) v = (v - mu[e]) / isd[e];
                                 }
-                                Xn[c * RP + r] = v;
+                                if (a.tct) put_a(c, r, v);
+                                else Xn[c * RP + r] = v;
                             }
                         }
+                        if (a.tct)   // K-index padding of the A operand (the cotangent chunks used the same buffers)
+                            for (int c = C + lane; c < 4 * NCA; c += 32) put_a(c, r, 0.f);
                     }
                 }
+                if (a.tct) tc_fence_async_smem();
             }
         }
         if constexpr (RUN) {
@@ -983,6 +1151,27 @@ __global__ void k_tc_pack(const MafImg g, TcBlk b0, TcBlk b1, int blk_words, int
     for (int o = t0; o < 2 * DP; o += stride) out[bk.bo + o] = o < 2 * t.ldt ? f[t.boF + o] : 0.f;
 }
 
+// Context weights of the persistent kernel's tensor-core tail: per (orientation, transform) a (hi | lo) strip in the K-major
+// core-matrix layout [k/4][n][4] (zero-filled by the host):
+//   orientation 0 (projection):      n = layer-0 unit u, k = context column c      strip[hl][c/4][u][c%4] = W0c_k[u][c]
+//   orientation 1 (back-projection): n = context column c, k = layer-0 unit u      strip[hl][u/4][c][u%4] = W0c_k[u][c]
+__global__ void k_tc_pack_ctx(const MafImg g, int strip_words, int nch0, int NB0, int nch1, int NB1, float* __restrict__ img) {
+    const int k = blockIdx.y, C = g.C, H0 = g.H[0];
+    const TImg t = g.t[k];
+    float* s0 = img + (size_t)k * strip_words;
+    float* s1 = img + ((size_t)g.K + k) * strip_words;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < H0 * C; o += gridDim.x * blockDim.x) {
+        const int u = o / C, c = o % C;
+        const float w = g.f[t.W0c + (size_t)u * t.ldc + c];
+        const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u), lo = w - hi;
+        const int a0 = ((c >> 2) * NB0 + u) * 4 + (c & 3), a1 = ((u >> 2) * NB1 + c) * 4 + (u & 3);
+        s0[a0] = hi;
+        s0[(size_t)nch0 * NB0 * 4 + a0] = lo;
+        s1[a1] = hi;
+        s1[(size_t)nch1 * NB1 * 4 + a1] = lo;
+    }
+}
+
 struct TcState {
     bool built = false, eligible = false;
     int DP = 4;
@@ -994,6 +1183,9 @@ struct TcState {
     unsigned long long packed_version = ~0ull;
     uint32_t* bits = nullptr;
     size_t bits_words = 0;
+    float* pimg = nullptr;   // strips of the persistent kernel's tensor-core tail
+    size_t pimg_words = 0;
+    unsigned long long pimg_version = ~0ull;
 };
 
 static inline int r4(int x) { return (x + 3) & ~3; }
@@ -1285,9 +1477,14 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
         if ((t.ldc & 3) || (t.W0c & 3)) return 2;
         wsum += (size_t)H0 * t.ldc;
     }
-    // (the 8-wide unit / column tiles of the two products may read a few floats past a row end: still inside shared memory,
+    // (the 8-wide unit / column tiles of the two FMA products may read a few floats past a row end: still inside shared memory,
     //  and those accumulators are never stored)
-    const size_t region = (std::max(std::max((size_t)s->blk_words, (size_t)C * g.ldKH), wsum) + 31) & ~(size_t)31;
+    // tensor-core tail: strips of both orientations padded to one size; D needs K * NB0 tensor-memory columns
+    const int nch0 = 2 * ((C + 7) / 8), NB0 = (H0 + 7) & ~7, nch1 = 2 * ((H0 + 7) / 8), NB1 = (C + 7) & ~7;
+    const size_t strip_words = (size_t)2 * 4 * std::max((size_t)nch0 * NB0, (size_t)nch1 * NB1);
+    const bool tct = rabi_env_int("RABI_TC_TAIL", 1) && K * NB0 <= 512 && NB0 <= 256 && NB1 <= 256;
+    const size_t region = ((tct ? std::max((size_t)s->blk_words, strip_words)
+                                : std::max(std::max((size_t)s->blk_words, (size_t)C * g.ldKH), wsum)) + 31) & ~(size_t)31;
     a.region_words = (int)region;
     const size_t budget = (size_t)h->max_smem_optin - 1024;
     int NT = TC_MAXTILES;
@@ -1300,6 +1497,8 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
     auto tail_words = [&](int R_) {
         const size_t RP_ = (size_t)((R_ + 7) & ~7) + 4;
         const size_t CG_ = (size_t)((C + 7) & ~7);
+        if (tct)   // A-operand buffers (hi | lo) [NCA][RT][4] + gradient tile [RT][CG] (+ the MMA's reads past row RT: finite garbage)
+            return (size_t)2 * std::max(nch0, nch1) * ((RP_ - 4) * 4 + 4) + (RP_ - 4) * CG_ + 1024;
         return std::max((size_t)K * H0 * RP_, RP_ * CG_ + (size_t)C * RP_);   // cotangent tile | gradient tile [RP][CG] + Xs [C][RP]
     };
     int Rmax = ((NT * 128) / r.S) & ~3;
@@ -1332,6 +1531,34 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
     a.zstride = (long long)r.S * r.B * h->D;
     const int grid = std::min(nblocks, h->sm_count);
     const int T = NT * 128;
+    a.tct = tct ? 1 : 0;
+    if (tct) {
+        const size_t need = (size_t)2 * K * strip_words;
+        if (need > s->pimg_words) {
+            if (s->pimg) {
+                RABI_CU_OK(h, cudaDeviceSynchronize());
+                RABI_CU_OK(h, cudaFree(s->pimg));
+                s->pimg = nullptr;
+            }
+            RABI_CU_OK(h, cudaMalloc(&s->pimg, need * sizeof(float)));
+            s->pimg_words = need;
+            s->pimg_version = ~0ull;
+        }
+        if (s->pimg_version != h->weights_version) {
+            RABI_CU_OK(h, cudaMemsetAsync(s->pimg, 0, need * sizeof(float), st));
+            k_tc_pack_ctx<<<dim3(16, K), 256, 0, st>>>(h->img, (int)strip_words, nch0, NB0, nch1, NB1, s->pimg);
+            h->launches++;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return rabi_fail(h, "k_tc_pack_ctx launch failed: %s", cudaGetErrorString(e));
+            s->pimg_version = h->weights_version;
+        }
+        a.pimg = s->pimg;
+        a.strip_words = (int)strip_words;
+        a.nch0 = nch0;
+        a.NB0 = NB0;
+        a.nch1 = nch1;
+        a.NB1 = NB1;
+    }
     a.vec_words = (int)std::max((size_t)T * a.VS, tail_words(R));
     a.xs_off = a.vec_words - C * RP;
     const size_t smem = (region + (size_t)a.vec_words) * 4;
@@ -1405,6 +1632,7 @@ void rabi_tc_destroy(rabi_maf* h) {
     if (s->img) cudaFree(s->img);
     if (s->maps) cudaFree(s->maps);
     if (s->bits) cudaFree(s->bits);
+    if (s->pimg) cudaFree(s->pimg);
     delete s;
     h->tc = nullptr;
 }
