@@ -444,14 +444,24 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                     tail_mma((uint32_t)(kk * a.NB0), a.nch0, a.NB0, true);
                 }
                 mark(0);
+                // epilogue: D (lane = row) -> + bias -> transposed through the (now dead) weight region [K H0][RT] -> 128-bit stores of
+                // four consecutive rows into the CTA's slab A[k,u,b0 + .]
                 const int row = 32 * (warp & 3) + lane, part = warp >> 2, nparts = nwarps >> 2, H0q = (H0 + 3) >> 2;
+                // (item i <-> (transform kk, unit quad uq) is advanced incrementally: no integer divisions in the loop)
+                int kk_i = part / H0q, uq_i = part - kk_i * H0q;
                 for (int i0 = part; i0 < K * H0q; i0 += 5 * nparts) {
                     float4 v[5];
+                    int kks[5], uqs[5];
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
-                        const int i = i0 + j * nparts;
-                        const int kk = i / H0q, u = 4 * (i - kk * H0q);
-                        v[j] = i < K * H0q ? tc_ld4(trow0 + (uint32_t)(kk * a.NB0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        kks[j] = kk_i;
+                        uqs[j] = uq_i;
+                        v[j] = kk_i < K ? tc_ld4(trow0 + (uint32_t)(kk_i * a.NB0 + 4 * uq_i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        uq_i += nparts;
+                        while (uq_i >= H0q) {
+                            uq_i -= H0q;
+                            ++kk_i;
+                        }
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;"
                                  : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[0].z), "+f"(v[0].w), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[1].z), "+f"(v[1].w),
@@ -459,14 +469,33 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
                                    "+f"(v[4].x), "+f"(v[4].y), "+f"(v[4].z), "+f"(v[4].w) :: "memory");
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
-                        const int i = i0 + j * nparts;
-                        if (i < K * H0q && row < nr) {
-                            const int kk = i / H0q, u = 4 * (i - kk * H0q);
+                        if (kks[j] < K && row < RT) {
+                            const int u = 4 * uqs[j];
+                            float* dst = Wb + (kks[j] * H0 + u) * RT + row;
                             const float vals[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                if (u + e < H0)
-                                    __stcg(pertA + ((size_t)kk * H0 + u + e) * a.B + b0 + row, vals[e] + __ldg(g.f + g.t[kk].b0 + u + e));
+                                if (u + e < H0) dst[e * RT] = vals[e];   // (the bias joins in the store loop)
+                        }
+                    }
+                }
+                __syncthreads();
+                {
+                    const int RQ = RT >> 2, n = K * H0 * RQ;
+                    const bool vec4 = (a.B & 3) == 0;   // b0 is a multiple of 4
+                    for (int i = tid; i < n; i += (int)blockDim.x) {
+                        const int j = i / RQ, r0 = 4 * (i - j * RQ), kk = j / H0;
+                        const float bias = __ldg(g.f + g.t[kk].b0 + (j - kk * H0));
+                        float4 v = *reinterpret_cast<const float4*>(Wb + j * RT + r0);
+                        v = make_float4(v.x + bias, v.y + bias, v.z + bias, v.w + bias);
+                        float* out = pertA + (size_t)j * a.B + b0 + r0;
+                        if (vec4 && r0 + 3 < nr) {
+                            __stcg(reinterpret_cast<float4*>(out), v);
+                        } else {
+                            const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (r0 + e < nr) __stcg(out + e, vals[e]);
                         }
                     }
                 }
@@ -1502,7 +1531,8 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
         return std::max((size_t)K * H0 * RP_, RP_ * CG_ + (size_t)C * RP_);   // cotangent tile | gradient tile [RP][CG] + Xs [C][RP]
     };
     int Rmax = ((NT * 128) / r.S) & ~3;
-    while (Rmax >= 4 && tail_words(Rmax) > spare) Rmax -= 4;
+    // (tensor-core tail: the projection epilogue transposes [K H0][round8(R)] through the weight region)
+    while (Rmax >= 4 && (tail_words(Rmax) > spare || (tct && (size_t)K * H0 * ((Rmax + 7) & ~7) > region))) Rmax -= 4;
     if (Rmax < 4) return 2;
     const int rounds = (r.B + h->sm_count * Rmax - 1) / (h->sm_count * Rmax);
     int R = ((r.B + h->sm_count * rounds - 1) / (h->sm_count * rounds) + 3) & ~3;
