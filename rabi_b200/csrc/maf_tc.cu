@@ -1607,12 +1607,14 @@ int rabi_tc_run(rabi_maf* h, const TcRunCall& r, int mode, cudaStream_t st) {
             if (max_persist <= 0 || max_window <= 0) return;
             static size_t limit_set = 0;
             const size_t want = std::min<size_t>(bytes, (size_t)max_persist);
-            if (want > limit_set) {
-                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+            // the carve-out is set-associative: some slack over the window keeps colliding lines resident too
+            const size_t carve = std::min<size_t>((size_t)max_persist, bytes * (size_t)rabi_env_int("RABI_TC_L2_CARVE_PCT", 100) / 100);
+            if (carve > limit_set) {
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) {
                     cudaGetLastError();
                     return;
                 }
-                limit_set = want;
+                limit_set = carve;
             }
             cudaStreamAttrValue av;
             memset(&av, 0, sizeof(av));
