@@ -197,6 +197,7 @@ class FIMTraceRegularizer(AdditiveRegularizer):
                     # the engine touch them would join the capturing stream with the legacy stream.
                     from torch.nn.utils import stateless
                     leaves = {n: p.detach().requires_grad_() for n, p in self.model.named_parameters()}
+                    self.model.invalidate()   # the graph carries its own re-pack of the weight image (see graphs.py)
                     with stateless._reparametrize_module(self.model, leaves):
                         with noise.injected([st["z"]]):
                             _, grads = self._reg_and_grads(st["x"], None, self.ema_mc_samples,

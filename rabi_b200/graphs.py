@@ -28,23 +28,35 @@ class _Replay(torch.autograd.Function):
     def forward(ctx, st, n_in, *args):
         inputs = args[:n_in]
         ctx.st = st
-        # every call keeps its own copy of the inputs: its backward re-stages them, so several forwards of one signature
-        # may precede their backwards (gradient accumulation, several pre-loss regularisers)
-        ctx.inputs = [t.detach().clone() for t in inputs]
+        # the call remembers its inputs (by reference + version counter) and the staging generation: when no other forward of
+        # this signature ran in between, its backward finds them still staged; otherwise it stages them again, so several
+        # forwards may precede their backwards (gradient accumulation, several pre-loss regularisers)
+        ctx.inputs = [t.detach() for t in inputs]
+        ctx.versions = [t._version for t in inputs]
         for dst, src in zip(st["in"], ctx.inputs):
             dst.copy_(src)
+        st["gen"] += 1
+        ctx.gen = st["gen"]
         st["fwd"].replay()
         return st["out"].clone()
 
     @staticmethod
     def backward(ctx, gout):
         st = ctx.st
-        for dst, src in zip(st["in"], ctx.inputs):
-            dst.copy_(src)
+        if st["gen"] != ctx.gen:
+            for t, v in zip(ctx.inputs, ctx.versions):
+                if t._version != v:
+                    raise RuntimeError("rabi_b200: an input of a graphed training segment was modified in place before its backward")
+            for dst, src in zip(st["in"], ctx.inputs):
+                dst.copy_(src)
+            st["gen"] += 1   # (the staged inputs now belong to nobody's forward)
         st["gout"].copy_(gout)
         st["bwd"].replay()
-        # clones: autograd may adopt the returned tensors as .grad, and the static buffers are rewritten next step
-        return (None, None) + (None,) * len(ctx.inputs) + tuple(g.clone() for g in st["grads"])
+        # ONE copy of the flat gradient block: autograd may adopt the returned tensors as .grad, and the static buffer is
+        # rewritten by the next replay; the per-parameter gradients are views of the copy
+        flat = st["flat"].clone()
+        return (None, None) + (None,) * len(ctx.inputs) + tuple(
+            flat[o: o + n].view(shape) for o, n, shape in st["slices"])
 
 
 class GraphedParamFunction:
@@ -55,13 +67,20 @@ class GraphedParamFunction:
         self._seen: Dict[tuple, int] = {}
         self._graphs: Dict[tuple, dict] = {}
         self._failed: set = set()
+        self._last = None   # (input objects, key, parameter list) of the latest ready(): __call__ follows with the same inputs
 
     def _key(self, inputs: Sequence[Tensor]):
-        return (tuple((tuple(t.shape), t.dtype, t.device) for t in inputs),
-                tuple(id(p) for p in self.module.parameters()))
+        last = self._last
+        if last is not None and len(last[0]) == len(inputs) and all(a is b for a, b in zip(last[0], inputs)):
+            return last[1]
+        params = list(self.module.parameters())   # one walk of the module tree per step
+        key = (tuple((tuple(t.shape), t.dtype, t.device) for t in inputs), tuple(id(p) for p in params))
+        self._last = (tuple(inputs), key, params)
+        return key
 
     def ready(self, inputs: Sequence[Tensor]) -> bool:
         """True once this input signature has been seen ``warmup`` times (the eager calls warm every lazy init up)."""
+        self._last = None
         key = self._key(inputs)
         if key in self._failed:
             return False
@@ -77,7 +96,12 @@ class GraphedParamFunction:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             fwd = torch.cuda.CUDAGraph()
+            # The device weight image is re-packed when the HOST sees new parameter versions -- a check no replay runs.  Each
+            # graph therefore captures its own re-pack (module.invalidate() forces one inside the capture): replays read the
+            # live parameter storage whatever happened to the weights since the capture.
+            invalidate = getattr(self.module, "invalidate", lambda: None)
             with torch.cuda.graph(fwd, stream=side):
+                invalidate()
                 # under enable_grad on purpose: the differentiable path (rabi_sgemm + glue) has no host-side state,
                 # whereas the inference path re-packs the weight image only when the host sees a new parameter version
                 with torch.enable_grad():
@@ -86,10 +110,17 @@ class GraphedParamFunction:
             bwd = torch.cuda.CUDAGraph()
             with torch.cuda.graph(bwd, stream=side):
                 leaves = {n: p.detach().requires_grad_() for n, p in self.module.named_parameters()}
+                invalidate()
                 with stateless._reparametrize_module(self.module, leaves), torch.enable_grad():
                     out = self.fn(*st["in"])
                 grads = torch.autograd.grad(out, [leaves[n] for n in names], grad_outputs=st["gout"], allow_unused=True)
-                st["grads"] = [g if g is not None else torch.zeros_like(leaves[n]) for g, n in zip(grads, names)]
+                grads = [g if g is not None else torch.zeros_like(leaves[n]) for g, n in zip(grads, names)]
+                st["flat"] = torch.cat([g.reshape(-1) for g in grads])   # (one launch inside the graph)
+        st["slices"], off = [], 0
+        for g_ in grads:
+            st["slices"].append((off, g_.numel(), tuple(g_.shape)))
+            off += g_.numel()
+        st["gen"] = 0
         torch.cuda.current_stream(dev).wait_stream(side)
         st["fwd"], st["bwd"] = fwd, bwd
         self._graphs[key] = st
@@ -110,4 +141,6 @@ class GraphedParamFunction:
                 self._failed.add(key)
                 torch.cuda.synchronize()
                 return self.fn(*inputs)
-        return _Replay.apply(st, len(inputs), *inputs, *self.module.parameters())
+        params = self._last[2]
+        self._last = None   # (do not keep the batch alive)
+        return _Replay.apply(st, len(inputs), *inputs, *params)

@@ -174,6 +174,10 @@ class TrainLoss(Loss):
                     input, target = pre_regularizer(input, target)
                     output = self.model(input)
                     loss += self._loss(output, target, input) / len(self.pre_loss_regularizers)
+            if len(self.post_loss_regularizers) == 0:
+                # nothing to add: the reference's "+ (zeros(1) - zeros(1))" only broadcasts the result to at least one dimension
+                out = reduce(loss, self.reduction, None)
+                return out.reshape(1) if out.dim() == 0 else out
             post_reg = torch.zeros(1, device=input.device)
             for post_regularizer in self.post_loss_regularizers.values():
                 post_reg += post_regularizer(input, output, target)

@@ -226,6 +226,41 @@ def test_graphed_nll_with_two_forwards_before_one_backward(dev):
         assert float((a.grad - b.grad).abs().max()) <= 1e-4 * scale
 
 
+def test_graphs_captured_before_any_weight_change_follow_later_updates(dev):
+    """A graph captured while the packed weight image was current (three calls without an optimizer step in between) must
+    still see later parameter updates: every captured graph carries its own re-pack of the image."""
+    import copy
+
+    from rabi_b200.defenses import FIMTraceRegularizer
+    from rabi_b200.loss import NLLLoss
+
+    g = load_golden("lotka_volterra")
+    m1 = build_product(g, dev, with_output_transform=False).train()
+    gen = torch.Generator().manual_seed(9)
+    x = (torch.randn(64, g["cfg"]["dx"], generator=gen) * g["zs_std"] + g["zs_mean"]).to(dev)
+    th = torch.randn(64, g["cfg"]["D"], generator=gen).to(dev)
+    lf1 = NLLLoss(m1, cuda_graph=True).train()
+    for _ in range(4):   # warm-up, capture, one replay: no parameter changes anywhere
+        m1.zero_grad()
+        lf1(x, th).backward()
+    assert lf1._graphed._graphs
+    with torch.no_grad():
+        for p in m1.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen).to(dev))
+    m2 = copy.deepcopy(m1).to(dev).train()
+    lf2 = NLLLoss(m2, cuda_graph=False).train()
+    losses = []
+    for m, lf in ((m1, lf1), (m2, lf2)):
+        m.zero_grad()
+        loss = lf(x, th)
+        loss.backward()
+        losses.append(float(loss.detach().reshape(-1)[0]))
+    assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[1]), losses
+    scale = max(float(p.grad.abs().max()) for p in m2.parameters())
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert float((a.grad - b.grad).abs().max()) <= 1e-4 * scale
+
+
 @pytest.mark.parametrize("shape", [dict(dx=100, D=4, hidden=[100, 100], B=512, S=1), dict(dx=10, D=10, hidden=[100, 100], B=130, S=1),
                                    dict(dx=12, D=3, hidden=[64, 48], B=77, S=3), dict(dx=20, D=4, hidden=[32, 32], B=9, S=2)])
 def test_fused_log_prob_backward_equals_the_op_by_op_graph(shape, dev):
