@@ -22,11 +22,14 @@ NVCC_FLAGS = [
 ]
 # translation units and the headers each one depends on (an object is rebuilt when one of them is newer)
 _COMMON = ["rabi_internal.h", "maf_image.h", "maf_tc.h"]
+# object -> (source, extra defines, headers)
 SOURCES = {
-    "rabi_maf.cu": _COMMON + ["maf_pairs.cuh", "maf_fast.cuh", "maf_fast2.cuh", "maf_deep.cuh", "maf_warp.cuh"],
-    "maf_tc.cu": _COMMON,
-    "maf_tcd.cu": _COMMON,
-    "maf_train.cu": _COMMON,
+    "rabi_maf": ("rabi_maf.cu", [], _COMMON + ["maf_pairs.cuh", "maf_fast.cuh", "maf_fast2.cuh", "maf_deep.cuh", "maf_warp.cuh"]),
+    "maf_tc": ("maf_tc.cu", [], _COMMON),                               # host code + the DP = 4 kernels
+    "maf_tc_dp8": ("maf_tc.cu", ["-DRABI_TC_SIDE_DP=8"], _COMMON),      # the same source: only the DP = 8 kernels
+    "maf_tc_dp12": ("maf_tc.cu", ["-DRABI_TC_SIDE_DP=12"], _COMMON),
+    "maf_tcd": ("maf_tcd.cu", [], _COMMON),
+    "maf_train": ("maf_train.cu", [], _COMMON),
 }
 
 EXPORTS = [
@@ -60,13 +63,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(stamp) or open(stamp).read() != flags_now:
         force = True
     jobs, objs = [], []
-    for src, hdrs in SOURCES.items():
-        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+    for name, (src, defines, hdrs) in SOURCES.items():
+        obj = os.path.join(obj_dir, name + ".o")
         objs.append(obj)
         deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, x) for x in hdrs] + [os.path.join(INCLUDE, "rabi_b200.h")]
         if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
             continue
-        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, *defines, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

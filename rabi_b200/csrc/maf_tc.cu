@@ -1141,6 +1141,52 @@ __global__ void __launch_bounds__(TC_MAXTILES * 128, 1) k_tc(const MafImg g, con
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base_s) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------- launchers
+// The kernel instantiations of one padded dimension DP (7 modes + 2 persistent ones) are one translation unit's worth of
+// compile time: this file is compiled once per DP (rabi_b200/_lib.py: -DRABI_TC_SIDE_DP=8 / =12 build only
+// tc_launch_mode<DP>; the plain compile holds DP = 4 and all host code), and the objects build in parallel.
+template <int MODE, int DP, bool RUN>
+static int tc_launch_inst(rabi_maf* h, const TcArgs& a, int grid, int T, size_t smem, cudaStream_t st) {
+    RABI_CU_OK(h, cudaFuncSetAttribute(k_tc<MODE, DP, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = MODE == TC_GRAD || MODE == TC_FKL;   // the attack kernels are the profiled ones
+    if (prof && rabi_prof_begin(h, st)) return 1;
+    k_tc<MODE, DP, RUN><<<grid, T, smem, st>>>(h->img, a);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return rabi_fail(h, "k_tc launch failed: %s", cudaGetErrorString(e));
+    if (prof && rabi_prof_end(h, st)) return 1;
+    return 0;
+}
+
+template <int DP>
+int tc_launch_mode(rabi_maf* h, const TcArgs& a, int mode, bool run, int grid, int T, size_t smem, cudaStream_t st) {
+    if (run) {
+        if (mode == TC_GRAD) return tc_launch_inst<TC_GRAD, DP, true>(h, a, grid, T, smem, st);
+        if (mode == TC_FKL) return tc_launch_inst<TC_FKL, DP, true>(h, a, grid, T, smem, st);
+        return 2;
+    }
+    switch (mode) {
+        case TC_FWD: return tc_launch_inst<TC_FWD, DP, false>(h, a, grid, T, smem, st);
+        case TC_GRAD: return tc_launch_inst<TC_GRAD, DP, false>(h, a, grid, T, smem, st);
+        case TC_FKL: return tc_launch_inst<TC_FKL, DP, false>(h, a, grid, T, smem, st);
+        case TC_RSAMPLE: return tc_launch_inst<TC_RSAMPLE, DP, false>(h, a, grid, T, smem, st);
+        case TC_LOGPROB: return tc_launch_inst<TC_LOGPROB, DP, false>(h, a, grid, T, smem, st);
+        case TC_NLL: return tc_launch_inst<TC_NLL, DP, false>(h, a, grid, T, smem, st);
+        case TC_RSB: return tc_launch_inst<TC_RSB, DP, false>(h, a, grid, T, smem, st);
+    }
+    return 2;
+}
+
+#ifdef RABI_TC_SIDE_DP
+#ifndef RABI_LEAN
+template int tc_launch_mode<RABI_TC_SIDE_DP>(rabi_maf* h, const TcArgs& a, int mode, bool run, int grid, int T, size_t smem, cudaStream_t st);
+#endif
+#else
+#ifndef RABI_LEAN
+extern template int tc_launch_mode<8>(rabi_maf* h, const TcArgs& a, int mode, bool run, int grid, int T, size_t smem, cudaStream_t st);
+extern template int tc_launch_mode<12>(rabi_maf* h, const TcArgs& a, int mode, bool run, int grid, int T, size_t smem, cudaStream_t st);
+#endif
+
 // ------------------------------------------------------------------------------------------------- image packing
 struct TcPackMaps {
     const int* pu0;   // [K][H0] padded index of layer-0 unit u
@@ -1349,38 +1395,6 @@ static int tc_build(rabi_maf* h, TcState* s) {
     s->packed_version = ~0ull;
     s->eligible = true;
     return 0;
-}
-
-template <int MODE, int DP, bool RUN>
-static int tc_launch_inst(rabi_maf* h, const TcArgs& a, int grid, int T, size_t smem, cudaStream_t st) {
-    RABI_CU_OK(h, cudaFuncSetAttribute(k_tc<MODE, DP, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const bool prof = MODE == TC_GRAD || MODE == TC_FKL;   // the attack kernels are the profiled ones
-    if (prof && rabi_prof_begin(h, st)) return 1;
-    k_tc<MODE, DP, RUN><<<grid, T, smem, st>>>(h->img, a);
-    h->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return rabi_fail(h, "k_tc launch failed: %s", cudaGetErrorString(e));
-    if (prof && rabi_prof_end(h, st)) return 1;
-    return 0;
-}
-
-template <int DP>
-static int tc_launch_mode(rabi_maf* h, const TcArgs& a, int mode, bool run, int grid, int T, size_t smem, cudaStream_t st) {
-    if (run) {
-        if (mode == TC_GRAD) return tc_launch_inst<TC_GRAD, DP, true>(h, a, grid, T, smem, st);
-        if (mode == TC_FKL) return tc_launch_inst<TC_FKL, DP, true>(h, a, grid, T, smem, st);
-        return 2;
-    }
-    switch (mode) {
-        case TC_FWD: return tc_launch_inst<TC_FWD, DP, false>(h, a, grid, T, smem, st);
-        case TC_GRAD: return tc_launch_inst<TC_GRAD, DP, false>(h, a, grid, T, smem, st);
-        case TC_FKL: return tc_launch_inst<TC_FKL, DP, false>(h, a, grid, T, smem, st);
-        case TC_RSAMPLE: return tc_launch_inst<TC_RSAMPLE, DP, false>(h, a, grid, T, smem, st);
-        case TC_LOGPROB: return tc_launch_inst<TC_LOGPROB, DP, false>(h, a, grid, T, smem, st);
-        case TC_NLL: return tc_launch_inst<TC_NLL, DP, false>(h, a, grid, T, smem, st);
-        case TC_RSB: return tc_launch_inst<TC_RSB, DP, false>(h, a, grid, T, smem, st);
-    }
-    return 2;
 }
 
 static int tc_dispatch_dp(rabi_maf* h, TcState* s, const TcArgs& a, int mode, bool run, int grid, int T, size_t smem, cudaStream_t st) {
@@ -1668,5 +1682,7 @@ void rabi_tc_destroy(rabi_maf* h) {
     delete s;
     h->tc = nullptr;
 }
+
+#endif  // !RABI_TC_SIDE_DP
 
 }  // namespace rabi
