@@ -512,11 +512,21 @@ def measure(wname, w, args, steps, warmup, dev, world, rank, local, scaling, wit
     step_e2e()
     ms_e2e = timed(step_e2e, steps)
     # separate pass for the dominant kernel's average launch duration (CUDA events around every launch on its stream)
+    # (attacks that run as two row lanes on two streams -- rabi_b200/engine.py: pgd_run -- are profiled as ONE lane: a kernel
+    #  timed while the other lane's kernel shares the GPU would not be a launch duration)
     n_prof = min(steps, 3)
-    eng.profile(True)
-    ms_prof = timed(step_device, n_prof)
-    kern_ms, kern_n = eng.profile_read()
-    eng.profile(False)
+    lanes_env = os.environ.get("RABI_PGD_LANES")
+    os.environ["RABI_PGD_LANES"] = "1"
+    try:
+        eng.profile(True)
+        ms_prof = timed(step_device, n_prof)
+        kern_ms, kern_n = eng.profile_read()
+        eng.profile(False)
+    finally:
+        if lanes_env is None:
+            os.environ.pop("RABI_PGD_LANES", None)
+        else:
+            os.environ["RABI_PGD_LANES"] = lanes_env
 
     pairs_step = w["rows"] * pairs_per_row(w) * world * n_eps
     value = pairs_step * steps / (ms * 1e-3)
@@ -588,6 +598,9 @@ def measure(wname, w, args, steps, warmup, dev, world, rank, local, scaling, wit
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": int(loss_host.numel() * 4 + xadv_host.numel() * 4), "ms_per_step": ms_e2e / steps},
         "gpu_launches": int(launches),
+        # 2: the attack's rows ran as two halves on two streams (engine.pgd_run: fills the ragged last round of a launch per
+        # iteration); the roofline's kernel time was taken in a separate single-lane pass
+        "attack_row_lanes": int(eng._lanes(w["S_att"], w["rows"] * n_eps)),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "gpu_eager_baseline": gpu_eager,

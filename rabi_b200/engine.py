@@ -49,9 +49,17 @@ class MafEngine:
             raise ValueError(msg) if "Hidden dimension" in msg else RabiError(msg)
         self._versions = None
         self.epoch = 0   # bumped whenever a layer is re-packed: projections computed before are stale
+        self._ctor = (K, D, C, list(hidden), log_scale_min, log_scale_max)
+        self._structure = None
+        self._params = None
+        self._lane = None          # second handle + stream for attacks whose launches leave a ragged last round (pgd_run)
+        self._row_scales = None
+        self._col_mask = None
 
     def invalidate(self):
         self._versions = None
+        if self._lane is not None:
+            self._lane[0].invalidate()
 
     def __del__(self):
         try:
@@ -71,7 +79,8 @@ class MafEngine:
 
     @property
     def launches(self) -> int:
-        return int(self.L.rabi_launch_count(self.h))
+        n = int(self.L.rabi_launch_count(self.h))
+        return n + (self._lane[0].launches if self._lane is not None else 0)
 
     def profile(self, enable: bool):
         self._check(self.L.rabi_profile(self.h, int(enable)))
@@ -100,12 +109,15 @@ class MafEngine:
                 self._check(self.L.rabi_maf_set_mask(self.h, k, l, ctypes.cast(m.data_ptr(), ctypes.POINTER(ctypes.c_float)),
                                                      m.shape[0], m.shape[1]))
         self._check(self.L.rabi_maf_finalize_structure(self.h))
+        self._structure = (perms, masks, post_perms)
+        self._lane = None
         self._versions = None
         self._has_post = post_perms is not None and any(p is not None for p in post_perms)
 
     def set_weights(self, params: List[List[Tuple[torch.Tensor, torch.Tensor]]]):
         """params[k][layer] = (weight, bias) CUDA fp32 tensors; re-packs only what changed since the last call."""
         vers = [[(w.data_ptr(), w._version, b.data_ptr(), b._version) for (w, b) in pk] for pk in params]
+        self._params = params
         if self._versions == vers:
             return
         self.epoch += 1
@@ -323,6 +335,31 @@ class MafEngine:
                                                  self._stream()))
         return kl
 
+    # ---- two lanes: the three-hidden-layer path runs ONE tile of 128 pairs per SM and one launch per PGD iteration, so an
+    # attack of T tiles costs ceil(T / SMs) tile times per iteration (pyloric, 12 500 rows x 5: 489 tiles = 3.3 -> 4 rounds).
+    # Rows are independent: two halves of the rows, each on its own handle (own scratch) and stream, fill each other's ragged
+    # rounds -- iteration i + 1 of one half starts on the SMs the other half's last round leaves idle.
+    def _lanes(self, S: int, B: int) -> int:
+        import os
+        want = int(os.environ.get("RABI_PGD_LANES", "0"))   # 0: decide here
+        if want:
+            return max(1, min(2, want))
+        if len(self.hidden) != 3 or B < 8:
+            return 1
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        tiles = (S * B + 127) // 128
+        rounds = -(-tiles // sms)
+        return 2 if (rounds >= 2 and tiles <= 0.9 * rounds * sms) else 1
+
+    def _lane_engine(self):
+        if self._lane is None:
+            eng = MafEngine(*self._ctor, self.device)
+            eng.set_structure(*self._structure)
+            self._lane = (eng, torch.cuda.Stream(device=self.device))
+        eng, stream = self._lane
+        eng.set_weights(self._params)
+        return eng, stream
+
     def pgd_run(self, x, delta, zs_mean, zs_std, A_q, z_all, eps, eps_iter, clip_min, clip_max, inv_B,
                 norm_floor=1e-6, forward_kl=False):
         """z_all [nb_iter, S, B, D]; updates delta in place and returns x_adv = clamp(x + delta).
@@ -330,10 +367,47 @@ class MafEngine:
         z_all = _f32c(z_all)
         nb_iter, S, B, _ = z_all.shape
         x_adv = torch.empty_like(x)
+        if nb_iter > 0 and x.is_contiguous() and delta.is_contiguous() and self._structure is not None \
+                and self._params is not None and self._lanes(S, B) == 2:
+            other, side = self._lane_engine()
+            B1 = ((B + 1) // 2 + 3) & ~3   # (row offsets stay 16-byte aligned for any feature count)
+            main = torch.cuda.current_stream(self.device)
+            # the halves of every [.., B, ..] operand as contiguous copies, made on the calling stream before the fork
+            parts = []
+            for lo, hi in ((0, B1), (B1, B)):
+                parts.append(dict(
+                    z=z_all[:, :, lo:hi].contiguous(),
+                    A=None if A_q is None else A_q[:, :, lo:hi].contiguous(),
+                    rows=None if self._row_scales is None else tuple(t[lo:hi].contiguous() for t in self._row_scales)))
+            other.set_column_mask(self._col_mask)
+            other.set_row_scales(*(parts[1]["rows"] or (None, None)))
+            saved_rows = self._row_scales
+            if saved_rows is not None:
+                self.set_row_scales(*parts[0]["rows"])
+            side.wait_stream(main)
+            try:
+                with torch.cuda.stream(side):
+                    other._pgd_run_into(x[B1:], delta[B1:], zs_mean, zs_std, parts[1]["A"], parts[1]["z"], eps, eps_iter, clip_min,
+                                        clip_max, inv_B, norm_floor, forward_kl, x_adv[B1:])
+                self._pgd_run_into(x[:B1], delta[:B1], zs_mean, zs_std, parts[0]["A"], parts[0]["z"], eps, eps_iter, clip_min,
+                                   clip_max, inv_B, norm_floor, forward_kl, x_adv[:B1])
+            finally:
+                main.wait_stream(side)
+                other.set_row_scales()
+                other.set_column_mask()
+                if saved_rows is not None:
+                    self.set_row_scales(*saved_rows)
+            return x_adv
+        self._pgd_run_into(x, delta, zs_mean, zs_std, A_q, z_all, eps, eps_iter, clip_min, clip_max, inv_B, norm_floor,
+                           forward_kl, x_adv)
+        return x_adv
+
+    def _pgd_run_into(self, x, delta, zs_mean, zs_std, A_q, z_all, eps, eps_iter, clip_min, clip_max, inv_B, norm_floor,
+                      forward_kl, x_adv):
+        nb_iter, S, B, _ = z_all.shape
         with torch.cuda.device(self.device):
             fn = self.L.rabi_fkl_pgd_run if forward_kl else self.L.rabi_rkl_pgd_run
             self._check(fn(self.h, _ptr(x), _ptr(delta), _ptr(zs_mean), _ptr(zs_std), _ptr(A_q),
                                                 _ptr(z_all), nb_iter, S, B, float(eps), float(eps_iter), float(clip_min),
                                                 float(clip_max), float(inv_B), float(norm_floor), _ptr(x_adv),
                                                 self._stream()))
-        return x_adv

@@ -702,6 +702,54 @@ def test_batched_eps_sweep_equals_one_attack_per_eps(shape, dev):
     assert all(torch.isfinite(torch.tensor(v))) and v[0] < v[1] < v[2], v
 
 
+def test_two_row_lanes_equal_one_launch_group(dev):
+    """MafEngine.pgd_run splits the rows of an attack on the three-hidden-layer path into two halves on two handles and
+    streams when a launch per iteration would end in a ragged round of tiles (rows are independent).  Same x_adv / delta as
+    the single-lane run, with a scalar radius, with per-row radii (eps-sweep) and with a column mask; the second lane's
+    launches are counted."""
+    import os
+
+    from rabi_b200 import noise
+    from rabi_b200.attacks import L2PGDAttack
+    from rabi_b200.loss import ReverseKLLoss
+
+    sh = dict(SHAPES["pyloric"], B=4003)
+    ref, model, x = _fresh(sh, dev, seed=41)
+    xd = x.to(dev)
+    B, D, S, n_it = sh["B"], sh["D"], 5, 3
+    eng = model.engine()
+    assert eng._lanes(S, B) == 2 and eng._lanes(S, 64) == 1
+    std = float(x.std(1).mean())
+    cmin, cmax = float(x.min()), float(x.max())
+    g = torch.Generator().manual_seed(12)
+    z = [torch.randn(S, B, D, generator=g) for _ in range(n_it)]
+    d0 = 0.02 * torch.randn(B, sh["dx"], generator=g)
+    mask = torch.ones(sh["dx"], dtype=torch.bool)
+    mask[::3] = False
+    eps_rows = (0.2 + 0.8 * torch.rand(B, generator=g)) * std
+    cases = {"scalar": dict(eps=0.5 * std, eps_iter=0.1 * std, kw={}),
+             "per-row radii": dict(eps=eps_rows.to(dev), eps_iter=(eps_rows / 4).to(dev), kw={}),
+             "column mask": dict(eps=0.5 * std, eps_iter=0.1 * std, kw={"feature_mask": mask})}
+    for name, c in cases.items():
+        outs, launches = [], []
+        for lanes in ("1", "2"):
+            os.environ["RABI_PGD_LANES"] = lanes
+            try:
+                atk = L2PGDAttack(model, loss_fn=ReverseKLLoss(mc_samples=S), eps=c["eps"], nb_iter=n_it, eps_iter=c["eps_iter"],
+                                  clip_min=cmin, clip_max=cmax)
+                n0 = eng.launches
+                with noise.injected(list(z)):
+                    outs.append(atk.perturb(xd, delta_init=d0.to(dev), **c["kw"]).cpu())
+                launches.append(eng.launches - n0)
+            finally:
+                os.environ.pop("RABI_PGD_LANES", None)
+        err = assert_trajectories_match(outs[1] - x, outs[0] - x, RTOL, max_flip_frac=0.02)
+        assert launches[1] > launches[0], launches      # both lanes launch their own groups
+        if name == "column mask":
+            assert torch.equal(outs[1][:, ~mask], x[:, ~mask])
+        print(f"\n[two row lanes, {name}] max row rel. err vs one lane {float(err.max()):.2e}; launches {launches}")
+
+
 @pytest.mark.parametrize("kernel", ["k_warp", "k_fast2", "k_fast", "k_tc"])
 def test_every_attack_gradient_kernel_against_the_oracle_at_its_own_launch_size(kernel, dev):
     """d[1/B sum_b KL(q(.|x~_b) || q(.|x_b))]/dx~ from each kernel family, at a launch size the dispatcher gives to THAT family,
