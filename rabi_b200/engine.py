@@ -344,7 +344,7 @@ class MafEngine:
         want = int(os.environ.get("RABI_PGD_LANES", "0"))   # 0: decide here
         if want:
             return max(1, min(2, want))
-        if len(self.hidden) != 3 or B < 8:
+        if len(self.hidden) != 3 or B < 8 or torch.cuda.is_current_stream_capturing():
             return 1
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         tiles = (S * B + 127) // 128
