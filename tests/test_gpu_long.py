@@ -120,10 +120,23 @@ def test_free_running_trajectory_divergence_per_checkpoint(long_case, dev):
     ref = g["rkl_eval"]
     rel_mean = abs(float(kl.mean()) - float(ref.mean())) / abs(float(ref.mean()))
     row_dev = ((kl - ref).abs() / ref.abs().clamp_min(1e-3))
+    # rows whose final perturbation still equals the reference's, and rows that left it after a ReLU flip (a different, equally
+    # valid trajectory inside the same ball; WHICH rows flip depends on the order of the fp32 reductions over the samples)
+    agree = err <= TRAJ_TOL
+    rel_agree = abs(float(kl[agree].mean()) - float(ref[agree].mean())) / abs(float(ref[agree].mean()))
+    ratio = (kl[~agree] / ref[~agree]) if bool((~agree).any()) else torch.ones(1)
     print(f"  final rKL (S=256): mean {float(kl.mean()):.6f} vs reference {float(ref.mean()):.6f} (rel {rel_mean:.2e}); "
-          f"per-row rel. deviation median {float(row_dev.median()):.2e}, p90 {float(row_dev.quantile(0.9)):.2e}")
+          f"per-row rel. deviation median {float(row_dev.median()):.2e}, p90 {float(row_dev.quantile(0.9)):.2e}; "
+          f"rows on the reference's trajectory {int(agree.sum())}/{keep}: mean rel {rel_agree:.2e}; departed rows: rKL ratio to the "
+          f"reference's in [{float(ratio.min()):.2f}, {float(ratio.max()):.2f}]")
     assert float((xa - xd).norm(dim=-1).max()) <= g["pgd"]["eps"] * (1 + 1e-5)
     # the first steps must agree everywhere except at proven near-kink rows (covered by the single-step test): typical error tiny
     assert rows[0][1] < 1e-6 and rows[0][4] <= 0.01, rows[0]
     assert all(r[1] < TRAJ_TOL for r in rows), "median row must stay within 1e-4 over the whole trajectory"
-    assert rel_mean < 2e-3
+    # attack result: rows on the reference's trajectory reproduce its S = 256 divergence (1e-3 of the mean: the estimate of a
+    # divergence of O(1e-3) carries an fp32 rounding floor of a few 1e-4 per row; measured 2.5e-4 pyloric, 2e-6 lotka_volterra).
+    # A departed row ends in another local maximum of its own (printed above: a single row's divergence may differ by a factor),
+    # so the claim for them is about the metric the reference reports -- the mean over the rows -- which agrees to 1 %
+    # (observed over repeated runs: 2e-4 .. 2e-3, depending on WHICH rows flipped; the former 2e-3 bound was a coin toss).
+    assert rel_agree < 1e-3, rel_agree
+    assert rel_mean < 1e-2, rel_mean
